@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — grid voxels/s of the polar-volume -> Cartesian gridding hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2|c5] [--style stress|storm]
+    python bench.py --impl reference ...      # the reference's own Cython path on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic input: a full single-radar
+3-D gridding (BASELINE config C3: 9x360x1840 VCP21-like volume -> 1201x1201x40 lon/lat grid at
+250 m).  `value` is timed with CUDA events around the kernel with every input resident in HBM;
+`e2e` is the same metric through the reference-facing API (pycwr_b200.RadarGridC.get_CAPPI_3d)
+with HOST buffers — volume upload, grid H2D, kernel, D2H — inside the timed region.
+With N > 1 (torchrun, one rank per GPU) every rank grids its own radar volume (radars are
+independent objects: weak scaling, no data-path collective); `value` is the aggregate.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FILL = -999.0
+METRIC = "grid voxels/sec"
+UNIT = "voxels/s"
+WORKLOADS = {"c1": 1, "c2": 2, "c3": 3, "c5": 5}
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(cfg, nfield):
+    """every input read once, every output written once, reference dtypes."""
+    vol = cfg["volume"]
+    ncol = cfg["GridX"].size
+    nval = sum(a.size for a in vol["vol_value"][cfg["fields"][0]])
+    ntab = sum(a.size for a in vol["vol_azimuth"]) + sum(a.size for a in vol["vol_range"])
+    ne = vol["fix_elevation"].size
+    if cfg["kind"] == "cr":
+        return 8 * ncol + 16 * ncol + 8 * nval + 8 * ntab + 8 * ne
+    nz = cfg["levels"].size
+    return 8 * nfield * nz * ncol + 16 * ncol + 8 * nfield * nval + 8 * ntab + 8 * (ne + nz)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own Cython kernels (oracle/_ref) when they were
+# built, else the C restatement (oracle/grid_oracle.c) — the only place bench.py executes oracle/
+# --------------------------------------------------------------------------------------------
+
+def _cpu_impl():
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is not None:
+        return ref, "reference"
+    from oracle import oracle as port
+    return port, "port"
+
+
+def _cpu_chunk(args):
+    mod_kind, vol, h, gx, gy, levels, blind = args
+    mod, _ = _cpu_impl()
+    va, vr, fe, vv = vol
+    t0 = time.perf_counter()
+    out = mod.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, levels, FILL, None, blind)
+    return out.size, time.perf_counter() - t0
+
+
+def cpu_sample(cfg, nlevels, workers):
+    """Time the CPU implementation on a bounded sample: the first `nlevels` levels per worker of
+    the full grid.  Returns (voxels/s, kind, cores, description)."""
+    from pycwr_b200 import synth
+    mod, kind = _cpu_impl()
+    va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"], cfg["fields"][0])
+    gx, gy = cfg["GridX"], cfg["GridY"]
+    levels = cfg["levels"] if cfg["levels"] is not None else np.array([1500.0])
+    blind = cfg["blind_method"]
+    if workers <= 1:
+        lv = np.ascontiguousarray(levels[:nlevels])
+        n, dt = _cpu_chunk((kind, (va, vr, fe, vv), h, gx, gy, lv, blind))
+        return n / dt, kind, 1, "%s x %d of %d levels, %dx%d grid" % (cfg["name"], lv.size, levels.size, gx.shape[0], gx.shape[1])
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")     # the reference's own strategy (RadarInterp.py:1816-1824)
+    chunks = []
+    for w in range(workers):
+        lv = np.ascontiguousarray(levels[(w * nlevels) % levels.size:][:nlevels])
+        if lv.size == 0:
+            lv = np.ascontiguousarray(levels[:nlevels])
+        chunks.append((kind, (va, vr, fe, vv), h, gx, gy, lv, blind))
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_chunk, chunks)
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    return total / wall, kind, workers, "%s: %d workers x %d levels, %dx%d grid" % (
+        cfg["name"], workers, nlevels, gx.shape[0], gx.shape[1])
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from pycwr_b200 import synth
+    cfg = synth.config(WORKLOADS[args.workload], style=args.style)
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    vals = []
+    for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
+        cpu_sample(cfg, 1, workers)
+    t_all = time.perf_counter()
+    desc = kind = None
+    for _ in range(args.steps):
+        v, kind, used, desc = cpu_sample(cfg, args.ref_levels, workers)
+        vals.append(v)
+    wall = time.perf_counter() - t_all
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": cfg["name"], "style": args.style},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# product arm
+# --------------------------------------------------------------------------------------------
+
+def run_product(args):
+    import ctypes
+
+    import torch
+
+    from pycwr_b200 import RadarGridC as G
+    from pycwr_b200 import _lib, synth
+    from pycwr_b200.runtime import DeviceVolume, pinned_copy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or _lib.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    _lib.check(_lib.load().pcg_set_device(local))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    cid = WORKLOADS[args.workload]
+    cfg = synth.config(cid, style=args.style)
+    if world > 1:   # every rank grids its own radar (independent volume, same shapes)
+        cfg["volume"] = synth.make_volume(synth.BASE_SEED + cid + 1000 * rank,
+                                          naz=cfg["volume"]["vol_azimuth"][0].size,
+                                          ngate=cfg["volume"]["vol_range"][0].size,
+                                          gate_m=float(cfg["volume"]["vol_range"][0][0]),
+                                          elevations=cfg["volume"]["fix_elevation"],
+                                          fields=tuple(cfg["fields"]), style=args.style)
+    vol = cfg["volume"]
+    fields = cfg["fields"]
+    nfield = len(fields)
+    gx_h, gy_h = cfg["GridX"], cfg["GridY"]
+    nx, ny = gx_h.shape
+    levels = cfg["levels"]
+    is_cr = cfg["kind"] == "cr"
+    nz = 1 if is_cr else int(levels.size)
+    blind = {"mask": 0, "hybrid": 3}[cfg["blind_method"]]
+    h = vol["radar_height"]
+    Re = G.DEFAULT_EFFECTIVE_EARTH_RADIUS
+    dv = DeviceVolume(vol["vol_azimuth"], vol["vol_range"], vol["fix_elevation"],
+                      [vol["vol_value"][f] for f in fields] if nfield > 1 else vol["vol_value"][fields[0]],
+                      value_dtype=args.value_dtype)
+    gx = torch.from_numpy(gx_h).to(dev)
+    gy = torch.from_numpy(gy_h).to(dev)
+    out = torch.empty((nfield, nz, nx, ny) if not is_cr else (nx, ny), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    lib = _lib.load()
+    lv_p = levels.ctypes.data_as(_lib.c_double_p) if not is_cr else None
+
+    def launch():
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if is_cr:
+            _lib.check(lib.pcg_get_cr_dev(dv.handle, h, Re, gx.data_ptr(), gy.data_ptr(), nx, ny, FILL,
+                                          0.0, 0.0, out.data_ptr(), st))
+        else:
+            _lib.check(lib.pcg_get_cappi3d_dev(dv.handle, h, Re, gx.data_ptr(), gy.data_ptr(), nx, ny, lv_p,
+                                               nz, FILL, blind, 1.0, 0.0, 0.0, 0, out.data_ptr(), None, st))
+
+    voxels = nfield * nz * nx * ny
+    for _ in range(max(args.warmup, 3)):
+        launch()
+        flush.zero_()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                      # L2 flush between timed iterations (not timed)
+        starts[i].record()
+        launch()
+        ends[i].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t_wall
+    if dist is not None:
+        dist.barrier()
+    launches = _lib.launch_count() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    dev_ms = float(sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * voxels * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e through the public API with host buffers (pinned), every copy inside the timing
+    USEP = True
+    va_p = [pinned_copy(a) for a in vol["vol_azimuth"]] if USEP else vol["vol_azimuth"]
+    vr_p = [pinned_copy(a) for a in vol["vol_range"]]
+    vv_p = [[pinned_copy(a) for a in vol["vol_value"][f]] for f in fields]
+    gx_p, gy_p = pinned_copy(gx_h), pinned_copy(gy_h)
+    fe = vol["fix_elevation"]
+
+    def e2e_once():
+        if is_cr:
+            return G.get_CR_xy(va_p, vr_p, fe, vv_p[0], h, gx_p, gy_p, FILL)
+        if nfield == 1:
+            return G.get_CAPPI_3d(va_p, vr_p, fe, vv_p[0], h, gx_p, gy_p, levels, FILL, None, cfg["blind_method"])
+        dvol = DeviceVolume(va_p, vr_p, fe, vv_p, value_dtype=args.value_dtype)
+        try:
+            return G.get_CAPPI_3d(None, None, None, dvol, h, gx_p, gy_p, levels, FILL, None, cfg["blind_method"])
+        finally:
+            dvol.close()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        res = e2e_once()
+        del res
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for _ in range(e2e_steps):
+        res = e2e_once()
+        checksum += float(res.reshape(-1)[0])
+        del res
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * voxels * e2e_steps / e2e_s
+    h2d = 8 * nfield * dv.nvalues + dv.table_bytes + 16 * nx * ny
+    d2h = 8 * voxels
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = read_peaks()
+    balg = algorithmic_bytes(cfg, nfield)
+    kern_ms = float(np.mean(step_ms))
+    achieved = balg / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(cfg["name"])
+        except Exception:
+            traffic = None
+    cpu = None
+    if not args.no_cpu:
+        v, kind, cores, desc = cpu_sample(cfg, args.cpu_levels, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["name"], "style": args.style, "grid": [nz, nx, ny], "fields": fields,
+                   "value_storage": args.value_dtype, "blind_method": cfg["blind_method"],
+                   "l2": "256 MB flush write between timed steps (excluded from step time)",
+                   "parallelism": "1 radar volume per GPU, no collective" if world > 1 else "single GPU",
+                   "wall_s_timed_region": wall},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "api": "pycwr_b200.RadarGridC.%s (host buffers in, host array out)"
+                % ("get_CR_xy" if is_cr else "get_CAPPI_3d")},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": int(balg),
+                     "kernel": "pcg::cr_kernel" if is_cr else "pcg::cappi3d_kernel", "kernel_ms": kern_ms},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--style", default="stress", choices=["stress", "storm"])
+    ap.add_argument("--value-dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--cpu-levels", type=int, default=6, help="levels of the full grid timed on 1 host core")
+    ap.add_argument("--ref-levels", type=int, default=2, help="levels per worker for --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_product(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,129 @@
+/*
+ * pycwr_b200.h — C ABI of the B200-native polar-volume -> Cartesian gridding path.
+ *
+ * This library replaces the compiled module `pycwr.core.RadarGridC` of the reference
+ * (YvZheng/pycwr, `pycwr/core/RadarGridC.pyx`) behind the import seam at
+ * `pycwr/core/__init__.py:10-54`, `pycwr/core/NRadar.py:17-20` and
+ * `pycwr/interp/RadarInterp.py:39-42,1050-1056`.  The Python module
+ * `pycwr_b200/RadarGridC.py` binds these entry points with ctypes and exports the reference's
+ * eleven names with unchanged signatures (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / numpy types.
+ *  - every function returns 0 on success or a negative pcg_status; pcg_last_error() gives the
+ *    message of the calling thread's last failure.  There is NO CPU fallback: when no CUDA
+ *    device is usable every compute entry point fails with PCG_ERR_CUDA.
+ *  - `*_dev` entry points take DEVICE pointers and a cudaStream_t (passed as void*) and only
+ *    enqueue work; the others take HOST pointers, copy in, launch, copy out and synchronise.
+ *  - grids are row-major (nx, ny) float64 in metres, exactly what the reference passes as
+ *    GridX/GridY; outputs are row-major float64 with `fill` marking "no data".
+ *  - blind_code: 0 mask, 1 nearest_gate, 2 lowest_sweep, 3 hybrid, 4 nearest_valid
+ *    (`RadarGridC.pyx:54-69`).
+ */
+#ifndef PYCWR_B200_H
+#define PYCWR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PCG_OK = 0,
+    PCG_ERR_ARG = -1,      /* bad argument (maps to the reference's ValueError)      */
+    PCG_ERR_CUDA = -2,     /* CUDA runtime failure / no device                       */
+    PCG_ERR_NOMEM = -3     /* host or device allocation failure                      */
+} pcg_status;
+
+/* index-record layout written by the *_index entry points (int32 x PCG_IDX_STRIDE per voxel):
+ * [0] state (0 skip_beam 1 skip_low 2 skip_high 3 single 4 pair 5 empty volume)
+ * [1] lower sweep [2] upper sweep, [3..5] iaz, ir, flags of the lower-sweep sample,
+ * [6..8] the same for the upper-sweep sample, [9] reserved (-1).
+ * flags: 1 azimuth wrapped, 2 range clamped to first gate, 4 beyond last gate, 8 before first
+ * gate, 16 degenerate sweep (naz<2 or ngate<2). */
+#define PCG_IDX_STRIDE 10
+
+/* value storage of a packed volume on the device */
+#define PCG_VALUE_F64 0   /* moments kept as float64: interpolation bit-compatible with the reference */
+#define PCG_VALUE_F32 1   /* moments rounded to float32 on upload: half the gather traffic          */
+
+typedef struct pcg_volume pcg_volume;   /* opaque: one radar volume resident in HBM */
+
+/* ---- runtime ---------------------------------------------------------------------------- */
+const char *pcg_last_error(void);
+const char *pcg_version(void);
+int pcg_device_count(int *count);
+int pcg_set_device(int device);
+/* pinned host memory for staging buffers (what the Python shim hands back as numpy arrays) */
+int pcg_host_alloc(size_t bytes, void **ptr);
+int pcg_host_free(void *ptr);
+/* kernels launched by this library since load (the bench's `gpu_launches` claim) */
+int64_t pcg_launch_count(void);
+
+/* ---- volume packing: replaces the list-of-arrays argument convention of the reference
+ *      (`vol_azimuth, vol_range, fix_elevation, vol_value`, produced by PRD.get_vol_data,
+ *      `pycwr/core/NRadar.py:1931-1961`).  Inputs are borrowed host arrays: az[s] has naz[s]
+ *      sorted float64 azimuths, rng[s] ng[s] ascending ranges, val[f][s] naz[s]*ng[s] row-major
+ *      (radial, gate) float64 moments with missing == the caller's fill value.  nfield >= 1
+ *      moments share the azimuth/range tables (one set of indices serves all of them). */
+int pcg_volume_create(int ne, const int *naz, const int *ng, const double *const *az,
+                      const double *const *rng, int nfield, const double *const *const *val,
+                      const double *fix_elev, int value_dtype, pcg_volume **out);
+int pcg_volume_destroy(pcg_volume *vol);
+int pcg_volume_info(const pcg_volume *vol, int *ne, int *nfield, int *value_dtype,
+                    size_t *device_bytes);
+
+/* ---- host-buffer entry points (drop-in for the reference functions) ------------------- */
+
+/* get_CAPPI_3d (`RadarGridC.pyx:485-521`) / get_CAPPI_xy (`:356-477`, nz == 1 with its
+ * beam_width_deg; get_CAPPI_3d callers pass 1.0 because the reference does not forward it).
+ * out: [nfield][nz][nx*ny].  index_out (optional, may be NULL): [nz][nx*ny][PCG_IDX_STRIDE]. */
+int pcg_get_cappi3d(const pcg_volume *vol, double radar_height, double effective_earth_radius,
+                    const double *grid_x, const double *grid_y, int nx, int ny,
+                    const double *level_heights, int nz, double fill, int blind_code,
+                    double beam_width_deg, double *out, int32_t *index_out);
+
+/* get_CR_xy (`RadarGridC.pyx:596-624`): max over sweeps of ppi_to_grid planes at the fixed
+ * elevations, blind "mask".  Uses field 0.  out: [nx*ny]. */
+int pcg_get_cr(const pcg_volume *vol, double radar_height, double effective_earth_radius,
+               const double *grid_x, const double *grid_y, int nx, int ny, double fill,
+               double *out);
+
+/* ppi_to_grid (`RadarGridC.pyx:303-352`): sweep `sweep` of the packed volume gridded at
+ * elevation `elevation_deg`.  out: [nx*ny]; index_out optional [nx*ny][PCG_IDX_STRIDE]. */
+int pcg_ppi_to_grid(const pcg_volume *vol, int sweep, double elevation_deg, double radar_height,
+                    double effective_earth_radius, const double *grid_x, const double *grid_y,
+                    int nx, int ny, double fill, int blind_code, double *out, int32_t *index_out);
+
+/* get_mosaic_CAPPI_3d (`RadarGridC.pyx:525-593`): per radar local grid = grid - (x, y),
+ * get_CAPPI_3d with blind "mask", fill-aware running max in radar order.  out: [nz][nx*ny]. */
+int pcg_get_mosaic_cappi3d(int nradar, const pcg_volume *const *vols, const double *radar_x,
+                           const double *radar_y, const double *radar_height,
+                           const double *effective_earth_radius, const double *grid_x,
+                           const double *grid_y, int nx, int ny, const double *level_heights,
+                           int nz, double fill, double *out);
+
+/* ---- device-resident entry points (what bench.py times with inputs already in HBM) ---- */
+int pcg_get_cappi3d_dev(const pcg_volume *vol, double radar_height, double effective_earth_radius,
+                        const double *d_grid_x, const double *d_grid_y, int nx, int ny,
+                        const double *level_heights /* host */, int nz, double fill,
+                        int blind_code, double beam_width_deg, double radar_x, double radar_y,
+                        int merge_max, double *d_out, int32_t *d_index_out, void *stream);
+int pcg_get_cr_dev(const pcg_volume *vol, double radar_height, double effective_earth_radius,
+                   const double *d_grid_x, const double *d_grid_y, int nx, int ny, double fill,
+                   double radar_x, double radar_y, double *d_out, void *stream);
+
+/* ---- diagnostics: the device's geometry inversion for a list of points (one level), used by
+ *      the tests to measure bit-agreement of the device math with glibc. ------------------- */
+int pcg_debug_cartesian_to_antenna(const double *x, const double *y, size_t n, double z, double h,
+                                   double effective_earth_radius, double *az, double *r,
+                                   double *el);
+int pcg_debug_xye_to_antenna(const double *x, const double *y, size_t n, double elevation_deg,
+                             double h, double effective_earth_radius, double *az, double *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYCWR_B200_H */

@@ -1,0 +1,627 @@
+// pcg_capi.cu — C ABI (include/pycwr_b200.h) over the sm_100a gridding kernels.
+//
+// Host-side responsibilities: pack the reference's list-of-arrays volume into device arenas
+// (the role of PRD.get_vol_data's output, pycwr/core/NRadar.py:1931-1961), evaluate the few
+// per-level / per-sweep constants that need glibc or plain IEEE arithmetic, stage host buffers
+// and launch.  There is no CPU compute path: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/pycwr_b200.h"
+#include "pcg_kernels.cuh"
+
+using namespace pcg;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+std::mutex g_mutex;   // guards the scratch arena and the library stream
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(PCG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+// grow-only device scratch buffers for the host-buffer entry points
+struct Scratch {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int device = -1;
+    int ensure(size_t bytes) {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (ptr && (cap < bytes || device != dev)) {
+            cudaFree(ptr);
+            ptr = nullptr;
+            cap = 0;
+        }
+        if (!ptr) {
+            size_t want = bytes < 256 ? 256 : bytes;
+            cudaError_t e = cudaMalloc(&ptr, want);
+            if (e != cudaSuccess) {
+                ptr = nullptr;
+                return fail(PCG_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            }
+            cap = want;
+            device = dev;
+        }
+        return PCG_OK;
+    }
+};
+
+enum { S_GX = 0, S_GY, S_OUT, S_IDX, S_TMP0, S_TMP1, S_TMP2, S_COUNT };
+Scratch g_scratch[S_COUNT];
+cudaStream_t g_stream[16] = {};
+
+int lib_stream(cudaStream_t* out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return fail(PCG_ERR_ARG, "device index %d out of range", dev);
+    if (!g_stream[dev]) CUDA_TRY(cudaStreamCreateWithFlags(&g_stream[dev], cudaStreamNonBlocking));
+    *out = g_stream[dev];
+    return PCG_OK;
+}
+
+double resolve_re(double re) { return re; }
+
+}  // namespace
+
+struct pcg_volume {
+    int ne = 0;
+    int nfield = 0;
+    int dtype = PCG_VALUE_F64;
+    int device = 0;
+    double* d_az = nullptr;
+    double* d_rng = nullptr;
+    void* d_val[kMaxFields] = {nullptr, nullptr, nullptr, nullptr};
+    SweepDesc* d_sweeps = nullptr;
+    std::vector<SweepDesc> sweeps;
+    size_t bytes = 0;
+};
+
+namespace {
+
+VolumeView view_of(const pcg_volume* v) {
+    VolumeView w;
+    w.az = v->d_az;
+    w.rng = v->d_rng;
+    for (int f = 0; f < kMaxFields; ++f) w.val[f] = v->d_val[f];
+    w.sweeps = v->d_sweeps;
+    w.ne = v->ne;
+    w.nfield = v->nfield;
+    return w;
+}
+
+int check_volume(const pcg_volume* v) {
+    if (!v) return fail(PCG_ERR_ARG, "volume handle is NULL");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != v->device)
+        return fail(PCG_ERR_ARG, "volume lives on device %d but the current device is %d", v->device, dev);
+    return PCG_OK;
+}
+
+int check_common(double re, int nx, int ny) {
+    if (!(re > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
+    if (nx < 0 || ny < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
+    return PCG_OK;
+}
+
+void fill_level(LevelConst* lc, double z, double Re, double a2, double twoa) {
+    // RadarGridC.pyx:145-146: gate_radius = Re + z; a*a + g*g - 2.0*a*g*cos(phi)
+    volatile double g = Re + z;
+    volatile double g2 = g * g;
+    volatile double a2g2 = a2 + g2;
+    volatile double twoag = twoa * g;
+    lc->z = z;
+    lc->g2 = g2;
+    lc->a2g2 = a2g2;
+    lc->twoag = twoag;
+}
+
+template <typename VT, bool EMIT>
+int launch_cappi_nf(const CappiArgs& args, int nf, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    switch (nf) {
+        case 1: cappi3d_kernel<VT, 1, EMIT><<<grid, block, smem, st>>>(args); break;
+        case 2: cappi3d_kernel<VT, 2, EMIT><<<grid, block, smem, st>>>(args); break;
+        case 3: cappi3d_kernel<VT, 3, EMIT><<<grid, block, smem, st>>>(args); break;
+        case 4: cappi3d_kernel<VT, 4, EMIT><<<grid, block, smem, st>>>(args); break;
+        default: return fail(PCG_ERR_ARG, "nfield must be 1..%d", kMaxFields);
+    }
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return PCG_OK;
+}
+
+int enqueue_cappi(const pcg_volume* vol, double h, double Re, const double* d_gx, const double* d_gy,
+                  long long ncol, const double* levels, int nz, double fill, int blind_code,
+                  double beam_width_deg, double radar_x, double radar_y, int shift, int merge_max,
+                  double* d_out, int32_t* d_idx, cudaStream_t st, int nfield_override = 0) {
+    const int nfield = nfield_override > 0 ? nfield_override : vol->nfield;
+    if (blind_code < 0 || blind_code > 4)
+        return fail(PCG_ERR_ARG,
+                    "blind_method must be one of 'mask', 'nearest_gate', 'lowest_sweep', 'hybrid', or "
+                    "'nearest_valid'.");
+    if (nz < 0) return fail(PCG_ERR_ARG, "nz must be non-negative");
+    if (ncol == 0 || nz == 0) return PCG_OK;
+    if (vol->ne > kMaxSweeps) return fail(PCG_ERR_ARG, "at most %d sweeps are supported", kMaxSweeps);
+    CappiArgs a;
+    memset(&a, 0, sizeof(a));
+    a.vol = view_of(vol);
+    a.grid.gx = d_gx;
+    a.grid.gy = d_gy;
+    a.grid.ncol = ncol;
+    a.grid.radar_x = radar_x;
+    a.grid.radar_y = radar_y;
+    a.grid.shift = shift;
+    volatile double av = Re + h;           // RadarGridC.pyx:144
+    volatile double a2 = av * av;
+    volatile double twoa = 2.0 * av;
+    a.a = av; a.a2 = a2; a.twoa = twoa; a.Re = Re; a.fill = fill;
+    if (beam_width_deg <= 0.0) beam_width_deg = 1.0;     // RadarGridC.pyx:400-404
+    double beam_half = beam_width_deg * 0.5;
+    if (beam_half < 0.1) beam_half = 0.1;
+    a.beam_half = beam_half;
+    a.nearest_gate = (blind_code == 1 || blind_code == 3 || blind_code == 4);
+    a.lowest_sweep = (blind_code == 2 || blind_code == 3 || blind_code == 4);
+    a.highest_sweep = (blind_code == 4);
+    a.merge_max = merge_max;
+    a.field_stride = (unsigned long long)nz * (unsigned long long)ncol;
+    const size_t smem = (size_t)(vol->ne > 0 ? vol->ne : 1) * sizeof(SweepDesc);
+    const dim3 block(256);
+    const dim3 grid((unsigned)((ncol + 255) / 256));
+    for (int z0 = 0; z0 < nz; z0 += kMaxLevelsPerLaunch) {
+        const int cnt = (nz - z0 < kMaxLevelsPerLaunch) ? nz - z0 : kMaxLevelsPerLaunch;
+        a.nz = cnt;
+        for (int k = 0; k < cnt; ++k) fill_level(&a.levels[k], levels[z0 + k], Re, a2, twoa);
+        a.out = d_out + (size_t)z0 * (size_t)ncol;
+        a.idx = d_idx ? d_idx + (size_t)z0 * (size_t)ncol * kIdxStride : nullptr;
+        int rc;
+        if (vol->dtype == PCG_VALUE_F32)
+            rc = d_idx ? launch_cappi_nf<float, true>(a, nfield, grid, block, smem, st)
+                       : launch_cappi_nf<float, false>(a, nfield, grid, block, smem, st);
+        else
+            rc = d_idx ? launch_cappi_nf<double, true>(a, nfield, grid, block, smem, st)
+                       : launch_cappi_nf<double, false>(a, nfield, grid, block, smem, st);
+        if (rc != PCG_OK) return rc;
+    }
+    return PCG_OK;
+}
+
+int enqueue_cr(const pcg_volume* vol, double h, double Re, const double* d_gx, const double* d_gy,
+               long long ncol, double fill, int single_sweep, double elevation_deg, int blind_code,
+               double radar_x, double radar_y, int shift, double* d_out, int32_t* d_idx,
+               cudaStream_t st) {
+    if (ncol == 0) return PCG_OK;
+    if (vol->ne > kMaxSweeps) return fail(PCG_ERR_ARG, "at most %d sweeps are supported", kMaxSweeps);
+    CrArgs a;
+    memset(&a, 0, sizeof(a));
+    a.vol = view_of(vol);
+    a.grid.gx = d_gx;
+    a.grid.gy = d_gy;
+    a.grid.ncol = ncol;
+    a.grid.radar_x = radar_x;
+    a.grid.radar_y = radar_y;
+    a.grid.shift = shift;
+    volatile double av = Re + h;
+    volatile double a2 = av * av;
+    volatile double twoa = 2.0 * av;
+    a.a = av; a.a2 = a2; a.twoa = twoa; a.Re = Re; a.fill = fill;
+    a.single_sweep = single_sweep;
+    a.tan_override = tan(elevation_deg * kDeg2Rad);   // RadarGridC.pyx:110,113
+    a.nearest_gate = (blind_code == 1 || blind_code == 3 || blind_code == 4);
+    a.out = d_out;
+    a.idx = d_idx;
+    const size_t smem = (size_t)(vol->ne > 0 ? vol->ne : 1) * sizeof(SweepDesc);
+    const dim3 block(256);
+    const dim3 grid((unsigned)((ncol + 255) / 256));
+    if (vol->dtype == PCG_VALUE_F32) {
+        if (d_idx) cr_kernel<float, true><<<grid, block, smem, st>>>(a);
+        else cr_kernel<float, false><<<grid, block, smem, st>>>(a);
+    } else {
+        if (d_idx) cr_kernel<double, true><<<grid, block, smem, st>>>(a);
+        else cr_kernel<double, false><<<grid, block, smem, st>>>(a);
+    }
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return PCG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pcg_last_error(void) { return g_err; }
+
+const char* pcg_version(void) { return "pycwr_b200 0.1 (sm_100a)"; }
+
+int pcg_device_count(int* count) {
+    if (!count) return fail(PCG_ERR_ARG, "count is NULL");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return PCG_OK;
+}
+
+int pcg_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return PCG_OK;
+}
+
+int pcg_host_alloc(size_t bytes, void** ptr) {
+    if (!ptr) return fail(PCG_ERR_ARG, "ptr is NULL");
+    *ptr = nullptr;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(PCG_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return PCG_OK;
+}
+
+int pcg_host_free(void* ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return PCG_OK;
+}
+
+int64_t pcg_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const* az,
+                      const double* const* rng, int nfield, const double* const* const* val,
+                      const double* fix_elev, int value_dtype, pcg_volume** out) {
+    if (!out) return fail(PCG_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (ne < 0 || ne > kMaxSweeps) return fail(PCG_ERR_ARG, "ne must be in [0, %d]", kMaxSweeps);
+    if (nfield < 1 || nfield > kMaxFields) return fail(PCG_ERR_ARG, "nfield must be in [1, %d]", kMaxFields);
+    if (value_dtype != PCG_VALUE_F64 && value_dtype != PCG_VALUE_F32)
+        return fail(PCG_ERR_ARG, "value_dtype must be PCG_VALUE_F64 or PCG_VALUE_F32");
+    if (ne > 0 && (!naz || !ng || !az || !rng || !val || !fix_elev))
+        return fail(PCG_ERR_ARG, "NULL table pointer");
+    pcg_volume* v = new (std::nothrow) pcg_volume();
+    if (!v) return fail(PCG_ERR_NOMEM, "out of host memory");
+    v->ne = ne;
+    v->nfield = nfield;
+    v->dtype = value_dtype;
+    cudaError_t e = cudaGetDevice(&v->device);
+    if (e != cudaSuccess) { delete v; return fail(PCG_ERR_CUDA, "cudaGetDevice failed: %s", cudaGetErrorString(e)); }
+
+    size_t n_az = 0, n_rng = 0, n_val = 0;
+    v->sweeps.resize(ne > 0 ? ne : 1);
+    memset(v->sweeps.data(), 0, v->sweeps.size() * sizeof(SweepDesc));
+    for (int s = 0; s < ne; ++s) {
+        if (naz[s] < 0 || ng[s] < 0) { delete v; return fail(PCG_ERR_ARG, "negative table length in sweep %d", s); }
+        SweepDesc& d = v->sweeps[s];
+        d.naz = naz[s];
+        d.ng = ng[s];
+        d.az_off = (unsigned)n_az;
+        d.rng_off = (unsigned)n_rng;
+        d.val_off = (unsigned long long)n_val;
+        d.elev = fix_elev[s];
+        d.tan_e = tan(fix_elev[s] * kDeg2Rad);   // RadarGridC.pyx:110,113 (host glibc)
+        d.sorted = 1;
+        if (naz[s] > 0) {
+            d.az_first = az[s][0];
+            const double span = az[s][naz[s] - 1] - az[s][0];
+            d.az_inv_step = (naz[s] > 1 && span > 0.0) ? (double)(naz[s] - 1) / span : 0.0;
+            for (int i = 1; i < naz[s]; ++i) if (!(az[s][i - 1] <= az[s][i])) d.sorted = 0;
+        }
+        if (ng[s] > 0) {
+            d.r_first = rng[s][0];
+            d.r_last = rng[s][ng[s] - 1];
+            const double span = d.r_last - d.r_first;
+            d.rng_inv_step = (ng[s] > 1 && span > 0.0) ? (double)(ng[s] - 1) / span : 0.0;
+            for (int i = 1; i < ng[s]; ++i) if (!(rng[s][i - 1] <= rng[s][i])) d.sorted = 0;
+        }
+        n_az += (size_t)naz[s];
+        n_rng += (size_t)ng[s];
+        n_val += (size_t)naz[s] * (size_t)ng[s];
+        n_val = (n_val + 1) & ~(size_t)1;   // keep every sweep tile 16-byte aligned
+    }
+    if (n_az > 0xffffffffull || n_rng > 0xffffffffull) { delete v; return fail(PCG_ERR_ARG, "tables too large"); }
+
+    const size_t vsz = (value_dtype == PCG_VALUE_F32) ? sizeof(float) : sizeof(double);
+    auto cleanup = [&]() { pcg_volume_destroy(v); };
+#define VOL_TRY(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            cleanup();                                                                         \
+            return fail(e__ == cudaErrorMemoryAllocation ? PCG_ERR_NOMEM : PCG_ERR_CUDA,       \
+                        "%s failed: %s", #expr, cudaGetErrorString(e__));                      \
+        }                                                                                      \
+    } while (0)
+    VOL_TRY(cudaMalloc((void**)&v->d_az, (n_az ? n_az : 1) * sizeof(double)));
+    VOL_TRY(cudaMalloc((void**)&v->d_rng, (n_rng ? n_rng : 1) * sizeof(double)));
+    VOL_TRY(cudaMalloc((void**)&v->d_sweeps, v->sweeps.size() * sizeof(SweepDesc)));
+    for (int f = 0; f < nfield; ++f) VOL_TRY(cudaMalloc(&v->d_val[f], (n_val ? n_val : 1) * vsz));
+    v->bytes = (n_az + n_rng) * sizeof(double) + v->sweeps.size() * sizeof(SweepDesc) + (size_t)nfield * n_val * vsz;
+
+    std::vector<float> tmp;
+    for (int s = 0; s < ne; ++s) {
+        const SweepDesc& d = v->sweeps[s];
+        if (d.naz) VOL_TRY(cudaMemcpy(v->d_az + d.az_off, az[s], (size_t)d.naz * sizeof(double), cudaMemcpyHostToDevice));
+        if (d.ng) VOL_TRY(cudaMemcpy(v->d_rng + d.rng_off, rng[s], (size_t)d.ng * sizeof(double), cudaMemcpyHostToDevice));
+        const size_t cnt = (size_t)d.naz * (size_t)d.ng;
+        if (!cnt) continue;
+        for (int f = 0; f < nfield; ++f) {
+            if (!val[f] || !val[f][s]) { cleanup(); return fail(PCG_ERR_ARG, "NULL value array (field %d, sweep %d)", f, s); }
+            if (value_dtype == PCG_VALUE_F32) {
+                tmp.resize(cnt);
+                for (size_t i = 0; i < cnt; ++i) tmp[i] = (float)val[f][s][i];
+                VOL_TRY(cudaMemcpy((float*)v->d_val[f] + d.val_off, tmp.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
+            } else {
+                VOL_TRY(cudaMemcpy((double*)v->d_val[f] + d.val_off, val[f][s], cnt * sizeof(double), cudaMemcpyHostToDevice));
+            }
+        }
+    }
+    VOL_TRY(cudaMemcpy(v->d_sweeps, v->sweeps.data(), v->sweeps.size() * sizeof(SweepDesc), cudaMemcpyHostToDevice));
+#undef VOL_TRY
+    *out = v;
+    return PCG_OK;
+}
+
+int pcg_volume_destroy(pcg_volume* v) {
+    if (!v) return PCG_OK;
+    cudaFree(v->d_az);
+    cudaFree(v->d_rng);
+    cudaFree(v->d_sweeps);
+    for (int f = 0; f < kMaxFields; ++f) cudaFree(v->d_val[f]);
+    delete v;
+    return PCG_OK;
+}
+
+int pcg_volume_info(const pcg_volume* v, int* ne, int* nfield, int* value_dtype, size_t* device_bytes) {
+    if (!v) return fail(PCG_ERR_ARG, "volume handle is NULL");
+    if (ne) *ne = v->ne;
+    if (nfield) *nfield = v->nfield;
+    if (value_dtype) *value_dtype = v->dtype;
+    if (device_bytes) *device_bytes = v->bytes;
+    return PCG_OK;
+}
+
+int pcg_get_cappi3d_dev(const pcg_volume* vol, double radar_height, double effective_earth_radius,
+                        const double* d_grid_x, const double* d_grid_y, int nx, int ny,
+                        const double* level_heights, int nz, double fill, int blind_code,
+                        double beam_width_deg, double radar_x, double radar_y, int merge_max,
+                        double* d_out, int32_t* d_index_out, void* stream) {
+    int rc = check_volume(vol);
+    if (rc) return rc;
+    rc = check_common(effective_earth_radius, nx, ny);
+    if (rc) return rc;
+    const int shift = (radar_x != 0.0 || radar_y != 0.0 || merge_max) ? 1 : 0;
+    return enqueue_cappi(vol, radar_height, resolve_re(effective_earth_radius), d_grid_x, d_grid_y,
+                         (long long)nx * ny, level_heights, nz, fill, blind_code, beam_width_deg,
+                         radar_x, radar_y, shift, merge_max, d_out, d_index_out, (cudaStream_t)stream);
+}
+
+int pcg_get_cr_dev(const pcg_volume* vol, double radar_height, double effective_earth_radius,
+                   const double* d_grid_x, const double* d_grid_y, int nx, int ny, double fill,
+                   double radar_x, double radar_y, double* d_out, void* stream) {
+    int rc = check_volume(vol);
+    if (rc) return rc;
+    rc = check_common(effective_earth_radius, nx, ny);
+    if (rc) return rc;
+    const int shift = (radar_x != 0.0 || radar_y != 0.0) ? 1 : 0;
+    return enqueue_cr(vol, radar_height, effective_earth_radius, d_grid_x, d_grid_y, (long long)nx * ny,
+                      fill, -1, 0.0, 0, radar_x, radar_y, shift, d_out, nullptr, (cudaStream_t)stream);
+}
+
+int pcg_get_cappi3d(const pcg_volume* vol, double radar_height, double effective_earth_radius,
+                    const double* grid_x, const double* grid_y, int nx, int ny,
+                    const double* level_heights, int nz, double fill, int blind_code,
+                    double beam_width_deg, double* out, int32_t* index_out) {
+    int rc = check_volume(vol);
+    if (rc) return rc;
+    rc = check_common(effective_earth_radius, nx, ny);
+    if (rc) return rc;
+    const size_t ncol = (size_t)nx * (size_t)ny;
+    const size_t nout = (size_t)vol->nfield * (size_t)nz * ncol;
+    if (ncol == 0 || nz <= 0) return nz < 0 ? fail(PCG_ERR_ARG, "nz must be non-negative") : PCG_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    if ((rc = g_scratch[S_GX].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_GY].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_OUT].ensure(nout * sizeof(double)))) return rc;
+    int32_t* d_idx = nullptr;
+    if (index_out) {
+        if ((rc = g_scratch[S_IDX].ensure((size_t)nz * ncol * kIdxStride * sizeof(int32_t)))) return rc;
+        d_idx = (int32_t*)g_scratch[S_IDX].ptr;
+    }
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = enqueue_cappi(vol, radar_height, effective_earth_radius, (const double*)g_scratch[S_GX].ptr,
+                       (const double*)g_scratch[S_GY].ptr, (long long)ncol, level_heights, nz, fill,
+                       blind_code, beam_width_deg, 0.0, 0.0, 0, 0, (double*)g_scratch[S_OUT].ptr, d_idx, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, g_scratch[S_OUT].ptr, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (index_out)
+        CUDA_TRY(cudaMemcpyAsync(index_out, d_idx, (size_t)nz * ncol * kIdxStride * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+int pcg_get_cr(const pcg_volume* vol, double radar_height, double effective_earth_radius,
+               const double* grid_x, const double* grid_y, int nx, int ny, double fill, double* out) {
+    int rc = check_volume(vol);
+    if (rc) return rc;
+    rc = check_common(effective_earth_radius, nx, ny);
+    if (rc) return rc;
+    const size_t ncol = (size_t)nx * (size_t)ny;
+    if (ncol == 0) return PCG_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    if ((rc = g_scratch[S_GX].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_GY].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_OUT].ensure(ncol * sizeof(double)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = enqueue_cr(vol, radar_height, effective_earth_radius, (const double*)g_scratch[S_GX].ptr,
+                    (const double*)g_scratch[S_GY].ptr, (long long)ncol, fill, -1, 0.0, 0, 0.0, 0.0, 0,
+                    (double*)g_scratch[S_OUT].ptr, nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, g_scratch[S_OUT].ptr, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+int pcg_ppi_to_grid(const pcg_volume* vol, int sweep, double elevation_deg, double radar_height,
+                    double effective_earth_radius, const double* grid_x, const double* grid_y,
+                    int nx, int ny, double fill, int blind_code, double* out, int32_t* index_out) {
+    int rc = check_volume(vol);
+    if (rc) return rc;
+    rc = check_common(effective_earth_radius, nx, ny);
+    if (rc) return rc;
+    if (sweep < 0 || sweep >= vol->ne) return fail(PCG_ERR_ARG, "sweep index %d out of range", sweep);
+    if (blind_code < 0 || blind_code > 4)
+        return fail(PCG_ERR_ARG,
+                    "blind_method must be one of 'mask', 'nearest_gate', 'lowest_sweep', 'hybrid', or "
+                    "'nearest_valid'.");
+    const size_t ncol = (size_t)nx * (size_t)ny;
+    if (ncol == 0) return PCG_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    if ((rc = g_scratch[S_GX].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_GY].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_OUT].ensure(ncol * sizeof(double)))) return rc;
+    int32_t* d_idx = nullptr;
+    if (index_out) {
+        if ((rc = g_scratch[S_IDX].ensure(ncol * kIdxStride * sizeof(int32_t)))) return rc;
+        d_idx = (int32_t*)g_scratch[S_IDX].ptr;
+    }
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = enqueue_cr(vol, radar_height, effective_earth_radius, (const double*)g_scratch[S_GX].ptr,
+                    (const double*)g_scratch[S_GY].ptr, (long long)ncol, fill, sweep, elevation_deg,
+                    blind_code, 0.0, 0.0, 0, (double*)g_scratch[S_OUT].ptr, d_idx, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, g_scratch[S_OUT].ptr, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (index_out)
+        CUDA_TRY(cudaMemcpyAsync(index_out, d_idx, ncol * kIdxStride * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+int pcg_get_mosaic_cappi3d(int nradar, const pcg_volume* const* vols, const double* radar_x,
+                           const double* radar_y, const double* radar_height,
+                           const double* effective_earth_radius, const double* grid_x,
+                           const double* grid_y, int nx, int ny, const double* level_heights,
+                           int nz, double fill, double* out) {
+    if (nradar < 0) return fail(PCG_ERR_ARG, "nradar must be non-negative");
+    if (nx < 0 || ny < 0 || nz < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
+    const size_t ncol = (size_t)nx * (size_t)ny;
+    const size_t nout = (size_t)nz * ncol;
+    if (nout == 0) return PCG_OK;
+    int rc;
+    for (int i = 0; i < nradar; ++i) {
+        if ((rc = check_volume(vols[i]))) return rc;
+        if (!(effective_earth_radius[i] > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
+    }
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    if ((rc = g_scratch[S_GX].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_GY].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_OUT].ensure(nout * sizeof(double)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    // GridValue = full(fill) (RadarGridC.pyx:548): merging the first radar into an all-fill grid
+    // is a plain store, so radar 0 writes and the others merge (RadarGridC.pyx:586-592).
+    if (nradar == 0) {
+        for (size_t i = 0; i < nout; ++i) out[i] = fill;
+        return PCG_OK;
+    }
+    for (int i = 0; i < nradar; ++i) {
+        // get_mosaic_CAPPI_3d uses field 0 of each radar, blind "mask", default beam width
+        rc = enqueue_cappi(vols[i], radar_height[i], effective_earth_radius[i], (const double*)g_scratch[S_GX].ptr,
+                           (const double*)g_scratch[S_GY].ptr, (long long)ncol, level_heights, nz, fill, 0,
+                           1.0, radar_x[i], radar_y[i], 1, i > 0 ? 1 : 0, (double*)g_scratch[S_OUT].ptr, nullptr,
+                           st, 1);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(out, g_scratch[S_OUT].ptr, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+int pcg_debug_cartesian_to_antenna(const double* x, const double* y, size_t n, double z, double h,
+                                   double effective_earth_radius, double* az, double* r, double* el) {
+    if (!(effective_earth_radius > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
+    if (n == 0) return PCG_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    int rc;
+    if ((rc = lib_stream(&st))) return rc;
+    Scratch* s = g_scratch;
+    const size_t b = n * sizeof(double);
+    if ((rc = s[S_GX].ensure(b)) || (rc = s[S_GY].ensure(b)) || (rc = s[S_TMP0].ensure(b)) ||
+        (rc = s[S_TMP1].ensure(b)) || (rc = s[S_TMP2].ensure(b)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(s[S_GX].ptr, x, b, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s[S_GY].ptr, y, b, cudaMemcpyHostToDevice, st));
+    volatile double av = effective_earth_radius + h;
+    volatile double a2 = av * av;
+    volatile double twoa = 2.0 * av;
+    LevelConst lc;
+    fill_level(&lc, z, effective_earth_radius, a2, twoa);
+    debug_c2a_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        (const double*)s[S_GX].ptr, (const double*)s[S_GY].ptr, n, lc, a2, twoa, effective_earth_radius,
+        (double*)s[S_TMP0].ptr, (double*)s[S_TMP1].ptr, (double*)s[S_TMP2].ptr);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(az, s[S_TMP0].ptr, b, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(r, s[S_TMP1].ptr, b, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(el, s[S_TMP2].ptr, b, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+int pcg_debug_xye_to_antenna(const double* x, const double* y, size_t n, double elevation_deg, double h,
+                             double effective_earth_radius, double* az, double* r) {
+    if (!(effective_earth_radius > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
+    if (n == 0) return PCG_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    int rc;
+    if ((rc = lib_stream(&st))) return rc;
+    Scratch* s = g_scratch;
+    const size_t b = n * sizeof(double);
+    if ((rc = s[S_GX].ensure(b)) || (rc = s[S_GY].ensure(b)) || (rc = s[S_TMP0].ensure(b)) ||
+        (rc = s[S_TMP1].ensure(b)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(s[S_GX].ptr, x, b, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s[S_GY].ptr, y, b, cudaMemcpyHostToDevice, st));
+    volatile double av = effective_earth_radius + h;
+    volatile double a2 = av * av;
+    volatile double twoa = 2.0 * av;
+    debug_xye_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        (const double*)s[S_GX].ptr, (const double*)s[S_GY].ptr, n, tan(elevation_deg * kDeg2Rad), av, a2,
+        twoa, effective_earth_radius, (double*)s[S_TMP0].ptr, (double*)s[S_TMP1].ptr);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(az, s[S_TMP0].ptr, b, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(r, s[S_TMP1].ptr, b, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+"""Host-side runtime objects: device-resident packed volumes and a pinned-host array pool.
+
+``DeviceVolume`` is the B200 form of the reference's ``PRD.vol`` tuple
+(``pycwr/core/NRadar.py:1931-1961``): the per-sweep azimuth / range / value lists packed into
+arenas that stay in HBM, so several products (CR, CAPPI levels, VIL/ET volumes, network
+passes) can be gridded from one upload.
+"""
+import ctypes
+import threading
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+
+def _f64_1d(a, what):
+    if not isinstance(a, np.ndarray):
+        a = np.asarray(a)
+    if a.dtype != np.float64:
+        raise ValueError("Buffer dtype mismatch, expected 'float64_t' but got %r (%s)" % (a.dtype.name, what))
+    if a.ndim != 1:
+        raise ValueError("Buffer has wrong number of dimensions (expected 1, got %d) (%s)" % (a.ndim, what))
+    return np.ascontiguousarray(a)
+
+
+def _f64_2d(a, what):
+    if not isinstance(a, np.ndarray):
+        a = np.asarray(a)
+    if a.dtype != np.float64:
+        raise ValueError("Buffer dtype mismatch, expected 'float64_t' but got %r (%s)" % (a.dtype.name, what))
+    if a.ndim != 2:
+        raise ValueError("Buffer has wrong number of dimensions (expected 2, got %d) (%s)" % (a.ndim, what))
+    return np.ascontiguousarray(a)
+
+
+class DeviceVolume:
+    """One radar volume (1..4 moments sharing azimuth/range tables) resident on the GPU."""
+
+    def __init__(self, vol_azimuth, vol_range, fix_elevation, vol_value, value_dtype="f64"):
+        lib = _lib.load()
+        fix = _f64_1d(fix_elevation, "fix_elevation")
+        ne = int(fix.shape[0])
+        # one moment: list of (naz, ng) arrays; several: list of such lists
+        if ne > 0 and len(vol_value) > 0 and isinstance(vol_value[0], (list, tuple)):
+            fields = [list(f) for f in vol_value]
+        else:
+            fields = [list(vol_value)]
+        if len(vol_azimuth) < ne or len(vol_range) < ne or any(len(f) < ne for f in fields):
+            raise IndexError("list index out of range")   # what the reference raises on use
+        az = [_f64_1d(vol_azimuth[s], "vol_azimuth[%d]" % s) for s in range(ne)]
+        rg = [_f64_1d(vol_range[s], "vol_range[%d]" % s) for s in range(ne)]
+        vals = [[_f64_2d(f[s], "vol_value[%d]" % s) for s in range(ne)] for f in fields]
+        naz = np.array([a.shape[0] for a in az], dtype=np.int32)
+        ng = np.array([a.shape[0] for a in rg], dtype=np.int32)
+        for f in vals:
+            for s in range(ne):
+                if f[s].shape[0] < naz[s] or f[s].shape[1] < ng[s]:
+                    raise IndexError("sweep %d: value array smaller than its azimuth/range tables" % s)
+                if f[s].shape != (naz[s], ng[s]):
+                    f[s] = np.ascontiguousarray(f[s][: naz[s], : ng[s]])
+        n1 = max(ne, 1)
+        azp = (_lib.c_double_p * n1)(*[a.ctypes.data_as(_lib.c_double_p) for a in az])
+        rgp = (_lib.c_double_p * n1)(*[a.ctypes.data_as(_lib.c_double_p) for a in rg])
+        fld = []
+        for f in vals:
+            fld.append((_lib.c_double_p * n1)(*[a.ctypes.data_as(_lib.c_double_p) for a in f]))
+        fpp = (_lib.c_double_pp * len(fld))(*[ctypes.cast(x, _lib.c_double_pp) for x in fld])
+        handle = ctypes.c_void_p()
+        dtype_code = {"f64": _lib.VALUE_F64, "f32": _lib.VALUE_F32}[value_dtype]
+        _lib.check(lib.pcg_volume_create(
+            ne, naz.ctypes.data_as(_lib.c_int_p), ng.ctypes.data_as(_lib.c_int_p),
+            ctypes.cast(azp, _lib.c_double_pp), ctypes.cast(rgp, _lib.c_double_pp), len(fld),
+            ctypes.cast(fpp, _lib.c_double_ppp), fix.ctypes.data_as(_lib.c_double_p), dtype_code,
+            ctypes.byref(handle)))
+        self.handle = handle
+        self.ne = ne
+        self.nfield = len(fld)
+        self.value_dtype = value_dtype
+        self.naz = naz
+        self.ng = ng
+        self.fix_elevation = fix.copy()
+        self.first_gate = np.array([r[0] if r.size else np.nan for r in rg], dtype=np.float64)
+        self.last_gate = np.array([r[-1] if r.size else np.nan for r in rg], dtype=np.float64)
+        self.nvalues = int(sum(int(a) * int(b) for a, b in zip(naz, ng)))
+        self.table_bytes = int(8 * (naz.sum() + ng.sum()))
+        self._finalizer = weakref.finalize(self, lib.pcg_volume_destroy, handle)
+
+    def close(self):
+        self._finalizer()
+
+    @property
+    def device_bytes(self):
+        n = ctypes.c_size_t(0)
+        _lib.check(_lib.load().pcg_volume_info(self.handle, None, None, None, ctypes.byref(n)))
+        return n.value
+
+
+class _PinnedPool:
+    """Recycles page-locked host blocks: pinning is slow (~ms per 10 MB), reuse is free."""
+
+    def __init__(self, max_cached_bytes=8 << 30):
+        self._free = {}
+        self._cached = 0
+        self._max = max_cached_bytes
+        self._lock = threading.Lock()
+
+    @staticmethod
+    def _bucket(nbytes):
+        b = 1 << 16
+        while b < nbytes:
+            b <<= 1
+        return b
+
+    def empty(self, shape, dtype=np.float64):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        bucket = self._bucket(max(nbytes, 1))
+        with self._lock:
+            lst = self._free.get(bucket)
+            ptr = lst.pop() if lst else None
+            if ptr is not None:
+                self._cached -= bucket
+        if ptr is None:
+            p = ctypes.c_void_p()
+            _lib.check(_lib.load().pcg_host_alloc(bucket, ctypes.byref(p)))
+            ptr = p.value
+        raw = (ctypes.c_char * bucket).from_address(ptr)
+        arr = np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+        weakref.finalize(raw, self._release, ptr, bucket)
+        return arr
+
+    def _release(self, ptr, bucket):
+        with self._lock:
+            if self._cached + bucket <= self._max:
+                self._free.setdefault(bucket, []).append(ptr)
+                self._cached += bucket
+                return
+        try:
+            _lib.load().pcg_host_free(ctypes.c_void_p(ptr))
+        except Exception:
+            pass
+
+
+pinned = _PinnedPool()
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked host memory (fast H2D/D2H), recycled on collection."""
+    return pinned.empty(shape, dtype)
+
+
+def pinned_copy(a):
+    out = pinned_empty(np.shape(a), np.asarray(a).dtype)
+    out[...] = a
+    return out

@@ -1,0 +1,222 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the
+committed fixtures generated from the compiled reference.
+
+Bars (BASELINE.json north_star): interpolation indices and valid/fill masks BIT-EXACT; moment
+values within 1e-3 dB absolute (dBZ/ZDR) and 1e-5 relative (velocity).  With float64 moment
+storage the value path is the reference's own unfused arithmetic, so the tests additionally
+report (and bound) the bit-identical fraction.
+"""
+import numpy as np
+import pytest
+
+from conftest import BLINDS, FILL, golden_volume
+from oracle import oracle as O
+from pycwr_b200 import RadarGridC as G
+from pycwr_b200 import synth
+from pycwr_b200.runtime import DeviceVolume
+
+pytestmark = pytest.mark.gpu
+
+ATOL_DB = 1e-3
+RTOL_V = 1e-5
+
+
+def assert_parity(got, want, idx_got=None, idx_want=None, what=""):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, what
+    assert np.array_equal(got == FILL, want == FILL), "fill mask differs: " + what
+    assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN mask differs: " + what
+    ok = (want != FILL) & ~np.isnan(want)
+    if ok.any():
+        err = np.abs(got[ok] - want[ok])
+        assert err.max() <= ATOL_DB, "%s: max |err| %.3e" % (what, err.max())
+        assert np.all(err <= RTOL_V * np.abs(want[ok]) + 1e-9), "%s: relative bar" % what
+    if idx_got is not None:
+        assert np.array_equal(idx_got, idx_want), "interpolation indices differ: " + what
+
+
+def test_known_answers_on_gpu():
+    # reference test/test_regression_grid.py:55-160, test/test_examples_interp.py:537-583
+    az = np.array([0.0, 90.0, 180.0, 270.0])
+    rg = np.array([1000.0, 2000.0])
+    x, y, z = G.antenna_to_cartesian(1500.0, 0.0, 1.5, 100.0)
+    gx, gy, lv = np.array([[x]]), np.array([[y]]), np.array([z])
+    vol = ([az, az], [rg, rg], np.array([1.0, 2.0]), [np.full((4, 2), 10.0), np.full((4, 2), 20.0)])
+    out = G.get_CAPPI_3d(*vol, 100.0, gx, gy, lv, FILL)
+    assert np.isclose(out[0, 0, 0], 15.0, rtol=0.0, atol=1e-6)
+    vol2 = ([az, az], [rg, rg], np.array([1.0, 2.0]), [np.full((4, 2), 30.0), np.full((4, 2), 40.0)])
+    mos = G.get_mosaic_CAPPI_3d([vol[0], vol2[0]], [vol[1], vol2[1]], [vol[2], vol2[2]], [vol[3], vol2[3]],
+                                np.zeros(2), np.zeros(2), np.full(2, 100.0), gx, gy, lv, FILL)
+    assert np.isclose(mos[0, 0, 0], 35.0, rtol=0.0, atol=1e-6)
+    x1, y1, _ = G.antenna_to_cartesian(1500.0, 0.0, 1.0, 100.0)
+    one = G.get_CAPPI_xy([az], [rg], np.array([1.0]), [np.full((4, 2), 10.0)], 100.0,
+                         np.array([[x1]]), np.array([[y1]]), 126.0, FILL)
+    assert np.isclose(one[0, 0], 10.0, rtol=0.0, atol=1e-6)
+    g500, g0 = np.array([[500.0]]), np.array([[0.0]])
+    m = G.get_CAPPI_3d(*vol, 0.0, g500, g0, np.array([0.0]), FILL, None, "mask")
+    h = G.get_CAPPI_3d(*vol, 0.0, g500, g0, np.array([0.0]), FILL, None, "hybrid")
+    assert m[0, 0, 0] == FILL and np.isclose(h[0, 0, 0], 10.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["uniform", "ragged"])
+def test_golden_case_a(golden, tag):
+    pre = "A_%s_" % tag
+    va, vr, fe, vv = golden_volume(golden, pre)
+    h = float(golden[pre + "h"])
+    gx, gy, lv = golden[pre + "gx"], golden[pre + "gy"], golden[pre + "levels"]
+    for b in BLINDS:
+        got, gi = G.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, b, return_index=True)
+        _, wi = O.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, b, return_index=True)
+        assert_parity(got, golden[pre + "cappi3d_" + b], gi, wi, "cappi3d " + b)
+    assert_parity(G.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, 8.1e6, "hybrid"),
+                  golden[pre + "cappi3d_re8p1e6"], what="custom Re")
+    assert_parity(G.get_CR_xy(va, vr, fe, vv, h, gx, gy, FILL), golden[pre + "cr"], what="CR")
+    got, gi = G.ppi_to_grid(va[2], vr[2], fe[2], vv[2], h, gx, gy, FILL, None, "hybrid", return_index=True)
+    _, wi = O.ppi_to_grid(va[2], vr[2], fe[2], vv[2], h, gx, gy, FILL, None, "hybrid", return_index=True)
+    assert_parity(got, golden[pre + "ppi2_hybrid"], gi, wi, "ppi hybrid")
+    assert_parity(G.ppi_to_grid(va[0], vr[0], fe[0], vv[0], h, gx, gy, FILL, None, "mask"),
+                  golden[pre + "ppi0_mask"], what="ppi mask")
+    assert_parity(G.get_CAPPI_xy(va[:1], vr[:1], fe[:1], vv[:1], h, gx, gy, 1500.0, FILL, None,
+                                 "nearest_gate", 3.0), golden[pre + "single_bw3"], what="single bw3")
+    assert_parity(G.get_CAPPI_xy(va[:1], vr[:1], fe[:1], vv[:1], h, gx, gy, 1500.0, FILL, None, "mask", 0.0),
+                  golden[pre + "single_bw0"], what="single bw0")
+
+
+def test_golden_case_b_mosaic(golden):
+    vols = [golden_volume(golden, "B_", radar=i) for i in range(3)]
+    args = ([v[0] for v in vols], [v[1] for v in vols], [v[2] for v in vols], [v[3] for v in vols],
+            golden["B_rx"], golden["B_ry"], golden["B_rh"], golden["B_gx"], golden["B_gy"], golden["B_levels"], FILL)
+    assert_parity(G.get_mosaic_CAPPI_3d(*args), golden["B_mosaic"], what="mosaic")
+    assert_parity(G.get_mosaic_CAPPI_3d(*args, [8.0e6, None, 8.6e6]), golden["B_mosaic_re"], what="mosaic Re")
+
+
+def test_golden_case_c_axis_and_diagonal_ties(golden):
+    """Regular grid through the radar with round-number azimuth/range tables: whole rows sit
+    exactly on table entries, so any last-bit difference in az flips an index."""
+    va, vr, fe, vv = golden_volume(golden, "C_")
+    gx, gy, lv = golden["C_gx"], golden["C_gy"], golden["C_levels"]
+    got, gi = G.get_CAPPI_3d(va, vr, fe, vv, 100.0, gx, gy, lv, FILL, None, "hybrid", return_index=True)
+    _, wi = O.get_CAPPI_3d(va, vr, fe, vv, 100.0, gx, gy, lv, FILL, None, "hybrid", return_index=True)
+    assert_parity(got, golden["C_cappi3d_hybrid"], gi, wi, "axis ties")
+    assert_parity(G.get_CR_xy(va, vr, fe, vv, 100.0, gx, gy, FILL), golden["C_cr"], what="axis ties CR")
+
+
+@pytest.mark.parametrize("cid,scale", [(1, 0.5), (2, 0.12), (3, 0.06), (5, 0.08)])
+def test_configs_against_oracle(cid, scale):
+    """BASELINE configs (grid thinned so the oracle finishes in seconds), stress moments."""
+    cfg = synth.config(cid, style="stress", scale=scale)
+    vol = cfg["volume"]
+    gx, gy = cfg["GridX"], cfg["GridY"]
+    for field in cfg["fields"]:
+        va, vr, fe, vv, h = synth.vol_tuple(vol, field)
+        if cfg["kind"] == "cr":
+            assert_parity(G.get_CR_xy(va, vr, fe, vv, h, gx, gy, FILL),
+                          O.get_CR_xy(va, vr, fe, vv, h, gx, gy, FILL), what=cfg["name"])
+            continue
+        for blind in ("mask", "hybrid"):
+            got, gi = G.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, cfg["levels"], FILL, None, blind, return_index=True)
+            want, wi = O.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, cfg["levels"], FILL, None, blind, return_index=True)
+            assert_parity(got, want, gi, wi, "%s %s %s" % (cfg["name"], field, blind))
+            same = np.mean(got == want)
+            assert same > 0.999, "bit-identical value fraction %.6f" % same
+
+
+def test_multifield_volume_shares_indices():
+    cfg = synth.config(2, style="stress", scale=0.08)
+    vol = cfg["volume"]
+    va, vr, fe = vol["vol_azimuth"], vol["vol_range"], vol["fix_elevation"]
+    fields = [vol["vol_value"][f] for f in cfg["fields"]]
+    dv = DeviceVolume(va, vr, fe, fields)
+    out = G.get_CAPPI_3d(None, None, None, dv, vol["radar_height"], cfg["GridX"], cfg["GridY"], cfg["levels"], FILL)
+    assert out.shape == (3,) + (cfg["levels"].size,) + cfg["GridX"].shape
+    for k, f in enumerate(cfg["fields"]):
+        want = O.get_CAPPI_3d(va, vr, fe, vol["vol_value"][f], vol["radar_height"], cfg["GridX"], cfg["GridY"],
+                              cfg["levels"], FILL)
+        assert_parity(out[k], want, what="multi-field " + f)
+    dv.close()
+
+
+def test_float32_storage_within_tolerance():
+    cfg = synth.config(3, style="stress", scale=0.05)
+    va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
+    dv = DeviceVolume(va, vr, fe, vv, value_dtype="f32")
+    got, gi = G.get_CAPPI_3d(None, None, None, dv, h, cfg["GridX"], cfg["GridY"], cfg["levels"], FILL,
+                             return_index=True)
+    want, wi = O.get_CAPPI_3d(va, vr, fe, vv, h, cfg["GridX"], cfg["GridY"], cfg["levels"], FILL, return_index=True)
+    assert_parity(got, want, gi, wi, "f32 storage")
+    dv.close()
+
+
+def test_edge_cases():
+    az = synth.azimuth_table(np.random.default_rng(1), 12)
+    rg = np.arange(1, 9) * 1000.0
+    val = np.random.default_rng(2).uniform(0, 50, (12, 8))
+    g = np.random.default_rng(3).uniform(-9e3, 9e3, (5, 7))
+    lv = np.array([100.0, 900.0])
+    # empty volume -> all fill (RadarGridC.pyx:398-399)
+    out = G.get_CAPPI_3d([], [], np.zeros(0), [], 10.0, g, g.T.copy().T, lv, FILL)
+    assert out.shape == (2, 5, 7) and np.all(out == FILL)
+    assert np.all(G.get_CR_xy([], [], np.zeros(0), [], 10.0, g, g, FILL) == FILL)
+    # degenerate sweeps (naz < 2 or ng < 2) -> fill (RadarGridC.pyx:273-274,337-339)
+    assert np.all(G.ppi_to_grid(az[:1], rg, 1.0, val[:1], 10.0, g, g, FILL) == FILL)
+    assert np.all(G.ppi_to_grid(az, rg[:1], 1.0, val[:, :1], 10.0, g, g, FILL) == FILL)
+    got = G.get_CAPPI_3d([az[:1], az], [rg, rg], np.array([1.0, 8.0]), [val[:1], val], 10.0, g, g, lv, FILL)
+    want = O.get_CAPPI_3d([az[:1], az], [rg, rg], np.array([1.0, 8.0]), [val[:1], val], 10.0, g, g, lv, FILL)
+    assert_parity(got, want, what="degenerate lower sweep")
+    # empty grid
+    e = np.zeros((0, 4))
+    assert G.get_CAPPI_3d([az], [rg], np.array([1.0]), [val], 10.0, e, e, lv, FILL).shape == (2, 0, 4)
+    # no levels
+    assert G.get_CAPPI_3d([az], [rg], np.array([1.0]), [val], 10.0, g, g, np.zeros(0), FILL).shape == (0, 5, 7)
+    # all-fill moments and a grid point exactly at the radar
+    g0 = np.zeros((1, 1))
+    allfill = np.full((12, 8), FILL)
+    assert G.get_CAPPI_3d([az, az], [rg, rg], np.array([1.0, 8.0]), [allfill, allfill], 10.0, g, g, lv, FILL).max() == FILL
+    got = G.get_CAPPI_3d([az, az], [rg, rg], np.array([1.0, 8.0]), [val, val], 10.0, g0, g0, np.array([10.0, 50.0]), FILL, None, "nearest_valid")
+    want = O.get_CAPPI_3d([az, az], [rg, rg], np.array([1.0, 8.0]), [val, val], 10.0, g0, g0, np.array([10.0, 50.0]), FILL, None, "nearest_valid")
+    assert_parity(got, want, what="origin")
+    # more than 64 levels goes through several launches
+    lv80 = np.linspace(50.0, 4000.0, 80)
+    got = G.get_CAPPI_3d([az, az], [rg, rg], np.array([1.0, 8.0]), [val, val], 10.0, g, g, lv80, FILL, None, "hybrid")
+    want = O.get_CAPPI_3d([az, az], [rg, rg], np.array([1.0, 8.0]), [val, val], 10.0, g, g, lv80, FILL, None, "hybrid")
+    assert_parity(got, want, what="80 levels")
+
+
+def test_inputs_not_mutated_and_output_owned():
+    cfg = synth.config(1, scale=0.1)
+    va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
+    copies = [a.copy() for a in vv]
+    gx0 = cfg["GridX"].copy()
+    a = G.get_CR_xy(va, vr, fe, vv, h, cfg["GridX"], cfg["GridY"], FILL)
+    b = G.get_CR_xy(va, vr, fe, vv, h, cfg["GridX"], cfg["GridY"], FILL)
+    assert all(np.array_equal(x, y) for x, y in zip(vv, copies)) and np.array_equal(gx0, cfg["GridX"])
+    assert a is not b and np.array_equal(a, b)
+    a[...] = 0.0
+    assert not np.array_equal(a, b)
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+
+
+def test_device_geometry_agreement_with_glibc():
+    """How often the device's az / r / el are bit-identical to the host libm chain (reported),
+    and that the differences never exceed a couple of ulps."""
+    import ctypes
+    from pycwr_b200 import _lib
+    rng = np.random.default_rng(20260319)
+    n = 400000
+    x, y = rng.uniform(-3e5, 3e5, n), rng.uniform(-3e5, 3e5, n)
+    az, r, el = (np.empty(n) for _ in range(3))
+    _lib.check(_lib.load().pcg_debug_cartesian_to_antenna(_lib.as_ptr(x), _lib.as_ptr(y), n, 3000.0, 321.0,
+                                                         O.DEFAULT_RE, _lib.as_ptr(az), _lib.as_ptr(r), _lib.as_ptr(el)))
+    waz, wr, wel = O.bulk_cartesian_to_antenna(x, y, 3000.0, 321.0)
+    frac = {k: float(np.mean(a == b)) for k, a, b in (("az", az, waz), ("r", r, wr), ("el", el, wel))}
+    print("device==glibc bit-identical fractions:", frac)
+    assert frac["r"] > 0.99 and frac["az"] > 0.5 and frac["el"] > 0.5
+    assert np.max(np.abs(az - waz)) < 2e-13 and np.max(np.abs(el - wel)) < 1e-13
+    assert np.max(np.abs(r - wr) / wr) < 1e-9
+    az2, r2 = np.empty(n), np.empty(n)
+    _lib.check(_lib.load().pcg_debug_xye_to_antenna(_lib.as_ptr(x), _lib.as_ptr(y), n, 2.4, 321.0, O.DEFAULT_RE,
+                                                   _lib.as_ptr(az2), _lib.as_ptr(r2)))
+    _, wr2, _ = O.bulk_xye_to_antenna(x, y, 2.4, 321.0)
+    print("CR geometry r bit-identical fraction:", float(np.mean(r2 == wr2)))
+    assert np.mean(r2 == wr2) > 0.99
