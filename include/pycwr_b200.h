@@ -46,8 +46,13 @@ typedef enum {
 #define PCG_IDX_STRIDE 10
 
 /* value storage of a packed volume on the device */
-#define PCG_VALUE_F64 0   /* moments kept as float64: interpolation bit-compatible with the reference */
-#define PCG_VALUE_F32 1   /* moments rounded to float32 on upload: half the gather traffic          */
+#define PCG_VALUE_F64 0   /* moments kept as float64; kernels restate the reference operation by operation
+                             (values bit-compatible with the reference wherever az/r/el are)          */
+#define PCG_VALUE_F32 1   /* production layout: float32 {lo,hi} radial pairs with the azimuth fill
+                             substitution resolved at pack time; indices/masks still bit-exact, values
+                             within a few float32 ulps (<< 1e-3 dB).  Falls back to PCG_VALUE_F64 for
+                             volumes it cannot serve (fewer than 2 sweeps, unsorted/duplicate tables):
+                             pcg_volume_info reports the layout actually used.                       */
 
 typedef struct pcg_volume pcg_volume;   /* opaque: one radar volume resident in HBM */
 
@@ -66,11 +71,12 @@ int64_t pcg_launch_count(void);
  *      (`vol_azimuth, vol_range, fix_elevation, vol_value`, produced by PRD.get_vol_data,
  *      `pycwr/core/NRadar.py:1931-1961`).  Inputs are borrowed host arrays: az[s] has naz[s]
  *      sorted float64 azimuths, rng[s] ng[s] ascending ranges, val[f][s] naz[s]*ng[s] row-major
- *      (radial, gate) float64 moments with missing == the caller's fill value.  nfield >= 1
+ *      (radial, gate) float64 moments with missing == `fill` (the value later passed as
+ *      `fillvalue` to the gridding calls; a mismatch there is PCG_ERR_ARG).  nfield >= 1
  *      moments share the azimuth/range tables (one set of indices serves all of them). */
 int pcg_volume_create(int ne, const int *naz, const int *ng, const double *const *az,
                       const double *const *rng, int nfield, const double *const *const *val,
-                      const double *fix_elev, int value_dtype, pcg_volume **out);
+                      const double *fix_elev, double fill, int value_dtype, pcg_volume **out);
 int pcg_volume_destroy(pcg_volume *vol);
 int pcg_volume_info(const pcg_volume *vol, int *ne, int *nfield, int *value_dtype,
                     size_t *device_bytes);

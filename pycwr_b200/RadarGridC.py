@@ -177,10 +177,16 @@ def interp_ppi(az, r, az_0, az_1, r_0, r_1, mat_00, mat_01, mat_10, mat_11, fill
 # gridding entry points
 # ------------------------------------------------------------------------------------------
 
-def _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value):
+# moment storage used when a call has to pack its own volume: "f32" = production layout
+# (exact indices/masks, values within a few float32 ulps), "f64" = reference arithmetic
+VALUE_DTYPE = "f32"
+
+
+def _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue):
     if isinstance(vol_value, DeviceVolume):
         return vol_value, False
-    return DeviceVolume(vol_azimuth, vol_range, fix_elevation, vol_value), True
+    return DeviceVolume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue=float(fillvalue),
+                        value_dtype=VALUE_DTYPE), True
 
 
 def _new_output(shape):
@@ -210,7 +216,8 @@ def ppi_to_grid(azimuth, ranges, elevation, mat_ppi, radar_height, GridX, GridY,
             idx[..., 1:3] = 0
             idx[..., 5] = 16
         return (out, idx) if return_index else out
-    vol = DeviceVolume([azimuth], [ranges], np.array([float(elevation)]), [mat_ppi])
+    vol = DeviceVolume([azimuth], [ranges], np.array([float(elevation)]), [mat_ppi], fillvalue=float(fillvalue),
+                       value_dtype="f64")
     try:
         _lib.check(_lib.load().pcg_ppi_to_grid(
             vol.handle, 0, float(elevation), float(radar_height), radius, _lib.as_ptr(gx), _lib.as_ptr(gy),
@@ -227,7 +234,7 @@ def get_CR_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height, Gr
     gx = _f64_2d(GridX, "GridX")
     gy = _f64_2d(GridY, "GridY")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
-    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value)
+    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue)
     nx, ny = gx.shape[0], gy.shape[1]
     out = _new_output((nx, ny))
     try:
@@ -266,7 +273,7 @@ def get_CAPPI_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height,
     gy = _f64_2d(GridY, "GridY")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
     blind_code = _resolve_blind_code(blind_method)
-    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value)
+    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue)
     try:
         levels = np.array([float(level_height)], dtype=np.float64)
         out, idx = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code,
@@ -288,7 +295,7 @@ def get_CAPPI_3d(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height,
     levels = _f64_1d(level_heights, "level_heights")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
     blind_code = _resolve_blind_code(blind_method)
-    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value)
+    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue)
     try:
         out, idx = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code, 1.0,
                           return_index)
@@ -324,7 +331,7 @@ def get_mosaic_CAPPI_3d(vol_azimuth, vol_range, fix_elevation, vol_value, radar_
     vols, owned = [], []
     try:
         for i in range(nradar):
-            v, o = _as_volume(vol_azimuth[i], vol_range[i], fix_elevation[i], vol_value[i])
+            v, o = _as_volume(vol_azimuth[i], vol_range[i], fix_elevation[i], vol_value[i], fillvalue)
             vols.append(v)
             owned.append(o)
         if nradar == 0:

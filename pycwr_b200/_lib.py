@@ -30,7 +30,7 @@ SIGNATURES = {
     "pcg_host_free": (_i, [_vp]),
     "pcg_launch_count": (ctypes.c_int64, []),
     "pcg_volume_create": (_i, [_i, c_int_p, c_int_p, c_double_pp, c_double_pp, _i, c_double_ppp,
-                               c_double_p, _i, c_void_pp]),
+                               c_double_p, _d, _i, c_void_pp]),
     "pcg_volume_destroy": (_i, [_vp]),
     "pcg_volume_info": (_i, [_vp, c_int_p, c_int_p, c_int_p, ctypes.POINTER(ctypes.c_size_t)]),
     "pcg_get_cappi3d": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, c_double_p, _i, _d, _i, _d, _vp, _vp]),

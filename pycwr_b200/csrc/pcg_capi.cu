@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/pycwr_b200.h"
+#include "pcg_fast.cuh"
 #include "pcg_kernels.cuh"
 
 using namespace pcg;
@@ -95,7 +96,9 @@ struct pcg_volume {
     double* d_rng = nullptr;
     void* d_val[kMaxFields] = {nullptr, nullptr, nullptr, nullptr};
     SweepDesc* d_sweeps = nullptr;
+    PairDesc* d_pairs = nullptr;     // [ne-1], packed (F32) volumes only
     std::vector<SweepDesc> sweeps;
+    double fill = -999.0;            // the missing-value marker the moments were packed with
     size_t bytes = 0;
 };
 
@@ -153,6 +156,109 @@ int launch_cappi_nf(const CappiArgs& args, int nf, dim3 grid, dim3 block, size_t
     return PCG_OK;
 }
 
+
+// Elevation weight of sweep pair (k, k+1) as a degree-5 polynomial in u = c - c_mid, where
+// c = cos(pi/2 + el) = -sin(el): w(u) = (el(u) - e_k) / (e_{k+1} - e_k), el(u) = -asin(c_mid + u)
+// in degrees (RadarGridC.pyx:155-157,469-476).  Interpolated at Chebyshev nodes in long double and
+// validated on a dense set; pairs that miss 1e-9 (or have e_{k+1} <= e_k) are marked !ok and their
+// voxels take the reference's own acos chain.
+void fit_pair(PairDesc* pr, double e0, double e1, double c0, double c1) {
+    memset(pr, 0, sizeof(*pr));
+    pr->c_mid = 0.5 * (c0 + c1);
+    if (!(e1 > e0) || !(c0 > c1)) return;
+    const long double mid = pr->c_mid;
+    const long double half = 0.5L * ((long double)c0 - (long double)c1) * 1.02L + 1e-12L;
+    const long double r2d = 180.0L / 3.14159265358979323846264338327950288L;
+    auto wfun = [&](long double u) -> long double {
+        long double c = mid + u;
+        if (c > 1.0L) c = 1.0L;
+        if (c < -1.0L) c = -1.0L;
+        return (-asinl(c) * r2d - (long double)e0) / ((long double)e1 - (long double)e0);
+    };
+    const int n = 6;
+    long double A[n][n + 1];
+    for (int j = 0; j < n; ++j) {
+        const long double t = cosl((2 * j + 1) * 3.14159265358979323846264338327950288L / (2 * n));
+        long double pw = 1.0L;
+        for (int i = 0; i < n; ++i) { A[j][i] = pw; pw *= t; }
+        A[j][n] = wfun(t * half);
+    }
+    for (int c = 0; c < n; ++c) {           // Gaussian elimination with partial pivoting
+        int piv = c;
+        for (int r = c + 1; r < n; ++r) if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+        for (int k = 0; k <= n; ++k) { long double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const long double f = A[r][c] / A[c][c];
+            for (int k = c; k <= n; ++k) A[r][k] -= f * A[c][k];
+        }
+    }
+    long double hp = 1.0L;
+    for (int i = 0; i < n; ++i) { pr->q[i] = (double)(A[i][n] / A[i][i] / hp); hp *= half; }
+    long double worst = 0.0L;
+    for (int j = 0; j <= 128; ++j) {
+        const long double u = half * (2.0L * j / 128.0L - 1.0L);
+        long double v = 0.0L;
+        for (int i = n - 1; i >= 0; --i) v = v * u + (long double)pr->q[i];
+        const long double e = fabsl(v - wfun(u));
+        if (e > worst) worst = e;
+    }
+    pr->ok = (worst <= 1e-9L) ? 1 : 0;
+}
+
+template <bool EMIT>
+int launch_fast_nf(const FastArgs& args, int nf, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    switch (nf) {
+        case 1: cappi3d_fast_kernel<1, EMIT><<<grid, block, smem, st>>>(args); break;
+        case 2: cappi3d_fast_kernel<2, EMIT><<<grid, block, smem, st>>>(args); break;
+        case 3: cappi3d_fast_kernel<3, EMIT><<<grid, block, smem, st>>>(args); break;
+        case 4: cappi3d_fast_kernel<4, EMIT><<<grid, block, smem, st>>>(args); break;
+        default: return fail(PCG_ERR_ARG, "nfield must be 1..%d", kMaxFields);
+    }
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return PCG_OK;
+}
+
+int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double* d_gx, const double* d_gy,
+                       long long ncol, const double* levels, int nz, double fill, int blind_code,
+                       double radar_x, double radar_y, int shift, int merge_max, double* d_out,
+                       int32_t* d_idx, cudaStream_t st, int nfield) {
+    if (!(fill == vol->fill))
+        return fail(PCG_ERR_ARG, "fillvalue %.17g differs from the value the volume was packed with (%.17g)",
+                    fill, vol->fill);
+    FastArgs A;
+    memset(&A, 0, sizeof(A));
+    A.vol = view_of(vol);
+    A.pairs = vol->d_pairs;
+    A.grid.gx = d_gx; A.grid.gy = d_gy; A.grid.ncol = ncol;
+    A.grid.radar_x = radar_x; A.grid.radar_y = radar_y; A.grid.shift = shift;
+    volatile double av = Re + h;
+    volatile double a2 = av * av;
+    volatile double twoa = 2.0 * av;
+    A.a = av; A.a2 = a2; A.twoa = twoa; A.Re = Re; A.fill = fill; A.fill32 = (float)fill;
+    A.guard = kGuardDelta * twoa;
+    A.nearest_gate = (blind_code == 1 || blind_code == 3 || blind_code == 4);
+    A.lowest_sweep = (blind_code == 2 || blind_code == 3 || blind_code == 4);
+    A.highest_sweep = (blind_code == 4);
+    A.merge_max = merge_max;
+    A.field_stride = (unsigned long long)nz * (unsigned long long)ncol;
+    const size_t smem = (size_t)vol->ne * sizeof(SweepDesc) + (size_t)(vol->ne - 1) * sizeof(PairDesc);
+    const dim3 block(256);
+    const dim3 grid((unsigned)((ncol + 255) / 256));
+    for (int z0 = 0; z0 < nz; z0 += kMaxLevelsPerLaunch) {
+        const int cnt = (nz - z0 < kMaxLevelsPerLaunch) ? nz - z0 : kMaxLevelsPerLaunch;
+        A.nz = cnt;
+        for (int k = 0; k < cnt; ++k) fill_level(&A.levels[k], levels[z0 + k], Re, a2, twoa);
+        A.out = d_out + (size_t)z0 * (size_t)ncol;
+        A.idx = d_idx ? d_idx + (size_t)z0 * (size_t)ncol * kIdxStride : nullptr;
+        const int rc = d_idx ? launch_fast_nf<true>(A, nfield, grid, block, smem, st)
+                             : launch_fast_nf<false>(A, nfield, grid, block, smem, st);
+        if (rc != PCG_OK) return rc;
+    }
+    return PCG_OK;
+}
+
 int enqueue_cappi(const pcg_volume* vol, double h, double Re, const double* d_gx, const double* d_gy,
                   long long ncol, const double* levels, int nz, double fill, int blind_code,
                   double beam_width_deg, double radar_x, double radar_y, int shift, int merge_max,
@@ -165,6 +271,9 @@ int enqueue_cappi(const pcg_volume* vol, double h, double Re, const double* d_gx
     if (nz < 0) return fail(PCG_ERR_ARG, "nz must be non-negative");
     if (ncol == 0 || nz == 0) return PCG_OK;
     if (vol->ne > kMaxSweeps) return fail(PCG_ERR_ARG, "at most %d sweeps are supported", kMaxSweeps);
+    if (vol->dtype == PCG_VALUE_F32)
+        return enqueue_cappi_fast(vol, h, Re, d_gx, d_gy, ncol, levels, nz, fill, blind_code, radar_x, radar_y,
+                                  shift, merge_max, d_out, d_idx, st, nfield);
     CappiArgs a;
     memset(&a, 0, sizeof(a));
     a.vol = view_of(vol);
@@ -196,13 +305,8 @@ int enqueue_cappi(const pcg_volume* vol, double h, double Re, const double* d_gx
         for (int k = 0; k < cnt; ++k) fill_level(&a.levels[k], levels[z0 + k], Re, a2, twoa);
         a.out = d_out + (size_t)z0 * (size_t)ncol;
         a.idx = d_idx ? d_idx + (size_t)z0 * (size_t)ncol * kIdxStride : nullptr;
-        int rc;
-        if (vol->dtype == PCG_VALUE_F32)
-            rc = d_idx ? launch_cappi_nf<float, true>(a, nfield, grid, block, smem, st)
-                       : launch_cappi_nf<float, false>(a, nfield, grid, block, smem, st);
-        else
-            rc = d_idx ? launch_cappi_nf<double, true>(a, nfield, grid, block, smem, st)
-                       : launch_cappi_nf<double, false>(a, nfield, grid, block, smem, st);
+        const int rc = d_idx ? launch_cappi_nf<double, true>(a, nfield, grid, block, smem, st)
+                             : launch_cappi_nf<double, false>(a, nfield, grid, block, smem, st);
         if (rc != PCG_OK) return rc;
     }
     return PCG_OK;
@@ -214,6 +318,26 @@ int enqueue_cr(const pcg_volume* vol, double h, double Re, const double* d_gx, c
                cudaStream_t st) {
     if (ncol == 0) return PCG_OK;
     if (vol->ne > kMaxSweeps) return fail(PCG_ERR_ARG, "at most %d sweeps are supported", kMaxSweeps);
+    if (vol->dtype == PCG_VALUE_F32) {
+        if (single_sweep >= 0) return fail(PCG_ERR_ARG, "ppi_to_grid needs a volume packed with PCG_VALUE_F64");
+        if (!(fill == vol->fill))
+            return fail(PCG_ERR_ARG, "fillvalue %.17g differs from the value the volume was packed with (%.17g)",
+                        fill, vol->fill);
+        CrFastArgs f;
+        memset(&f, 0, sizeof(f));
+        f.vol = view_of(vol);
+        f.grid.gx = d_gx; f.grid.gy = d_gy; f.grid.ncol = ncol;
+        f.grid.radar_x = radar_x; f.grid.radar_y = radar_y; f.grid.shift = shift;
+        volatile double fav = Re + h;
+        volatile double fa2 = fav * fav;
+        volatile double ftwoa = 2.0 * fav;
+        f.a = fav; f.a2 = fa2; f.twoa = ftwoa; f.Re = Re; f.fill = fill; f.fill32 = (float)fill;
+        f.out = d_out;
+        cr_fast_kernel<<<(unsigned)((ncol + 255) / 256), 256, (size_t)vol->ne * sizeof(SweepDesc), st>>>(f);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+        return PCG_OK;
+    }
     CrArgs a;
     memset(&a, 0, sizeof(a));
     a.vol = view_of(vol);
@@ -235,13 +359,8 @@ int enqueue_cr(const pcg_volume* vol, double h, double Re, const double* d_gx, c
     const size_t smem = (size_t)(vol->ne > 0 ? vol->ne : 1) * sizeof(SweepDesc);
     const dim3 block(256);
     const dim3 grid((unsigned)((ncol + 255) / 256));
-    if (vol->dtype == PCG_VALUE_F32) {
-        if (d_idx) cr_kernel<float, true><<<grid, block, smem, st>>>(a);
-        else cr_kernel<float, false><<<grid, block, smem, st>>>(a);
-    } else {
-        if (d_idx) cr_kernel<double, true><<<grid, block, smem, st>>>(a);
-        else cr_kernel<double, false><<<grid, block, smem, st>>>(a);
-    }
+    if (d_idx) cr_kernel<double, true><<<grid, block, smem, st>>>(a);
+    else cr_kernel<double, false><<<grid, block, smem, st>>>(a);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return PCG_OK;
@@ -284,7 +403,7 @@ int64_t pcg_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const* az,
                       const double* const* rng, int nfield, const double* const* const* val,
-                      const double* fix_elev, int value_dtype, pcg_volume** out) {
+                      const double* fix_elev, double fill, int value_dtype, pcg_volume** out) {
     if (!out) return fail(PCG_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (ne < 0 || ne > kMaxSweeps) return fail(PCG_ERR_ARG, "ne must be in [0, %d]", kMaxSweeps);
@@ -293,49 +412,83 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         return fail(PCG_ERR_ARG, "value_dtype must be PCG_VALUE_F64 or PCG_VALUE_F32");
     if (ne > 0 && (!naz || !ng || !az || !rng || !val || !fix_elev))
         return fail(PCG_ERR_ARG, "NULL table pointer");
+    for (int s = 0; s < ne; ++s) {
+        if (naz[s] < 0 || ng[s] < 0) return fail(PCG_ERR_ARG, "negative table length in sweep %d", s);
+        for (int f = 0; f < nfield; ++f)
+            if ((size_t)naz[s] * (size_t)ng[s] > 0 && (!val[f] || !val[f][s]))
+                return fail(PCG_ERR_ARG, "NULL value array (field %d, sweep %d)", f, s);
+    }
     pcg_volume* v = new (std::nothrow) pcg_volume();
     if (!v) return fail(PCG_ERR_NOMEM, "out of host memory");
     v->ne = ne;
     v->nfield = nfield;
-    v->dtype = value_dtype;
+    v->fill = fill;
     cudaError_t e = cudaGetDevice(&v->device);
     if (e != cudaSuccess) { delete v; return fail(PCG_ERR_CUDA, "cudaGetDevice failed: %s", cudaGetErrorString(e)); }
 
+    // ---- descriptors; identical range tables share storage (one bracket serves both sweeps) ----
     size_t n_az = 0, n_rng = 0, n_val = 0;
+    bool strict = true;        // every table strictly increasing (no duplicate coordinates)
     v->sweeps.resize(ne > 0 ? ne : 1);
     memset(v->sweeps.data(), 0, v->sweeps.size() * sizeof(SweepDesc));
+    std::vector<int> rng_owner(ne > 0 ? ne : 1, -1);
     for (int s = 0; s < ne; ++s) {
-        if (naz[s] < 0 || ng[s] < 0) { delete v; return fail(PCG_ERR_ARG, "negative table length in sweep %d", s); }
         SweepDesc& d = v->sweeps[s];
         d.naz = naz[s];
         d.ng = ng[s];
         d.az_off = (unsigned)n_az;
-        d.rng_off = (unsigned)n_rng;
         d.val_off = (unsigned long long)n_val;
         d.elev = fix_elev[s];
-        d.tan_e = tan(fix_elev[s] * kDeg2Rad);   // RadarGridC.pyx:110,113 (host glibc)
+        d.tan_e = tan(fix_elev[s] * kDeg2Rad);     // RadarGridC.pyx:110,113 (host glibc)
+        d.cthr = -sin(fix_elev[s] * kDeg2Rad);     // cos(pi/2 + el): elevation threshold in cosine space
         d.sorted = 1;
+        if (s > 0 && !(fix_elev[s - 1] <= fix_elev[s])) strict = false;   // packer sorts by fixed angle
         if (naz[s] > 0) {
             d.az_first = az[s][0];
             const double span = az[s][naz[s] - 1] - az[s][0];
             d.az_inv_step = (naz[s] > 1 && span > 0.0) ? (double)(naz[s] - 1) / span : 0.0;
-            for (int i = 1; i < naz[s]; ++i) if (!(az[s][i - 1] <= az[s][i])) d.sorted = 0;
+            for (int i = 1; i < naz[s]; ++i) {
+                if (!(az[s][i - 1] <= az[s][i])) d.sorted = 0;
+                if (!(az[s][i - 1] < az[s][i])) strict = false;
+            }
+            // the wrap interval (az[last]-360, az[0]) must be non-degenerate too
+            if (naz[s] > 1 && !(az[s][naz[s] - 1] - 360.0 < az[s][0])) strict = false;
         }
         if (ng[s] > 0) {
             d.r_first = rng[s][0];
             d.r_last = rng[s][ng[s] - 1];
             const double span = d.r_last - d.r_first;
             d.rng_inv_step = (ng[s] > 1 && span > 0.0) ? (double)(ng[s] - 1) / span : 0.0;
-            for (int i = 1; i < ng[s]; ++i) if (!(rng[s][i - 1] <= rng[s][i])) d.sorted = 0;
+            for (int i = 1; i < ng[s]; ++i) {
+                if (!(rng[s][i - 1] <= rng[s][i])) d.sorted = 0;
+                if (!(rng[s][i - 1] < rng[s][i])) strict = false;
+            }
+        }
+        if (!d.sorted) strict = false;
+        for (int t = 0; t < s && rng_owner[s] < 0; ++t)
+            if (rng_owner[t] == t && ng[t] == ng[s] &&
+                (ng[s] == 0 || memcmp(rng[t], rng[s], (size_t)ng[s] * sizeof(double)) == 0))
+                rng_owner[s] = t;
+        if (rng_owner[s] < 0) {
+            rng_owner[s] = s;
+            d.rng_off = (unsigned)n_rng;
+            n_rng += (size_t)ng[s];
+        } else {
+            d.rng_off = v->sweeps[rng_owner[s]].rng_off;
         }
         n_az += (size_t)naz[s];
-        n_rng += (size_t)ng[s];
         n_val += (size_t)naz[s] * (size_t)ng[s];
         n_val = (n_val + 1) & ~(size_t)1;   // keep every sweep tile 16-byte aligned
     }
     if (n_az > 0xffffffffull || n_rng > 0xffffffffull) { delete v; return fail(PCG_ERR_ARG, "tables too large"); }
 
-    const size_t vsz = (value_dtype == PCG_VALUE_F32) ? sizeof(float) : sizeof(double);
+    // packed (fast) storage needs >= 2 sweeps and clean tables; anything else keeps the float64
+    // layout and runs the kernels that restate the reference operation by operation.
+    const bool packed = (value_dtype == PCG_VALUE_F32) && ne >= 2 && strict;
+    v->dtype = packed ? PCG_VALUE_F32 : PCG_VALUE_F64;
+    const size_t vsz = sizeof(double);                       // float2 pair == 8 bytes as well
+    const size_t rsz = packed ? sizeof(double2) : sizeof(double);
+
     auto cleanup = [&]() { pcg_volume_destroy(v); };
 #define VOL_TRY(expr)                                                                          \
     do {                                                                                       \
@@ -347,30 +500,66 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         }                                                                                      \
     } while (0)
     VOL_TRY(cudaMalloc((void**)&v->d_az, (n_az ? n_az : 1) * sizeof(double)));
-    VOL_TRY(cudaMalloc((void**)&v->d_rng, (n_rng ? n_rng : 1) * sizeof(double)));
+    VOL_TRY(cudaMalloc((void**)&v->d_rng, (n_rng ? n_rng : 1) * rsz));
     VOL_TRY(cudaMalloc((void**)&v->d_sweeps, v->sweeps.size() * sizeof(SweepDesc)));
     for (int f = 0; f < nfield; ++f) VOL_TRY(cudaMalloc(&v->d_val[f], (n_val ? n_val : 1) * vsz));
-    v->bytes = (n_az + n_rng) * sizeof(double) + v->sweeps.size() * sizeof(SweepDesc) + (size_t)nfield * n_val * vsz;
+    v->bytes = n_az * sizeof(double) + n_rng * rsz + v->sweeps.size() * sizeof(SweepDesc) +
+               (size_t)nfield * n_val * vsz;
 
-    std::vector<float> tmp;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if (lib_stream(&st) != PCG_OK) { cleanup(); return PCG_ERR_CUDA; }
+    size_t max_sweep = 1;
+    for (int s = 0; s < ne; ++s) {
+        const size_t cnt = (size_t)naz[s] * (size_t)ng[s];
+        if (cnt > max_sweep) max_sweep = cnt;
+        if ((size_t)ng[s] > max_sweep) max_sweep = (size_t)ng[s];
+    }
+    double* tmp = nullptr;
+    if (packed) {
+        // one float64 staging tile; uploads and pack kernels are ordered by the stream
+        if (g_scratch[S_TMP0].ensure(max_sweep * sizeof(double)) != PCG_OK) { cleanup(); return PCG_ERR_NOMEM; }
+        tmp = (double*)g_scratch[S_TMP0].ptr;
+    }
     for (int s = 0; s < ne; ++s) {
         const SweepDesc& d = v->sweeps[s];
-        if (d.naz) VOL_TRY(cudaMemcpy(v->d_az + d.az_off, az[s], (size_t)d.naz * sizeof(double), cudaMemcpyHostToDevice));
-        if (d.ng) VOL_TRY(cudaMemcpy(v->d_rng + d.rng_off, rng[s], (size_t)d.ng * sizeof(double), cudaMemcpyHostToDevice));
+        if (d.naz) VOL_TRY(cudaMemcpyAsync(v->d_az + d.az_off, az[s], (size_t)d.naz * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (d.ng && rng_owner[s] == s) {
+            if (packed) {
+                VOL_TRY(cudaMemcpyAsync(tmp, rng[s], (size_t)d.ng * sizeof(double), cudaMemcpyHostToDevice, st));
+                pack_range_kernel<<<(d.ng + 255) / 256, 256, 0, st>>>(tmp, (double2*)v->d_rng + d.rng_off, d.ng);
+                g_launches.fetch_add(1);
+                VOL_TRY(cudaGetLastError());
+            } else {
+                VOL_TRY(cudaMemcpyAsync(v->d_rng + d.rng_off, rng[s], (size_t)d.ng * sizeof(double), cudaMemcpyHostToDevice, st));
+            }
+        }
         const size_t cnt = (size_t)d.naz * (size_t)d.ng;
         if (!cnt) continue;
         for (int f = 0; f < nfield; ++f) {
-            if (!val[f] || !val[f][s]) { cleanup(); return fail(PCG_ERR_ARG, "NULL value array (field %d, sweep %d)", f, s); }
-            if (value_dtype == PCG_VALUE_F32) {
-                tmp.resize(cnt);
-                for (size_t i = 0; i < cnt; ++i) tmp[i] = (float)val[f][s][i];
-                VOL_TRY(cudaMemcpy((float*)v->d_val[f] + d.val_off, tmp.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
+            if (packed) {
+                VOL_TRY(cudaMemcpyAsync(tmp, val[f][s], cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+                const unsigned blocks = (unsigned)((cnt + 255) / 256 < 148 * 16 ? (cnt + 255) / 256 : 148 * 16);
+                pack_pairs_kernel<<<blocks, 256, 0, st>>>(tmp, (float2*)v->d_val[f] + d.val_off, d.naz, d.ng,
+                                                          fill, (float)fill);
+                g_launches.fetch_add(1);
+                VOL_TRY(cudaGetLastError());
             } else {
-                VOL_TRY(cudaMemcpy((double*)v->d_val[f] + d.val_off, val[f][s], cnt * sizeof(double), cudaMemcpyHostToDevice));
+                VOL_TRY(cudaMemcpyAsync((double*)v->d_val[f] + d.val_off, val[f][s], cnt * sizeof(double), cudaMemcpyHostToDevice, st));
             }
         }
     }
-    VOL_TRY(cudaMemcpy(v->d_sweeps, v->sweeps.data(), v->sweeps.size() * sizeof(SweepDesc), cudaMemcpyHostToDevice));
+    VOL_TRY(cudaMemcpyAsync(v->d_sweeps, v->sweeps.data(), v->sweeps.size() * sizeof(SweepDesc), cudaMemcpyHostToDevice, st));
+    std::vector<PairDesc> pairs;
+    if (packed) {
+        pairs.resize(ne - 1);
+        for (int k = 0; k + 1 < ne; ++k)
+            fit_pair(&pairs[k], v->sweeps[k].elev, v->sweeps[k + 1].elev, v->sweeps[k].cthr, v->sweeps[k + 1].cthr);
+        VOL_TRY(cudaMalloc((void**)&v->d_pairs, pairs.size() * sizeof(PairDesc)));
+        VOL_TRY(cudaMemcpyAsync(v->d_pairs, pairs.data(), pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+        v->bytes += pairs.size() * sizeof(PairDesc);
+    }
+    VOL_TRY(cudaStreamSynchronize(st));
 #undef VOL_TRY
     *out = v;
     return PCG_OK;
@@ -381,6 +570,7 @@ int pcg_volume_destroy(pcg_volume* v) {
     cudaFree(v->d_az);
     cudaFree(v->d_rng);
     cudaFree(v->d_sweeps);
+    cudaFree(v->d_pairs);
     for (int f = 0; f < kMaxFields; ++f) cudaFree(v->d_val[f]);
     delete v;
     return PCG_OK;

@@ -34,6 +34,7 @@ struct SweepDesc {
     double rng_inv_step;             // index guess: floor((r - r_first) * rng_inv_step) + 1
     int sorted;                      // tables verified ascending on the host at pack time
     int pad;
+    double cthr;                     // -sin(elev): the sweep's elevation as a threshold in cosine space
 };
 
 struct LevelConst {                  // per output level, evaluated on the host in IEEE double

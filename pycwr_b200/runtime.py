@@ -35,9 +35,18 @@ def _f64_2d(a, what):
 
 
 class DeviceVolume:
-    """One radar volume (1..4 moments sharing azimuth/range tables) resident on the GPU."""
+    """One radar volume (1..4 moments sharing azimuth/range tables) resident on the GPU.
 
-    def __init__(self, vol_azimuth, vol_range, fix_elevation, vol_value, value_dtype="f64"):
+    ``value_dtype="f32"`` (default) asks for the production layout (float32 radial pairs, exact
+    indices, values within a few float32 ulps); ``"f64"`` keeps float64 moments and runs the
+    kernels that restate the reference operation by operation.  The library falls back to
+    ``"f64"`` for volumes the packed layout cannot serve (a single sweep, unsorted or duplicate
+    table entries); ``self.value_dtype`` reports the layout in use.  ``fillvalue`` must be the
+    value later passed to the gridding calls.
+    """
+
+    def __init__(self, vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue=-999.0,
+                 value_dtype="f32"):
         lib = _lib.load()
         fix = _f64_1d(fix_elevation, "fix_elevation")
         ne = int(fix.shape[0])
@@ -71,12 +80,15 @@ class DeviceVolume:
         _lib.check(lib.pcg_volume_create(
             ne, naz.ctypes.data_as(_lib.c_int_p), ng.ctypes.data_as(_lib.c_int_p),
             ctypes.cast(azp, _lib.c_double_pp), ctypes.cast(rgp, _lib.c_double_pp), len(fld),
-            ctypes.cast(fpp, _lib.c_double_ppp), fix.ctypes.data_as(_lib.c_double_p), dtype_code,
-            ctypes.byref(handle)))
+            ctypes.cast(fpp, _lib.c_double_ppp), fix.ctypes.data_as(_lib.c_double_p), float(fillvalue),
+            dtype_code, ctypes.byref(handle)))
         self.handle = handle
         self.ne = ne
         self.nfield = len(fld)
-        self.value_dtype = value_dtype
+        self.fillvalue = float(fillvalue)
+        used = ctypes.c_int(0)
+        _lib.check(lib.pcg_volume_info(handle, None, None, ctypes.byref(used), None))
+        self.value_dtype = "f32" if used.value == _lib.VALUE_F32 else "f64"
         self.naz = naz
         self.ng = ng
         self.fix_elevation = fix.copy()

@@ -35,7 +35,9 @@ def stress_moment(rng, naz, ng, lo, hi, fill=FILL):
     blk = rng.random(nblk) < 0.05
     gate_blk = np.minimum(np.arange(ng) // 64, nblk - 1)
     val[:, blk[gate_blk]] = fill
-    return np.ascontiguousarray(val, dtype=np.float64)
+    # the reference's readers emit float32 moments (pycwr/io/PAFile.py:434-444) which
+    # PRD.get_vol_data widens to float64: keep the synthetic moments float32-representable too
+    return np.ascontiguousarray(val.astype(np.float32), dtype=np.float64)
 
 
 def storm_moment(rng, az, rg, elev, lo, hi, cells, fill=FILL):
@@ -52,7 +54,7 @@ def storm_moment(rng, az, rg, elev, lo, hi, cells, fill=FILL):
     val = lo + (hi - lo) * np.clip(acc, 0.0, 1.0)
     val = np.round(val * 2.0) / 2.0
     val[acc < 0.07] = fill
-    return np.ascontiguousarray(val, dtype=np.float64)
+    return np.ascontiguousarray(val.astype(np.float32), dtype=np.float64)
 
 
 def make_volume(seed, elevations=VCP21, naz=366, ngate=1840, gate_m=250.0, fields=("dBZ",),
