@@ -126,6 +126,9 @@ int pcg_get_cr_dev(const pcg_volume *vol, double radar_height, double effective_
 int pcg_debug_cartesian_to_antenna(const double *x, const double *y, size_t n, double z, double h,
                                    double effective_earth_radius, double *az, double *r,
                                    double *el);
+/* the kernels' fused sqrt + reciprocal-root against the IEEE square root: number of inputs whose
+ * root differs (must be 0) and the worst |y*sqrt(a) - 1| of the reciprocal by-product */
+int pcg_debug_sqrt_check(const double *a, size_t n, uint64_t *mismatches, double *worst_rinv_err);
 int pcg_debug_xye_to_antenna(const double *x, const double *y, size_t n, double elevation_deg,
                              double h, double effective_earth_radius, double *az, double *r);
 

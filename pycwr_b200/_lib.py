@@ -42,6 +42,7 @@ SIGNATURES = {
                                  _i, _vp, _vp, _vp]),
     "pcg_get_cr_dev": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, _d, _d, _d, _vp, _vp]),
     "pcg_debug_cartesian_to_antenna": (_i, [_vp, _vp, ctypes.c_size_t, _d, _d, _d, _vp, _vp, _vp]),
+    "pcg_debug_sqrt_check": (_i, [_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), c_double_p]),
     "pcg_debug_xye_to_antenna": (_i, [_vp, _vp, ctypes.c_size_t, _d, _d, _d, _vp, _vp]),
 }
 

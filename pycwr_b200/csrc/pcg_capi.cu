@@ -238,6 +238,7 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     volatile double twoa = 2.0 * av;
     A.a = av; A.a2 = a2; A.twoa = twoa; A.Re = Re; A.fill = fill; A.fill32 = (float)fill;
     A.guard = kGuardDelta * twoa;
+    A.inv_twoa = 1.0 / twoa;
     A.nearest_gate = (blind_code == 1 || blind_code == 3 || blind_code == 4);
     A.lowest_sweep = (blind_code == 2 || blind_code == 3 || blind_code == 4);
     A.highest_sweep = (blind_code == 4);
@@ -782,6 +783,31 @@ int pcg_debug_cartesian_to_antenna(const double* x, const double* y, size_t n, d
     CUDA_TRY(cudaMemcpyAsync(r, s[S_TMP1].ptr, b, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(el, s[S_TMP2].ptr, b, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+int pcg_debug_sqrt_check(const double* a, size_t n, uint64_t* mismatches, double* worst_rinv_err) {
+    if (!a || !mismatches || !worst_rinv_err) return fail(PCG_ERR_ARG, "NULL pointer");
+    *mismatches = 0;
+    *worst_rinv_err = 0.0;
+    if (n == 0) return PCG_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    int rc;
+    if ((rc = lib_stream(&st))) return rc;
+    if ((rc = g_scratch[S_GX].ensure(n * sizeof(double))) || (rc = g_scratch[S_TMP0].ensure(16))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, a, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(g_scratch[S_TMP0].ptr, 0, 16, st));
+    debug_sqrt_kernel<<<148 * 8, 256, 0, st>>>((const double*)g_scratch[S_GX].ptr, n,
+                                               (unsigned long long*)g_scratch[S_TMP0].ptr,
+                                               (double*)g_scratch[S_TMP0].ptr + 1);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long host[2];
+    CUDA_TRY(cudaMemcpyAsync(host, g_scratch[S_TMP0].ptr, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *mismatches = host[0];
+    memcpy(worst_rinv_err, &host[1], sizeof(double));
     return PCG_OK;
 }
 
