@@ -164,6 +164,8 @@ int launch_cappi_nf(const CappiArgs& args, int nf, dim3 grid, dim3 block, size_t
 // voxels take the reference's own acos chain.
 void fit_pair(PairDesc* pr, double e0, double e1, double c0, double c1) {
     memset(pr, 0, sizeof(*pr));
+    pr->c_lo = c0;
+    pr->c_hi = c1;
     pr->c_mid = 0.5 * (c0 + c1);
     if (!(e1 > e0) || !(c0 > c1)) return;
     const long double mid = pr->c_mid;
@@ -203,18 +205,29 @@ void fit_pair(PairDesc* pr, double e0, double e1, double c0, double c1) {
         const long double e = fabsl(v - wfun(u));
         if (e > worst) worst = e;
     }
-    pr->ok = (worst <= 1e-9L) ? 1 : 0;
+    if (worst <= 1e-9L) pr->flags |= kPairPolyOk;
+}
+
+template <int NF, bool EMIT>
+int launch_fast_one(const FastArgs& args, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024)   // opt in to large dynamic shared memory (per device, cheap)
+        CUDA_TRY(cudaFuncSetAttribute(cappi3d_fast_kernel<NF, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    cappi3d_fast_kernel<NF, EMIT><<<grid, block, smem, st>>>(args);
+    return PCG_OK;
 }
 
 template <bool EMIT>
 int launch_fast_nf(const FastArgs& args, int nf, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    int rc;
     switch (nf) {
-        case 1: cappi3d_fast_kernel<1, EMIT><<<grid, block, smem, st>>>(args); break;
-        case 2: cappi3d_fast_kernel<2, EMIT><<<grid, block, smem, st>>>(args); break;
-        case 3: cappi3d_fast_kernel<3, EMIT><<<grid, block, smem, st>>>(args); break;
-        case 4: cappi3d_fast_kernel<4, EMIT><<<grid, block, smem, st>>>(args); break;
+        case 1: rc = launch_fast_one<1, EMIT>(args, grid, block, smem, st); break;
+        case 2: rc = launch_fast_one<2, EMIT>(args, grid, block, smem, st); break;
+        case 3: rc = launch_fast_one<3, EMIT>(args, grid, block, smem, st); break;
+        case 4: rc = launch_fast_one<4, EMIT>(args, grid, block, smem, st); break;
         default: return fail(PCG_ERR_ARG, "nfield must be 1..%d", kMaxFields);
     }
+    if (rc != PCG_OK) return rc;
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return PCG_OK;
@@ -244,9 +257,15 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     A.highest_sweep = (blind_code == 4);
     A.merge_max = merge_max;
     A.field_stride = (unsigned long long)nz * (unsigned long long)ncol;
-    const size_t smem = (size_t)vol->ne * sizeof(SweepDesc) + (size_t)(vol->ne - 1) * sizeof(PairDesc);
-    const dim3 block(256);
-    const dim3 grid((unsigned)((ncol + 255) / 256));
+    // shared memory: descriptors + the per-thread azimuth table [sweep][thread]; pick the block
+    // size so that several blocks still fit an SM (227 KB)
+    const size_t fixed = (size_t)vol->ne * sizeof(SweepDesc) + (size_t)(vol->ne - 1) * sizeof(PairDesc);
+    const size_t per_thread = (size_t)vol->ne * (sizeof(AzEntry) + (d_idx ? sizeof(int) : 0));
+    int threads = 256;
+    while (threads > 32 && fixed + per_thread * threads > 56 * 1024) threads >>= 1;
+    const size_t smem = fixed + per_thread * threads;
+    const dim3 block(threads);
+    const dim3 grid((unsigned)((ncol + threads - 1) / threads));
     for (int z0 = 0; z0 < nz; z0 += kMaxLevelsPerLaunch) {
         const int cnt = (nz - z0 < kMaxLevelsPerLaunch) ? nz - z0 : kMaxLevelsPerLaunch;
         A.nz = cnt;
@@ -482,10 +501,11 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         n_val = (n_val + 1) & ~(size_t)1;   // keep every sweep tile 16-byte aligned
     }
     if (n_az > 0xffffffffull || n_rng > 0xffffffffull) { delete v; return fail(PCG_ERR_ARG, "tables too large"); }
+    const bool fits32 = n_val < 0xfffffff0ull;     // packed layout addresses pair rows with 32 bits
 
     // packed (fast) storage needs >= 2 sweeps and clean tables; anything else keeps the float64
     // layout and runs the kernels that restate the reference operation by operation.
-    const bool packed = (value_dtype == PCG_VALUE_F32) && ne >= 2 && strict;
+    const bool packed = (value_dtype == PCG_VALUE_F32) && ne >= 2 && ne <= 120 && strict && fits32;
     v->dtype = packed ? PCG_VALUE_F32 : PCG_VALUE_F64;
     const size_t vsz = sizeof(double);                       // float2 pair == 8 bytes as well
     const size_t rsz = packed ? sizeof(double2) : sizeof(double);
@@ -554,8 +574,18 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
     std::vector<PairDesc> pairs;
     if (packed) {
         pairs.resize(ne - 1);
-        for (int k = 0; k + 1 < ne; ++k)
-            fit_pair(&pairs[k], v->sweeps[k].elev, v->sweeps[k + 1].elev, v->sweeps[k].cthr, v->sweeps[k + 1].cthr);
+        for (int k = 0; k + 1 < ne; ++k) {
+            const SweepDesc& d0 = v->sweeps[k];
+            const SweepDesc& d1 = v->sweeps[k + 1];
+            fit_pair(&pairs[k], d0.elev, d1.elev, d0.cthr, d1.cthr);
+            pairs[k].r_first = d0.r_first;
+            pairs[k].r_last = d0.r_last;
+            pairs[k].inv_step = d0.rng_inv_step;
+            pairs[k].rng_off = d0.rng_off;
+            pairs[k].ngm1 = d0.ng - 1;
+            if (d0.rng_off == d1.rng_off && d0.ng == d1.ng && d0.naz >= 2 && d1.naz >= 2 && d0.ng >= 2)
+                pairs[k].flags |= kPairShared;
+        }
         VOL_TRY(cudaMalloc((void**)&v->d_pairs, pairs.size() * sizeof(PairDesc)));
         VOL_TRY(cudaMemcpyAsync(v->d_pairs, pairs.data(), pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
         v->bytes += pairs.size() * sizeof(PairDesc);
