@@ -353,7 +353,7 @@ def run_product(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(cfg["name"])
+            traffic = json.load(open(tpath)).get(cfg["name"], {}).get("bytes")
         except Exception:
             traffic = None
     cpu = None
@@ -398,7 +398,8 @@ def main():
     ap.add_argument("--style", default="stress", choices=["stress", "storm"])
     ap.add_argument("--value-dtype", default="f32", choices=["f64", "f32"],
                     help="device moment layout: f32 = production pair layout, f64 = reference arithmetic")
-    ap.add_argument("--cpu-levels", type=int, default=6, help="levels of the full grid timed on 1 host core")
+    ap.add_argument("--cpu-levels", type=int, default=40,
+                    help="levels of the full grid timed on 1 host core (40 = all of C3, about 11 s)")
     ap.add_argument("--ref-levels", type=int, default=2, help="levels per worker for --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
