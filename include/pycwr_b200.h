@@ -121,6 +121,58 @@ int pcg_get_cr_dev(const pcg_volume *vol, double radar_height, double effective_
                    const double *d_grid_x, const double *d_grid_y, int nx, int ny, double fill,
                    double radar_x, double radar_y, double *d_out, void *stream);
 
+/* ---- network compositing: the multi-radar merge of run_radar_network_3d, one fused pass per
+ *      field (`pycwr/interp/RadarInterp.py`): per radar grid_single_radar_to_latlon_3d (:963-1023,
+ *      get_CAPPI_3d on grid - (radar_x, radar_y) with `blind_code`, then the range-sanity filter),
+ *      _compute_quality_weight_volume (:603-696), _compute_observability_mask (:540-600),
+ *      _build_composite_weight_cache (:1379-1396) and compose_network_volume (:1399-1487), plus the
+ *      coverage_count / blind_mask (:1938-1945) and the CR max-merge of per-radar get_CR_xy
+ *      (:1026-1068, 2047-2063).  Every volume must be packed (PCG_VALUE_F32 in effect) and uses
+ *      field 0.  beam_widths: NULL (1 degree everywhere) or per radar NULL / [ne] degrees
+ *      (`_get_sweep_beam_widths`, :527-537).  Outputs: composite [nz][nx*ny] (fill where no data);
+ *      optional valid_count int16 [nz][nx*ny] (second result of compose_network_volume),
+ *      coverage_count int16 and blind_mask int8 [nz][nx*ny], cr [nx*ny] (NaN where no echo),
+ *      quality [nz][nx*ny] = geometric quality weight of the LAST radar (the per-radar function
+ *      when nradar == 1), tie_voxels = voxels whose observability gate was decided by evaluating
+ *      the reference's NumPy-twin geometry (within 1e-12 of a gate or inside the elevation guard
+ *      band).  Sharding: pass a row slab (pointer offset into GridX/GridY, smaller nx). */
+#define PCG_NET_MAX 0               /* composite_method "max"              */
+#define PCG_NET_NEAREST 1           /* "nearest"                           */
+#define PCG_NET_EXP_WEIGHTED 2      /* "exp_weighted"                      */
+#define PCG_NET_QUALITY_WEIGHTED 3  /* "quality_weighted" (the default, `pycwr/configure/config.py:26`) */
+#define PCG_TERM_RANGE 1
+#define PCG_TERM_BEAM 2
+#define PCG_TERM_VERTICAL 4
+typedef struct {
+    int method;                 /* PCG_NET_*                                                     */
+    int blind_code;             /* as for pcg_get_cappi3d (network default: 3 hybrid, :1759)     */
+    int quality_terms;          /* PCG_TERM_* bits (`quality_weight_terms`)                      */
+    int sanity_filter;          /* 1: range-sanity filter of grid_single_radar_to_latlon_3d      */
+    double influence_radius_m;  /* 300000 (:1683)                                                */
+    double range_decay_m;       /* 230000 (:1769-1774)                                           */
+    double beam_radius_ref_m;   /* 3000                                                          */
+    double vertical_gap_ref_deg;/* 0.5                                                           */
+} pcg_network_params;
+
+int pcg_network_compose(int nradar, const pcg_volume *const *vols, const double *radar_x,
+                        const double *radar_y, const double *radar_height,
+                        const double *effective_earth_radius, const double *const *beam_widths,
+                        const pcg_network_params *params, const double *grid_x, const double *grid_y,
+                        int nx, int ny, const double *level_heights, int nz, double fill,
+                        double *composite, int16_t *valid_count, int16_t *coverage_count,
+                        int8_t *blind_mask, double *cr, double *quality, uint64_t *tie_voxels);
+int pcg_network_compose_dev(int nradar, const pcg_volume *const *vols, const double *radar_x,
+                            const double *radar_y, const double *radar_height,
+                            const double *effective_earth_radius, const double *const *beam_widths,
+                            const pcg_network_params *params, const double *d_grid_x,
+                            const double *d_grid_y, int nx, int ny, const double *level_heights /* host */,
+                            int nz, double fill, double *d_composite, int16_t *d_valid_count,
+                            int16_t *d_coverage_count, int8_t *d_blind_mask, double *d_cr,
+                            double *d_quality, void *stream);
+/* min / max / count of the valid (finite, != fill) source values of one moment: the window of the
+ * range-sanity filter (`pycwr/interp/RadarInterp.py:1003-1007`), reduced on the device at pack time */
+int pcg_volume_value_range(const pcg_volume *vol, int field, double *vmin, double *vmax, uint64_t *count);
+
 /* ---- diagnostics: the device's geometry inversion for a list of points (one level), used by
  *      the tests to measure bit-agreement of the device math with glibc. ------------------- */
 int pcg_debug_cartesian_to_antenna(const double *x, const double *y, size_t n, double z, double h,

@@ -18,6 +18,7 @@
 #include "../../include/pycwr_b200.h"
 #include "pcg_fast.cuh"
 #include "pcg_kernels.cuh"
+#include "pcg_network.cuh"
 
 using namespace pcg;
 
@@ -70,7 +71,7 @@ struct Scratch {
     }
 };
 
-enum { S_GX = 0, S_GY, S_OUT, S_IDX, S_TMP0, S_TMP1, S_TMP2, S_COUNT };
+enum { S_GX = 0, S_GY, S_OUT, S_IDX, S_TMP0, S_TMP1, S_TMP2, S_NET, S_AUX0, S_AUX1, S_AUX2, S_AUX3, S_AUX4, S_COUNT };
 Scratch g_scratch[S_COUNT];
 cudaStream_t g_stream[16] = {};
 
@@ -100,6 +101,10 @@ struct pcg_volume {
     std::vector<SweepDesc> sweeps;
     double fill = -999.0;            // the missing-value marker the moments were packed with
     size_t bytes = 0;
+    // valid (finite, != fill) source values per moment: the range-sanity window of the network path
+    double src_min[kMaxFields] = {0, 0, 0, 0};
+    double src_max[kMaxFields] = {0, 0, 0, 0};
+    unsigned long long src_count[kMaxFields] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -536,6 +541,14 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         if (cnt > max_sweep) max_sweep = cnt;
         if ((size_t)ng[s] > max_sweep) max_sweep = (size_t)ng[s];
     }
+    unsigned long long* d_mm = nullptr;      // [nfield][3]: min key, max key, count
+    if (g_scratch[S_TMP1].ensure(kMaxFields * 3 * sizeof(unsigned long long)) != PCG_OK) { cleanup(); return PCG_ERR_NOMEM; }
+    d_mm = (unsigned long long*)g_scratch[S_TMP1].ptr;
+    {
+        unsigned long long init[kMaxFields * 3];
+        for (int f = 0; f < kMaxFields; ++f) { init[3 * f] = ~0ull; init[3 * f + 1] = 0ull; init[3 * f + 2] = 0ull; }
+        VOL_TRY(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
     double* tmp = nullptr;
     if (packed) {
         // one float64 staging tile; uploads and pack kernels are ordered by the stream
@@ -563,10 +576,16 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
                 const unsigned blocks = (unsigned)((cnt + 255) / 256 < 148 * 16 ? (cnt + 255) / 256 : 148 * 16);
                 pack_pairs_kernel<<<blocks, 256, 0, st>>>(tmp, (float2*)v->d_val[f] + d.val_off, d.naz, d.ng,
                                                           fill, (float)fill);
-                g_launches.fetch_add(1);
+                minmax_kernel<<<blocks, 256, 0, st>>>(tmp, cnt, fill, d_mm + 3 * f);
+                g_launches.fetch_add(2);
                 VOL_TRY(cudaGetLastError());
             } else {
-                VOL_TRY(cudaMemcpyAsync((double*)v->d_val[f] + d.val_off, val[f][s], cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+                double* dst = (double*)v->d_val[f] + d.val_off;
+                VOL_TRY(cudaMemcpyAsync(dst, val[f][s], cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+                const unsigned blocks = (unsigned)((cnt + 255) / 256 < 148 * 16 ? (cnt + 255) / 256 : 148 * 16);
+                minmax_kernel<<<blocks, 256, 0, st>>>(dst, cnt, fill, d_mm + 3 * f);
+                g_launches.fetch_add(1);
+                VOL_TRY(cudaGetLastError());
             }
         }
     }
@@ -590,8 +609,23 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         VOL_TRY(cudaMemcpyAsync(v->d_pairs, pairs.data(), pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
         v->bytes += pairs.size() * sizeof(PairDesc);
     }
+    unsigned long long mm[kMaxFields * 3];
+    VOL_TRY(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, st));
     VOL_TRY(cudaStreamSynchronize(st));
 #undef VOL_TRY
+    for (int f = 0; f < nfield; ++f) {
+        v->src_count[f] = mm[3 * f + 2];
+        if (v->src_count[f]) {
+            auto unkey = [](unsigned long long k) {
+                const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+                double d;
+                memcpy(&d, &b, sizeof(d));
+                return d;
+            };
+            v->src_min[f] = unkey(mm[3 * f]);
+            v->src_max[f] = unkey(mm[3 * f + 1]);
+        }
+    }
     *out = v;
     return PCG_OK;
 }
@@ -871,3 +905,263 @@ int pcg_debug_xye_to_antenna(const double* x, const double* y, size_t n, double 
 }
 
 }  // extern "C"
+
+// ---- network compositing (K_net) ------------------------------------------------------------
+
+namespace {
+
+struct NetHostTables {
+    std::vector<NetRadar> radars;
+    std::vector<NetPair> npairs;
+    std::vector<NetLevel> levels;
+};
+
+int launch_network(const NetArgs& a, int method, dim3 grid, size_t smem, cudaStream_t st) {
+#define NET_CASE(M)                                                                                  \
+    case M:                                                                                          \
+        if (smem > 48 * 1024)                                                                        \
+            CUDA_TRY(cudaFuncSetAttribute(network_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                               \
+        network_kernel<M><<<grid, kNetThreads, smem, st>>>(a);                                       \
+        break;
+    switch (method) {
+        NET_CASE(kNetMax)
+        NET_CASE(kNetNearest)
+        NET_CASE(kNetExp)
+        NET_CASE(kNetQuality)
+        default: return fail(PCG_ERR_ARG, "Unsupported composite_method code %d", method);
+    }
+#undef NET_CASE
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return PCG_OK;
+}
+
+// d_* pointers are DEVICE pointers; tables are built on the host and uploaded through S_NET.
+int enqueue_network(int nradar, const pcg_volume* const* vols, const double* radar_x, const double* radar_y,
+                    const double* radar_height, const double* re, const double* const* beam_widths,
+                    const pcg_network_params* prm, const double* d_gx, const double* d_gy, long long ncol,
+                    const double* levels, int nz, double fill, double* d_comp, int16_t* d_valid,
+                    int16_t* d_cov, int8_t* d_blind, double* d_cr, double* d_quality,
+                    unsigned long long* d_ties, cudaStream_t st) {
+    if (!prm) return fail(PCG_ERR_ARG, "params is NULL");
+    if (nradar < 1) return fail(PCG_ERR_ARG, "radar_volumes must contain at least one volume.");
+    if (nradar > 255) return fail(PCG_ERR_ARG, "at most 255 radars per composite");
+    if (prm->method < 0 || prm->method > 3) return fail(PCG_ERR_ARG, "Unsupported composite_method code %d", prm->method);
+    if (!(prm->influence_radius_m > 0.0)) return fail(PCG_ERR_ARG, "influence_radius_m must be positive.");
+    if (prm->blind_code < 0 || prm->blind_code > 4)
+        return fail(PCG_ERR_ARG,
+                    "blind_method must be one of 'mask', 'nearest_gate', 'lowest_sweep', 'hybrid', or "
+                    "'nearest_valid'.");
+    if (nz < 0) return fail(PCG_ERR_ARG, "nz must be non-negative");
+    if (ncol == 0 || nz == 0) return PCG_OK;
+    int rc;
+    int max_ne = 2;
+    for (int i = 0; i < nradar; ++i) {
+        if ((rc = check_volume(vols[i]))) return rc;
+        if (!(re[i] > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
+        if (vols[i]->dtype != PCG_VALUE_F32)
+            return fail(PCG_ERR_ARG, "radar %d: network compositing needs a packed volume (>= 2 sweeps, strictly "
+                                     "increasing tables, value_dtype f32)", i);
+        if (vols[i]->ne > kNetMaxSweeps) return fail(PCG_ERR_ARG, "radar %d: at most %d sweeps", i, kNetMaxSweeps);
+        if (!(fill == vols[i]->fill))
+            return fail(PCG_ERR_ARG, "fillvalue %.17g differs from the value volume %d was packed with (%.17g)", fill, i,
+                        vols[i]->fill);
+        if (vols[i]->ne > max_ne) max_ne = vols[i]->ne;
+    }
+    NetHostTables T;
+    T.radars.resize(nradar);
+    size_t npair_total = 0;
+    for (int i = 0; i < nradar; ++i) npair_total += (size_t)(vols[i]->ne - 1);
+    T.npairs.resize(npair_total);
+    T.levels.resize((size_t)nradar * nz);
+    double zmin = levels[0];
+    for (int k = 1; k < nz; ++k) zmin = levels[k] < zmin ? levels[k] : zmin;
+
+    const size_t bytes_radars = sizeof(NetRadar) * (size_t)nradar;
+    const size_t bytes_pairs = sizeof(NetPair) * npair_total;
+    const size_t bytes_levels = sizeof(NetLevel) * T.levels.size();
+    if ((rc = g_scratch[S_NET].ensure(bytes_radars + bytes_pairs + bytes_levels + 64))) return rc;
+    char* d_base = (char*)g_scratch[S_NET].ptr;
+    const NetPair* d_pairs = (const NetPair*)(d_base + bytes_radars);
+    const NetLevel* d_levels = (const NetLevel*)(d_base + bytes_radars + bytes_pairs);
+
+    size_t poff = 0;
+    for (int i = 0; i < nradar; ++i) {
+        const pcg_volume* v = vols[i];
+        NetRadar& R = T.radars[i];
+        memset(&R, 0, sizeof(R));
+        R.vol = view_of(v);
+        R.pairs = v->d_pairs;
+        R.npairs = d_pairs + poff;
+        R.levels = d_levels + (size_t)i * nz;
+        R.x = radar_x[i];
+        R.y = radar_y[i];
+        R.Re = re[i];
+        volatile double av = re[i] + radar_height[i];   // RadarGridC.pyx:144
+        volatile double a2 = av * av;
+        volatile double twoa = 2.0 * av;
+        R.a = av; R.a2 = a2; R.twoa = twoa;
+        R.guard = kGuardDelta * twoa;
+        R.inv_twoa = 1.0 / twoa;
+        R.a2_np = pow((double)av, 2.0);                 // radar_radius ** 2 (transforms.py:213)
+        R.ne = v->ne;
+        // range-sanity window (RadarInterp.py:1003-1011)
+        if (v->src_count[0] == 0) {
+            R.src_lo = 1.0; R.src_hi = 0.0;             // no valid source value: everything -> fill
+        } else {
+            const double mn = v->src_min[0], mx = v->src_max[0];
+            double m = fabs(mn) > fabs(mx) ? fabs(mn) : fabs(mx);
+            if (m < 1.0) m = 1.0;
+            double tol = 1e-6 * m;
+            if (tol < 1e-6) tol = 1e-6;
+            R.src_lo = mn - tol;
+            R.src_hi = mx + tol;
+        }
+        R.inv_decay = (prm->quality_terms & kTermRange) ? (float)(1.0 / prm->range_decay_m) : 0.f;
+        R.inv_r2inf4 = (float)(4.0 / (prm->influence_radius_m * prm->influence_radius_m));
+        // reach of the radar: slant range r >= 0.999 * s * min(a, g) / Re for phi < 0.15
+        double rlast = 0.0;
+        for (int k = 0; k < v->ne; ++k) rlast = v->sweeps[k].r_last > rlast ? v->sweeps[k].r_last : rlast;
+        const double min_ag = re[i] + (radar_height[i] < zmin ? radar_height[i] : zmin);
+        const double factor = 0.999 * min_ag / re[i];
+        if (factor < 0.9 || !(rlast < 1.0e6)) R.cull2 = HUGE_VAL;
+        else { const double cr = rlast / factor * 1.001 + 1.0; R.cull2 = cr * cr; }
+        const double* bw = beam_widths ? beam_widths[i] : nullptr;
+        for (int k = 0; k + 1 < v->ne; ++k) {
+            NetPair& np = T.npairs[poff + k];
+            const SweepDesc& d0 = v->sweeps[k];
+            const SweepDesc& d1 = v->sweeps[k + 1];
+            np.obs_first = d0.r_first > d1.r_first ? d0.r_first : d1.r_first;
+            np.obs_last = d0.r_last < d1.r_last ? d0.r_last : d1.r_last;
+            const double b0 = bw ? bw[k] : 1.0, b1 = bw ? bw[k + 1] : 1.0;
+            const double rep = 0.5 * (b0 + b1);
+            np.beam_k = (prm->quality_terms & kTermBeam)
+                            ? (float)(tan(rep * kDeg2Rad * 0.5) / prm->beam_radius_ref_m) : 0.f;
+            const double gap_half = 0.5 * (d1.elev - d0.elev);
+            const double gq = gap_half / prm->vertical_gap_ref_deg;
+            np.vert_w = (prm->quality_terms & kTermVertical) ? (float)(1.0 / (1.0 + gq * gq)) : 1.f;
+        }
+        poff += (size_t)(v->ne - 1);
+        for (int k = 0; k < nz; ++k) {
+            NetLevel& L = T.levels[(size_t)i * nz + k];
+            fill_level(&L.cy, levels[k], re[i], a2, twoa);
+            const double g = re[i] + levels[k];
+            L.g2_np = pow(g, 2.0);
+            L.a2g2_np = R.a2_np + L.g2_np;
+            volatile double t = 2.0 * (double)av;
+            volatile double tg = t * g;                 // 2 * radar_radius * gate_radius (left to right)
+            L.twoag_np = tg;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_base, T.radars.data(), bytes_radars, cudaMemcpyHostToDevice, st));
+    if (bytes_pairs)
+        CUDA_TRY(cudaMemcpyAsync(d_base + bytes_radars, T.npairs.data(), bytes_pairs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_base + bytes_radars + bytes_pairs, T.levels.data(), bytes_levels, cudaMemcpyHostToDevice, st));
+    // the host vectors die with this frame: make the uploads complete before returning
+    CUDA_TRY(cudaStreamSynchronize(st));
+
+    NetArgs A;
+    memset(&A, 0, sizeof(A));
+    A.radars = (const NetRadar*)d_base;
+    A.nradar = nradar;
+    A.nz = nz;
+    A.gx = d_gx; A.gy = d_gy; A.ncol = ncol;
+    A.fill = fill; A.fill32 = (float)fill;
+    A.quality = 1;
+    A.sanity = prm->sanity_filter ? 1 : 0;
+    A.nearest_gate = (prm->blind_code == 1 || prm->blind_code == 3 || prm->blind_code == 4);
+    A.lowest_sweep = (prm->blind_code == 2 || prm->blind_code == 3 || prm->blind_code == 4);
+    A.highest_sweep = (prm->blind_code == 4);
+    size_t desc = (size_t)max_ne * sizeof(SweepDesc) + (size_t)(max_ne - 1) * (sizeof(PairDesc) + sizeof(NetPair)) +
+                  (size_t)kNetZC * sizeof(NetLevel);
+    desc = (desc + 15) & ~(size_t)15;
+    A.smem_desc_bytes = (int)desc;
+    A.max_ne = max_ne;
+    A.composite = d_comp; A.valid_count = d_valid; A.coverage = d_cov; A.blind = d_blind; A.cr = d_cr;
+    A.quality_out = d_quality; A.tie_count = d_ties;
+    // descriptors + azimuth table [sweep][thread] + accumulators (2 float + 1 double per level and thread)
+    const size_t smem = desc + (size_t)max_ne * kNetThreads * sizeof(AzEntry) +
+                        (size_t)kNetZC * kNetThreads * (2 * sizeof(float) + sizeof(double));
+    const dim3 grid((unsigned)((ncol + kNetThreads - 1) / kNetThreads), (unsigned)((nz + kNetZC - 1) / kNetZC));
+    return launch_network(A, prm->method, grid, smem, st);
+}
+
+}  // namespace
+
+extern "C" int pcg_volume_value_range(const pcg_volume* v, int field, double* vmin, double* vmax, uint64_t* count) {
+    if (!v) return fail(PCG_ERR_ARG, "volume handle is NULL");
+    if (field < 0 || field >= v->nfield) return fail(PCG_ERR_ARG, "field index %d out of range", field);
+    if (vmin) *vmin = v->src_min[field];
+    if (vmax) *vmax = v->src_max[field];
+    if (count) *count = v->src_count[field];
+    return PCG_OK;
+}
+
+extern "C" int pcg_network_compose_dev(int nradar, const pcg_volume* const* vols, const double* radar_x,
+                                       const double* radar_y, const double* radar_height,
+                                       const double* effective_earth_radius, const double* const* beam_widths,
+                                       const pcg_network_params* params, const double* d_grid_x,
+                                       const double* d_grid_y, int nx, int ny, const double* level_heights, int nz,
+                                       double fill, double* d_composite, int16_t* d_valid_count,
+                                       int16_t* d_coverage_count, int8_t* d_blind_mask, double* d_cr,
+                                       double* d_quality, void* stream) {
+    if (nx < 0 || ny < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
+    std::lock_guard<std::mutex> lock(g_mutex);   // the table scratch is shared
+    return enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
+                           d_grid_x, d_grid_y, (long long)nx * ny, level_heights, nz, fill, d_composite,
+                           d_valid_count, d_coverage_count, d_blind_mask, d_cr, d_quality, nullptr,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, const double* radar_x,
+                                   const double* radar_y, const double* radar_height,
+                                   const double* effective_earth_radius, const double* const* beam_widths,
+                                   const pcg_network_params* params, const double* grid_x, const double* grid_y,
+                                   int nx, int ny, const double* level_heights, int nz, double fill,
+                                   double* composite, int16_t* valid_count, int16_t* coverage_count,
+                                   int8_t* blind_mask, double* cr, double* quality, uint64_t* tie_voxels) {
+    if (nx < 0 || ny < 0 || nz < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
+    if (!composite) return fail(PCG_ERR_ARG, "composite is NULL");
+    const size_t ncol = (size_t)nx * (size_t)ny;
+    const size_t nvox = (size_t)nz * ncol;
+    if (tie_voxels) *tie_voxels = 0;
+    if (nvox == 0 && !(cr && ncol)) return PCG_OK;
+    int rc;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    if ((rc = g_scratch[S_GX].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_GY].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_OUT].ensure((nvox ? nvox : 1) * sizeof(double)))) return rc;
+    if (valid_count && (rc = g_scratch[S_AUX0].ensure(nvox * sizeof(int16_t)))) return rc;
+    if (coverage_count && (rc = g_scratch[S_AUX1].ensure(nvox * sizeof(int16_t)))) return rc;
+    if (blind_mask && (rc = g_scratch[S_AUX2].ensure(nvox * sizeof(int8_t)))) return rc;
+    if (cr && (rc = g_scratch[S_AUX3].ensure(ncol * sizeof(double)))) return rc;
+    if (quality && (rc = g_scratch[S_AUX4].ensure(nvox * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_TMP2].ensure(sizeof(unsigned long long)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(g_scratch[S_TMP2].ptr, 0, sizeof(unsigned long long), st));
+    rc = enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
+                         (const double*)g_scratch[S_GX].ptr, (const double*)g_scratch[S_GY].ptr, (long long)ncol,
+                         level_heights, nz, fill, (double*)g_scratch[S_OUT].ptr,
+                         valid_count ? (int16_t*)g_scratch[S_AUX0].ptr : nullptr,
+                         coverage_count ? (int16_t*)g_scratch[S_AUX1].ptr : nullptr,
+                         blind_mask ? (int8_t*)g_scratch[S_AUX2].ptr : nullptr,
+                         cr ? (double*)g_scratch[S_AUX3].ptr : nullptr,
+                         quality ? (double*)g_scratch[S_AUX4].ptr : nullptr,
+                         (unsigned long long*)g_scratch[S_TMP2].ptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(composite, g_scratch[S_OUT].ptr, nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (valid_count) CUDA_TRY(cudaMemcpyAsync(valid_count, g_scratch[S_AUX0].ptr, nvox * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    if (coverage_count) CUDA_TRY(cudaMemcpyAsync(coverage_count, g_scratch[S_AUX1].ptr, nvox * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    if (blind_mask) CUDA_TRY(cudaMemcpyAsync(blind_mask, g_scratch[S_AUX2].ptr, nvox * sizeof(int8_t), cudaMemcpyDeviceToHost, st));
+    if (cr) CUDA_TRY(cudaMemcpyAsync(cr, g_scratch[S_AUX3].ptr, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (quality) CUDA_TRY(cudaMemcpyAsync(quality, g_scratch[S_AUX4].ptr, nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    unsigned long long ties = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ties, g_scratch[S_TMP2].ptr, sizeof(ties), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (tie_voxels) *tie_voxels = ties;
+    return PCG_OK;
+}

@@ -1,0 +1,327 @@
+// pcg_network.cuh — K_net: the multi-radar merge of run_radar_network_3d as ONE pass per field.
+//
+// Replaces, per output voxel and fused over all radars (pycwr/interp/RadarInterp.py):
+//   grid_single_radar_to_latlon_3d  :963-1023   get_CAPPI_3d on the radar-local grid + range-sanity filter
+//   _compute_quality_weight_volume  :603-696    observable gating x range / beam / vertical terms
+//   _compute_observability_mask     :540-600    the same gating -> coverage_count, blind_mask (:1938-1945)
+//   _build_composite_weight_cache   :1379-1396  exp(-4 d^2 / R^2) (or d^2 for "nearest")
+//   compose_network_volume          :1399-1487  max / nearest / exp_weighted / quality_weighted, valid_count
+//   grid_single_radar_cr_to_latlon + CR max-merge :1026-1068, 2047-2063
+// The reference materialises an (nradar, nz, nlat, nlon) float64 stack per quantity; here the
+// per-radar values live in registers and only the merged outputs touch HBM.
+//
+// Decomposition: blockIdx.x tiles the grid columns (128 consecutive columns per block, so grid
+// reads and every output plane are coalesced), blockIdx.y tiles the levels in chunks of kNetZC
+// whose accumulators stay in registers.  The radar loop is block-uniform: a radar whose range
+// disc misses every column of the block is skipped by one __syncthreads_or, the others have
+// their descriptor tables staged in shared memory (same layout as the single-radar kernel) and
+// each in-reach column builds its azimuth table once per (radar, level chunk).
+//
+// Exactness: values, valid_count come from the same voxel body as get_CAPPI_3d (indices bit-exact).
+// The observability gates compare the reference's NumPy-twin geometry (np.hypot / ranges**2,
+// pycwr/core/transforms.py:201-222) with table entries; the twin agrees with the gridding geometry
+// to a few ulps, so a voxel is decided from the gridding's r / elevation bracket unless it lies
+// within a guard distance of a gate, in which case the twin chain itself is evaluated.
+#pragma once
+#include "pcg_fast.cuh"
+
+namespace pcg {
+
+constexpr int kNetZC = 8;            // levels per thread (register accumulators)
+constexpr int kNetThreads = 128;
+constexpr int kNetMaxSweeps = 32;    // per radar, bounded by the shared-memory azimuth table
+
+enum NetMethod { kNetMax = 0, kNetNearest = 1, kNetExp = 2, kNetQuality = 3 };
+enum NetTerm { kTermRange = 1, kTermBeam = 2, kTermVertical = 4 };
+
+struct NetPair {                     // sweep pair (k, k+1) of one radar
+    double obs_first, obs_last;      // max(first gates), min(last gates) (RadarInterp.py:671-672)
+    float beam_k;                    // tan(deg2rad(0.5*(bw_k + bw_k+1)) * 0.5) / beam_radius_ref (0: term off)
+    float vert_w;                    // 1 / (1 + (gap_half / vertical_gap_ref)^2)             (1: term off)
+};
+
+struct NetLevel {                    // per (radar, level) constants, host-evaluated
+    LevelConst cy;                   // the gridding chain (RadarGridC.pyx:145-146)
+    double a2g2_np, twoag_np, g2_np; // the NumPy twin: a**2 + g**2, 2*a*g, g**2 (transforms.py:213-218)
+};
+
+struct NetRadar {
+    VolumeView vol;
+    const PairDesc* pairs;
+    const NetPair* npairs;
+    const NetLevel* levels;          // [nz]
+    double x, y;                     // site on the common grid (m)
+    double Re, a, a2, twoa, guard, inv_twoa;
+    double a2_np;                    // a**2 as Python evaluates it
+    double cull2;                    // columns with d^2 above this are out of reach of every gate
+    double src_lo, src_hi;           // range-sanity window (src_lo > src_hi: no valid source value -> all fill)
+    float inv_decay;                 // 1 / range_decay_m   (0: term off)
+    float inv_r2inf4;                // 4 / influence_radius^2
+    int ne;
+    int pad;
+};
+
+struct NetArgs {
+    const NetRadar* radars;
+    int nradar;
+    int nz;
+    const double* gx;
+    const double* gy;
+    long long ncol;
+    double fill;
+    float fill32;
+    int quality;                     // multiply the 2-D weight by the geometric quality weight
+    int sanity;                      // apply the range-sanity filter
+    int nearest_gate, lowest_sweep, highest_sweep;
+    int smem_desc_bytes;             // descriptor area per block (max over radars)
+    int max_ne;                      // azimuth-table rows per block (max sweeps over radars)
+    double* composite;               // [nz][ncol]
+    int16_t* valid_count;            // [nz][ncol] or NULL
+    int16_t* coverage;               // [nz][ncol] or NULL
+    int8_t* blind;                   // [nz][ncol] or NULL
+    double* cr;                      // [ncol] or NULL (NaN where no radar has an echo)
+    double* quality_out;             // [nz][ncol] or NULL: quality weight of the LAST radar (per-radar diagnostics)
+    unsigned long long* tie_count;   // voxels whose observability was decided by the twin chain
+};
+
+// hypot with a single rounding (what glibc >= 2.35 returns): sqrt of the double-double x^2 + y^2
+// followed by one Newton correction on the residual.
+__device__ __forceinline__ double hypot_cr(double x, double y) {
+    x = fabs(x); y = fabs(y);
+    if (y > x) { const double t = x; x = y; y = t; }
+    if (x == 0.0) return 0.0;
+    const double xx = mul(x, x), xl = __fma_rn(x, x, -xx);
+    const double yy = mul(y, y), yl = __fma_rn(y, y, -yy);
+    const double sh = add(xx, yy);
+    const double sl = add(add(sub(xx, sh), yy), add(xl, yl));   // x^2 + y^2 = sh + sl (xx >= yy)
+    const double h = sqrt_rn(sh);
+    // residual of h^2 against sh + sl
+    const double hh = mul(h, h), hl = __fma_rn(h, h, -hh);
+    const double res = add(sub(sub(sh, hh), hl), sl);
+    return add(h, div(res, mul(2.0, h)));
+}
+
+// The NumPy-twin observability of one voxel (RadarInterp.py:566-599 with transforms.py:201-222).
+__device__ __noinline__ bool twin_observable(double x, double y, const NetRadar& R, const NetLevel& L,
+                                             const SweepDesc* s_sw, const NetPair* s_np, int ne) {
+    const double s = hypot_cr(x, y);
+    const double cphi = cos_small(div(s, R.Re));
+    double r2 = sub(L.a2g2_np, mul(L.twoag_np, cphi));
+    if (!(r2 > 0.0)) r2 = (r2 != r2) ? r2 : 0.0;
+    const double r = sqrt_rn(r2);
+    // cos_arg = (a**2 + ranges**2 - g**2) / (2*a*ranges); 0/0 -> NaN -> not finite -> unobservable
+    const double c0 = div(sub(add(R.a2_np, mul(r, r)), L.g2_np), mul(R.twoa, r));
+    if (c0 != c0) return false;
+    const double c = c0 > 1.0 ? 1.0 : (c0 < -1.0 ? -1.0 : c0);
+    const double el = div(mul(sub(acos(c), kHalfPi), 180.0), kPi);
+    if (!(el >= s_sw[0].elev) || !(el <= s_sw[ne - 1].elev)) return false;
+    int lo = 0, hi = ne;                              // np.searchsorted(side="right")
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (el < s_sw[mid].elev) hi = mid; else lo = mid + 1; }
+    int up = lo < 1 ? 1 : (lo > ne - 1 ? ne - 1 : lo);
+    const NetPair& np = s_np[up - 1];
+    return (r >= np.obs_first) && (r <= np.obs_last);
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kNetThreads) network_kernel(const __grid_constant__ NetArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // descriptor area (re-staged per radar) followed by the per-thread azimuth table
+    AzEntry* s_az = reinterpret_cast<AzEntry*>(smem_raw + p.smem_desc_bytes);
+
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = col < p.ncol;
+    const int z0 = blockIdx.y * kNetZC;
+    const int nzc = min(kNetZC, p.nz - z0);
+    const bool do_cr = (p.cr != nullptr) && (blockIdx.y == 0);
+    const float fill32 = p.fill32;
+
+    double gx = 0.0, gy = 0.0;
+    if (active) { gx = p.gx[col]; gy = p.gy[col]; }
+
+    // per-thread accumulators live in shared memory ([level][thread], conflict free) so the level
+    // loop stays rolled: weighted: sum w*v, sum w;  max / nearest: chosen value, has-data flag
+    float* acc_wv = reinterpret_cast<float*>(s_az + (size_t)p.max_ne * blockDim.x) + threadIdx.x;
+    float* acc_w = acc_wv + (size_t)kNetZC * blockDim.x;
+    double* best_d2 = reinterpret_cast<double*>(acc_wv - threadIdx.x + (size_t)2 * kNetZC * blockDim.x) + threadIdx.x;
+    unsigned long long cnt = 0, cov = 0;       // valid_count / coverage_count, 8 bits per level
+    for (int i = 0; i < kNetZC; ++i) {
+        acc_wv[i * blockDim.x] = 0.f;
+        acc_w[i * blockDim.x] = 0.f;
+        if (METHOD == kNetNearest) best_d2[i * blockDim.x] = __longlong_as_double(0x7ff0000000000000LL);
+        if (p.quality_out && active && i < nzc) p.quality_out[(size_t)(z0 + i) * (size_t)p.ncol + (size_t)col] = 0.0;
+    }
+    float cr_best = 0.f;
+    bool cr_any = false;
+    unsigned long long ties = 0;
+
+    for (int ir = 0; ir < p.nradar; ++ir) {
+        const NetRadar& R = p.radars[ir];
+        // radar-local coordinates (RadarInterp.py:990-991) and the 2-D distance of the weight cache
+        const double x = sub(gx, R.x), y = sub(gy, R.y);
+        const double d2 = add(mul(x, x), mul(y, y));
+        const bool reach = active && (d2 <= R.cull2);
+        if (!__syncthreads_or(reach)) continue;
+
+        const int ne = R.ne;
+        SweepDesc* s_sw = reinterpret_cast<SweepDesc*>(smem_raw);
+        PairDesc* s_pr = reinterpret_cast<PairDesc*>(s_sw + ne);
+        NetPair* s_np = reinterpret_cast<NetPair*>(s_pr + (ne - 1));
+        NetLevel* s_lv = reinterpret_cast<NetLevel*>(s_np + (ne - 1));
+        stage_sweeps(s_sw, R.vol.sweeps, ne);
+        stage_pairs(s_pr, R.pairs, ne - 1, R.twoa);
+        for (int i = threadIdx.x; i < ne - 1; i += blockDim.x) s_np[i] = R.npairs[i];
+        for (int i = threadIdx.x; i < nzc; i += blockDim.x) s_lv[i] = R.levels[z0 + i];
+        __syncthreads();
+
+        if (reach) {
+            // column invariants of this radar (RadarGridC.pyx:142-146,158)
+            const double s = sqrt_rn(d2);
+            const double phi = div(s, R.Re);
+            const double cphi = cos_small(phi);
+            const double az = azimuth_from_xy(x, y);
+            column_azimuth_table<false>(s_sw, ne, R.vol.az, az, s_az + threadIdx.x, nullptr, blockDim.x);
+            ColumnCtx c;
+            c.s_sw = s_sw; c.s_pr = s_pr;
+            c.my_az = s_az + threadIdx.x; c.my_iaz = nullptr; c.az_stride = blockDim.x;
+            c.ne = ne;
+            c.rg_t = reinterpret_cast<const double2*>(R.vol.rng);
+            c.a2 = R.a2; c.twoa = R.twoa; c.guard = R.guard; c.inv_twoa = R.inv_twoa;
+            c.fill32 = fill32;
+            c.nearest_gate = p.nearest_gate != 0; c.lowest_sweep = p.lowest_sweep != 0;
+            c.highest_sweep = p.highest_sweep != 0;
+            // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
+            const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? expf(-(float)d2 * R.inv_r2inf4) : 1.f;
+
+            int k = 0;
+#pragma unroll 1
+            for (int i = 0; i < nzc; ++i) {
+                float res[1];
+                VoxelInfo vi;
+                fast_voxel<1, false>(c, R.vol.val, s_lv[i].cy, cphi, k, res, vi);
+                float v = res[0];
+                // range-sanity filter (RadarInterp.py:1003-1014), compared in double like the reference
+                if (p.sanity && v != fill32) {
+                    const double vd = (double)v;
+                    if (!(R.src_lo <= R.src_hi) || vd < R.src_lo || vd > R.src_hi) v = fill32;
+                }
+                const bool valid = (v != fill32) && (v == v) && (fabsf(v) != __int_as_float(0x7f800000));
+                // observability (RadarInterp.py:566-599 / 636-684)
+                const int kk = vi.lower < ne - 1 ? vi.lower : ne - 2;
+                const NetPair& np = s_np[vi.bracket == kPair ? kk : 0];
+                bool obs = (vi.bracket == kPair) && (vi.r >= np.obs_first) && (vi.r <= np.obs_last);
+                const double tol = mul(vi.r, 1e-12);
+                const bool near_gate = (vi.bracket == kPair) &&
+                                       ((fabs(sub(vi.r, np.obs_first)) <= tol) || (fabs(sub(vi.r, np.obs_last)) <= tol));
+                if (vi.tie || near_gate || !(vi.r > 0.0)) {
+                    obs = twin_observable(x, y, R, s_lv[i], s_sw, s_np, ne);
+                    ++ties;
+                }
+                float q = 0.f;
+                if (obs) {
+                    // RadarInterp.py:687-695
+                    const float rf = (float)vi.r;
+                    const float t = rf * R.inv_decay;
+                    const float b = rf * np.beam_k;
+                    q = expf(-t * t) * __frcp_rn(fmaf(b, b, 1.f)) * np.vert_w;
+                    cov += 1ull << (8 * i);
+                }
+                if (p.quality_out) p.quality_out[(size_t)(z0 + i) * (size_t)p.ncol + (size_t)col] = (double)q;
+                if (valid) {
+                    cnt += 1ull << (8 * i);
+                    float& awv = acc_wv[i * blockDim.x];
+                    float& aw = acc_w[i * blockDim.x];
+                    if (METHOD == kNetMax) {
+                        if (aw == 0.f || v > awv) awv = v;
+                        aw = 1.f;
+                    } else if (METHOD == kNetNearest) {
+                        double& bd = best_d2[i * blockDim.x];
+                        if (d2 < bd) { bd = d2; awv = v; aw = 1.f; }
+                    } else {
+                        const float w = (METHOD == kNetQuality && p.quality) ? w2d * q : w2d;
+                        awv = fmaf(w, v, awv);
+                        aw += w;
+                    }
+                }
+            }
+
+            if (do_cr) {
+                // get_CR_xy on the local grid: every sweep at its fixed elevation, blind "mask"
+                // (RadarGridC.pyx:596-624), then the NaN-aware max over radars (RadarInterp.py:2047-2063)
+                const double sphi = sin_small(phi);
+                const double2* rg_t = reinterpret_cast<const double2*>(R.vol.rng);
+                const float2* val = static_cast<const float2*>(R.vol.val[0]);
+                for (int ie = 0; ie < ne; ++ie) {
+                    const SweepDesc& d = s_sw[ie];
+                    if (d.naz < 2 || d.ng < 2) continue;
+                    const double denom = sub(cphi, mul(sphi, d.tan_e));
+                    if (denom == 0.0) continue;
+                    const double g = div(R.a, denom);
+                    double r2 = sub(add(R.a2, mul(g, g)), mul(mul(R.twoa, g), cphi));
+                    if (r2 < 0.0) r2 = 0.0;
+                    const double r = sqrt_rn(r2);
+                    if (r != r) continue;
+                    const RangeBracket rb = range_bracket(d, rg_t, r, false);
+                    const float v = sample_pairs(val, s_az[(size_t)ie * blockDim.x + threadIdx.x], rb, fill32);
+                    if (v == fill32 || v != v) continue;
+                    if (!cr_any || v > cr_best) cr_best = v;
+                    cr_any = true;
+                }
+            }
+        }
+        __syncthreads();     // the descriptor area is re-staged by the next radar
+    }
+
+    if (!active) return;
+    for (int i = 0; i < nzc; ++i) {
+        const size_t o = (size_t)(z0 + i) * (size_t)p.ncol + (size_t)col;
+        const float awv = acc_wv[i * blockDim.x], aw = acc_w[i * blockDim.x];
+        double out = p.fill;
+        if (METHOD == kNetMax || METHOD == kNetNearest) {
+            if (aw != 0.f) out = (double)awv;
+        } else {
+            if (aw > 0.f) out = (double)awv / (double)aw;            // has_data = total_weight > 0
+        }
+        const unsigned c8 = (unsigned)(cov >> (8 * i)) & 0xffu;
+        p.composite[o] = out;
+        if (p.valid_count) p.valid_count[o] = (int16_t)((unsigned)(cnt >> (8 * i)) & 0xffu);
+        if (p.coverage) p.coverage[o] = (int16_t)c8;
+        if (p.blind) p.blind[o] = (int8_t)(c8 == 0u);
+    }
+    if (do_cr) p.cr[col] = cr_any ? (double)cr_best : __longlong_as_double(0x7ff8000000000000LL);
+    if (ties && p.tie_count) atomicAdd(p.tie_count, ties);
+}
+
+// min / max / count of the valid (finite, != fill) source values of one sweep tile: the window of
+// the range-sanity filter (RadarInterp.py:1003-1007).  Doubles are ordered through their bit
+// patterns (sign-flipped) so unsigned atomics implement min / max.
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void minmax_kernel(const double* __restrict__ src, size_t n, double fill,
+                              unsigned long long* __restrict__ out /* [min_key, max_key, count] */) {
+    unsigned long long lo = ~0ull, hi = 0ull, cnt = 0ull;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = src[i];
+        if (v == fill || v != v || fabs(v) == __longlong_as_double(0x7ff0000000000000LL)) continue;
+        const unsigned long long kx = order_key(v);
+        lo = kx < lo ? kx : lo;
+        hi = kx > hi ? kx : hi;
+        ++cnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long l2 = __shfl_down_sync(0xffffffffu, lo, o);
+        const unsigned long long h2 = __shfl_down_sync(0xffffffffu, hi, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+        atomicAdd(out + 2, cnt);
+    }
+}
+
+}  // namespace pcg
