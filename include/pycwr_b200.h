@@ -173,6 +173,37 @@ int pcg_network_compose_dev(int nradar, const pcg_volume *const *vols, const dou
  * range-sanity filter (`pycwr/interp/RadarInterp.py:1003-1007`), reduced on the device at pack time */
 int pcg_volume_value_range(const pcg_volume *vol, int field, double *vmin, double *vmax, uint64_t *count);
 
+/* _compute_observability_mask (`pycwr/interp/RadarInterp.py:540-600`) and
+ * _compute_quality_weight_volume (:603-696) as stand-alone functions for any sweep count (the
+ * NumPy-twin geometry of `pycwr/core/transforms.py:201-222` restated in FP64 for every voxel).
+ * first_gate / last_gate: vol_range[s][0] / vol_range[s][-1]; beam_widths [ne] degrees or NULL (1.0).
+ * mask: uint8 [nz][nx*ny] or NULL; quality: float64 [nz][nx*ny] or NULL. */
+int pcg_network_gates(int ne, const double *fix_elev, const double *first_gate, const double *last_gate,
+                      const double *beam_widths, double radar_height, double effective_earth_radius,
+                      double radar_x, double radar_y, const double *grid_x, const double *grid_y, int nx,
+                      int ny, const double *level_heights, int nz, int quality_terms,
+                      double range_decay_m, double beam_radius_ref_m, double vertical_gap_ref_deg,
+                      unsigned char *mask, double *quality);
+
+/* compose_network_volume (`pycwr/interp/RadarInterp.py:1399-1487`) on already gridded per-radar
+ * volumes (host arrays [nz][nx*ny] each), restated in FP64 with the radar axis accumulated in order.
+ * quality: per-radar weight volumes or NULL; weight2d: [nradar][nx*ny] the 2-D cache of
+ * _build_composite_weight_cache (:1379-1396; squared distances for "nearest"), NULL for "max". */
+int pcg_compose_volumes(int nradar, const double *const *volumes, const double *const *quality,
+                        const double *weight2d, int method, int nz, int nx, int ny, double fill,
+                        double *composite, int16_t *valid_count);
+
+/* derive_cr / derive_vil / derive_et (`pycwr/core/RadarProduct.py:26-85`) over a gridded volume
+ * [nz][nx*ny]; every output is optional (NULL skips it): cr, vil, et [nx*ny] float64 (NaN where
+ * undefined), topped [nx*ny] uint8. */
+int pcg_column_products(const double *volume, const double *level_heights, int nz, int nx, int ny,
+                        double fill, double min_dbz, double max_dbz_cap, double threshold_dbz,
+                        double *cr, double *vil, double *et, unsigned char *topped);
+int pcg_column_products_dev(const double *d_volume, const double *d_levels, int nz, int nx, int ny,
+                            double fill, double min_dbz, double max_dbz_cap, double threshold_dbz,
+                            double *d_cr, double *d_vil, double *d_et, unsigned char *d_topped,
+                            void *stream);
+
 /* ---- diagnostics: the device's geometry inversion for a list of points (one level), used by
  *      the tests to measure bit-agreement of the device math with glibc. ------------------- */
 int pcg_debug_cartesian_to_antenna(const double *x, const double *y, size_t n, double z, double h,

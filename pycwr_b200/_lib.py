@@ -41,10 +41,32 @@ SIGNATURES = {
     "pcg_get_cappi3d_dev": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, c_double_p, _i, _d, _i, _d, _d, _d,
                                  _i, _vp, _vp, _vp]),
     "pcg_get_cr_dev": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, _d, _d, _d, _vp, _vp]),
+    "pcg_volume_value_range": (_i, [_vp, _i, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_uint64)]),
+    "pcg_network_compose": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_pp, _vp,
+                                 _vp, _vp, _i, _i, c_double_p, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 ctypes.POINTER(ctypes.c_uint64)]),
+    "pcg_network_compose_dev": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_pp,
+                                     _vp, _vp, _vp, _i, _i, c_double_p, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcg_network_gates": (_i, [_i, c_double_p, c_double_p, c_double_p, c_double_p, _d, _d, _d, _d, _vp, _vp, _i, _i,
+                               c_double_p, _i, _i, _d, _d, _d, _vp, _vp]),
+    "pcg_compose_volumes": (_i, [_i, c_double_pp, c_double_pp, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
+    "pcg_column_products": (_i, [_vp, c_double_p, _i, _i, _i, _d, _d, _d, _d, _vp, _vp, _vp, _vp]),
+    "pcg_column_products_dev": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "pcg_debug_cartesian_to_antenna": (_i, [_vp, _vp, ctypes.c_size_t, _d, _d, _d, _vp, _vp, _vp]),
     "pcg_debug_sqrt_check": (_i, [_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), c_double_p]),
     "pcg_debug_xye_to_antenna": (_i, [_vp, _vp, ctypes.c_size_t, _d, _d, _d, _vp, _vp]),
 }
+
+
+class NetworkParams(ctypes.Structure):
+    """pcg_network_params (include/pycwr_b200.h)."""
+    _fields_ = [("method", _i), ("blind_code", _i), ("quality_terms", _i), ("sanity_filter", _i),
+                ("influence_radius_m", _d), ("range_decay_m", _d), ("beam_radius_ref_m", _d),
+                ("vertical_gap_ref_deg", _d)]
+
+
+NET_METHODS = {"max": 0, "nearest": 1, "exp_weighted": 2, "quality_weighted": 3}
+QUALITY_TERMS = {"range": 1, "beam": 2, "vertical": 4}
 
 
 class PcgError(RuntimeError):

@@ -19,6 +19,7 @@
 #include "pcg_fast.cuh"
 #include "pcg_kernels.cuh"
 #include "pcg_network.cuh"
+#include "pcg_products.cuh"
 
 using namespace pcg;
 
@@ -1163,5 +1164,204 @@ extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, co
     CUDA_TRY(cudaMemcpyAsync(&ties, g_scratch[S_TMP2].ptr, sizeof(ties), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (tie_voxels) *tie_voxels = ties;
+    return PCG_OK;
+}
+
+// ---- compose_network_volume on gridded volumes, column products ---------------------------------
+
+extern "C" int pcg_compose_volumes(int nradar, const double* const* volumes, const double* const* quality,
+                                   const double* weight2d, int method, int nz, int nx, int ny, double fill,
+                                   double* composite, int16_t* valid_count) {
+    if (nradar < 1) return fail(PCG_ERR_ARG, "radar_volumes must contain at least one volume.");
+    if (nradar > kComposeMaxRadars) return fail(PCG_ERR_ARG, "at most %d radar volumes per call", kComposeMaxRadars);
+    if (method < 0 || method > 3) return fail(PCG_ERR_ARG, "Unsupported composite_method code %d", method);
+    if (nx < 0 || ny < 0 || nz < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
+    if (method != 0 && !weight2d) return fail(PCG_ERR_ARG, "weight2d is required for this method");
+    if (!volumes || !composite) return fail(PCG_ERR_ARG, "NULL pointer");
+    const size_t ncol = (size_t)nx * (size_t)ny, nvox = ncol * (size_t)nz;
+    if (nvox == 0) return PCG_OK;
+    int rc;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    const bool has_q = (method == 3) && quality;
+    if ((rc = g_scratch[S_AUX4].ensure((size_t)nradar * nvox * sizeof(double)))) return rc;
+    if (has_q && (rc = g_scratch[S_IDX].ensure((size_t)nradar * nvox * sizeof(double)))) return rc;
+    if (weight2d && (rc = g_scratch[S_AUX3].ensure((size_t)nradar * ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_OUT].ensure(nvox * sizeof(double)))) return rc;
+    if (valid_count && (rc = g_scratch[S_AUX0].ensure(nvox * sizeof(int16_t)))) return rc;
+    ComposeArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int r = 0; r < nradar; ++r) {
+        if (!volumes[r] || (has_q && !quality[r])) return fail(PCG_ERR_ARG, "NULL volume pointer (radar %d)", r);
+        double* dv = (double*)g_scratch[S_AUX4].ptr + (size_t)r * nvox;
+        CUDA_TRY(cudaMemcpyAsync(dv, volumes[r], nvox * sizeof(double), cudaMemcpyHostToDevice, st));
+        A.vol[r] = dv;
+        if (has_q) {
+            double* dq = (double*)g_scratch[S_IDX].ptr + (size_t)r * nvox;
+            CUDA_TRY(cudaMemcpyAsync(dq, quality[r], nvox * sizeof(double), cudaMemcpyHostToDevice, st));
+            A.qual[r] = dq;
+        }
+    }
+    if (weight2d) {
+        CUDA_TRY(cudaMemcpyAsync(g_scratch[S_AUX3].ptr, weight2d, (size_t)nradar * ncol * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+        A.w2d = (const double*)g_scratch[S_AUX3].ptr;
+    }
+    A.nradar = nradar; A.method = method; A.has_quality = has_q ? 1 : 0;
+    A.ncol = (long long)ncol; A.nvox = (long long)nvox; A.fill = fill;
+    A.out = (double*)g_scratch[S_OUT].ptr;
+    A.count = valid_count ? (int16_t*)g_scratch[S_AUX0].ptr : nullptr;
+    const unsigned blocks = (unsigned)((nvox + 255) / 256 < 148 * 32 ? (nvox + 255) / 256 : 148 * 32);
+    compose_kernel<<<blocks, 256, 0, st>>>(A);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(composite, A.out, nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (valid_count) CUDA_TRY(cudaMemcpyAsync(valid_count, A.count, nvox * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+namespace {
+int enqueue_columns(const double* d_vol, const double* d_levels, int nz, long long ncol, double fill, double min_dbz,
+                    double max_dbz_cap, double threshold, double* d_cr, double* d_vil, double* d_et,
+                    unsigned char* d_topped, cudaStream_t st) {
+    ColumnArgs A;
+    A.vol = d_vol; A.levels = d_levels; A.nz = nz; A.ncol = ncol; A.fill = fill;
+    A.min_dbz = min_dbz; A.max_dbz_cap = max_dbz_cap; A.threshold = threshold;
+    A.cr = d_cr; A.vil = d_vil; A.et = d_et; A.topped = d_topped;
+    const unsigned blocks = (unsigned)((ncol + 255) / 256 < 148 * 32 ? (ncol + 255) / 256 : 148 * 32);
+    column_kernel<<<blocks, 256, 0, st>>>(A);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return PCG_OK;
+}
+}  // namespace
+
+extern "C" int pcg_column_products_dev(const double* d_volume, const double* d_levels, int nz, int nx, int ny,
+                                       double fill, double min_dbz, double max_dbz_cap, double threshold_dbz,
+                                       double* d_cr, double* d_vil, double* d_et, unsigned char* d_topped,
+                                       void* stream) {
+    if (nx < 0 || ny < 0 || nz < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
+    if ((size_t)nx * ny == 0) return PCG_OK;
+    return enqueue_columns(d_volume, d_levels, nz, (long long)nx * ny, fill, min_dbz, max_dbz_cap, threshold_dbz, d_cr,
+                           d_vil, d_et, d_topped, (cudaStream_t)stream);
+}
+
+extern "C" int pcg_column_products(const double* volume, const double* level_heights, int nz, int nx, int ny,
+                                   double fill, double min_dbz, double max_dbz_cap, double threshold_dbz, double* cr,
+                                   double* vil, double* et, unsigned char* topped) {
+    if (nx < 0 || ny < 0 || nz < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
+    const size_t ncol = (size_t)nx * (size_t)ny, nvox = ncol * (size_t)nz;
+    if (ncol == 0) return PCG_OK;
+    int rc;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    if ((rc = g_scratch[S_OUT].ensure((nvox ? nvox : 1) * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_TMP0].ensure((size_t)(nz ? nz : 1) * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_AUX3].ensure(3 * ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_AUX2].ensure(ncol))) return rc;
+    if (nvox) CUDA_TRY(cudaMemcpyAsync(g_scratch[S_OUT].ptr, volume, nvox * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nz) CUDA_TRY(cudaMemcpyAsync(g_scratch[S_TMP0].ptr, level_heights, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, st));
+    double* d3 = (double*)g_scratch[S_AUX3].ptr;
+    rc = enqueue_columns((const double*)g_scratch[S_OUT].ptr, (const double*)g_scratch[S_TMP0].ptr, nz, (long long)ncol,
+                         fill, min_dbz, max_dbz_cap, threshold_dbz, cr ? d3 : nullptr, vil ? d3 + ncol : nullptr,
+                         et ? d3 + 2 * ncol : nullptr, topped ? (unsigned char*)g_scratch[S_AUX2].ptr : nullptr, st);
+    if (rc) return rc;
+    if (cr) CUDA_TRY(cudaMemcpyAsync(cr, d3, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (vil) CUDA_TRY(cudaMemcpyAsync(vil, d3 + ncol, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (et) CUDA_TRY(cudaMemcpyAsync(et, d3 + 2 * ncol, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (topped) CUDA_TRY(cudaMemcpyAsync(topped, g_scratch[S_AUX2].ptr, ncol, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+// ---- stand-alone observability mask / quality weight volume --------------------------------------
+
+extern "C" int pcg_network_gates(int ne, const double* fix_elev, const double* first_gate, const double* last_gate,
+                                 const double* beam_widths, double radar_height, double effective_earth_radius,
+                                 double radar_x, double radar_y, const double* grid_x, const double* grid_y, int nx,
+                                 int ny, const double* level_heights, int nz, int quality_terms, double range_decay_m,
+                                 double beam_radius_ref_m, double vertical_gap_ref_deg, unsigned char* mask,
+                                 double* quality) {
+    if (!(effective_earth_radius > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
+    if (ne < 0 || nx < 0 || ny < 0 || nz < 0) return fail(PCG_ERR_ARG, "sizes must be non-negative");
+    const size_t ncol = (size_t)nx * (size_t)ny, nvox = ncol * (size_t)nz;
+    if (nvox == 0) return PCG_OK;
+    if (ne == 0) {                                   // RadarInterp.py:555-556 / 625-626
+        if (mask) memset(mask, 0, nvox);
+        if (quality) for (size_t i = 0; i < nvox; ++i) quality[i] = 0.0;
+        return PCG_OK;
+    }
+    const int npair = ne > 1 ? ne - 1 : 1;
+    std::vector<GateSweep> sw(ne);
+    std::vector<NetPair> pr(npair);
+    std::vector<double> btan(npair), gap(npair);
+    std::vector<NetLevel> lv(nz);
+    for (int k = 0; k < ne; ++k) { sw[k].elev = fix_elev[k]; sw[k].r_first = first_gate[k]; sw[k].r_last = last_gate[k]; }
+    memset(pr.data(), 0, pr.size() * sizeof(NetPair));
+    if (ne == 1) {
+        btan[0] = tan((beam_widths ? beam_widths[0] : 1.0) * kDeg2Rad * 0.5);
+        gap[0] = 0.0;
+    }
+    for (int k = 0; k + 1 < ne; ++k) {
+        pr[k].obs_first = first_gate[k] > first_gate[k + 1] ? first_gate[k] : first_gate[k + 1];
+        pr[k].obs_last = last_gate[k] < last_gate[k + 1] ? last_gate[k] : last_gate[k + 1];
+        const double rep = 0.5 * ((beam_widths ? beam_widths[k] : 1.0) + (beam_widths ? beam_widths[k + 1] : 1.0));
+        btan[k] = tan(rep * kDeg2Rad * 0.5);         // np.tan(np.deg2rad(rep) * 0.5)
+        gap[k] = 0.5 * (fix_elev[k + 1] - fix_elev[k]);
+    }
+    volatile double av = effective_earth_radius + radar_height;
+    const double a2_np = pow((double)av, 2.0);
+    volatile double twoa = 2.0 * av;
+    for (int k = 0; k < nz; ++k) {
+        memset(&lv[k], 0, sizeof(NetLevel));
+        const double g = effective_earth_radius + level_heights[k];
+        lv[k].g2_np = pow(g, 2.0);
+        lv[k].a2g2_np = a2_np + lv[k].g2_np;
+        volatile double tg = twoa * g;
+        lv[k].twoag_np = tg;
+    }
+    int rc;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    const size_t b_sw = sw.size() * sizeof(GateSweep), b_pr = pr.size() * sizeof(NetPair),
+                 b_d = (size_t)npair * sizeof(double), b_lv = lv.size() * sizeof(NetLevel);
+    if ((rc = g_scratch[S_NET].ensure(b_sw + b_pr + 2 * b_d + b_lv + 64))) return rc;
+    if ((rc = g_scratch[S_GX].ensure(ncol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_GY].ensure(ncol * sizeof(double)))) return rc;
+    if (mask && (rc = g_scratch[S_AUX2].ensure(nvox))) return rc;
+    if (quality && (rc = g_scratch[S_AUX4].ensure(nvox * sizeof(double)))) return rc;
+    char* base = (char*)g_scratch[S_NET].ptr;
+    CUDA_TRY(cudaMemcpyAsync(base, sw.data(), b_sw, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(base + b_sw, pr.data(), b_pr, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(base + b_sw + b_pr, btan.data(), b_d, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(base + b_sw + b_pr + b_d, gap.data(), b_d, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(base + b_sw + b_pr + 2 * b_d, lv.data(), b_lv, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    GatesArgs A;
+    memset(&A, 0, sizeof(A));
+    A.sweeps = (const GateSweep*)base;
+    A.pairs = (const NetPair*)(base + b_sw);
+    A.beam_tan = (const double*)(base + b_sw + b_pr);
+    A.gap_half = (const double*)(base + b_sw + b_pr + b_d);
+    A.levels = (const NetLevel*)(base + b_sw + b_pr + 2 * b_d);
+    A.ne = ne; A.nz = nz;
+    A.gx = (const double*)g_scratch[S_GX].ptr; A.gy = (const double*)g_scratch[S_GY].ptr; A.ncol = (long long)ncol;
+    A.radar_x = radar_x; A.radar_y = radar_y; A.Re = effective_earth_radius; A.a2_np = a2_np; A.twoa = twoa;
+    double half = (beam_widths ? beam_widths[0] : 1.0) * 0.5;     // RadarInterp.py:573 / 653
+    A.beam_half = half < 0.1 ? 0.1 : half;
+    A.terms = quality_terms; A.range_decay = range_decay_m; A.beam_ref = beam_radius_ref_m; A.gap_ref = vertical_gap_ref_deg;
+    A.mask = mask ? (unsigned char*)g_scratch[S_AUX2].ptr : nullptr;
+    A.quality = quality ? (double*)g_scratch[S_AUX4].ptr : nullptr;
+    gates_kernel<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(A);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    if (mask) CUDA_TRY(cudaMemcpyAsync(mask, A.mask, nvox, cudaMemcpyDeviceToHost, st));
+    if (quality) CUDA_TRY(cudaMemcpyAsync(quality, A.quality, nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return PCG_OK;
 }

@@ -291,6 +291,84 @@ __global__ void __launch_bounds__(kNetThreads) network_kernel(const __grid_const
     if (ties && p.tie_count) atomicAdd(p.tie_count, ties);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// gates_kernel — _compute_observability_mask (RadarInterp.py:540-600) and
+// _compute_quality_weight_volume (:603-696) as stand-alone functions: the NumPy-twin chain
+// (transforms.py:201-222) restated in FP64 for every voxel, any sweep count (including the
+// single-sweep beam-width gate).  Needs only the range-table ends and the fixed elevations.
+// ---------------------------------------------------------------------------------------------
+struct GateSweep { double elev, r_first, r_last; };
+
+struct GatesArgs {
+    const GateSweep* sweeps;      // [ne]
+    const NetPair* pairs;         // [ne-1]: obs_first/last; beam_k, vert_w unused (double versions below)
+    const double* beam_tan;       // [max(ne-1,1)]: tan(deg2rad(representative_beam) * 0.5)
+    const double* gap_half;       // [max(ne-1,1)]
+    const NetLevel* levels;       // [nz]
+    int ne, nz;
+    const double* gx;
+    const double* gy;
+    long long ncol;
+    double radar_x, radar_y, Re, a2_np, twoa;
+    double beam_half;             // single sweep: max(bw/2, 0.1)
+    int terms;                    // kTerm* bits
+    double range_decay, beam_ref, gap_ref;
+    unsigned char* mask;          // [nz][ncol] or NULL
+    double* quality;              // [nz][ncol] or NULL
+};
+
+__global__ void __launch_bounds__(256) gates_kernel(const __grid_constant__ GatesArgs p) {
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= p.ncol) return;
+    const double x = sub(p.gx[col], p.radar_x), y = sub(p.gy[col], p.radar_y);
+    const double cphi = cos_small(div(hypot_cr(x, y), p.Re));
+    const int ne = p.ne;
+    for (int iz = 0; iz < p.nz; ++iz) {
+        const NetLevel& L = p.levels[iz];
+        double r2 = sub(L.a2g2_np, mul(L.twoag_np, cphi));
+        if (!(r2 > 0.0)) r2 = (r2 != r2) ? r2 : 0.0;
+        const double r = sqrt_rn(r2);
+        const double c0 = div(sub(add(p.a2_np, mul(r, r)), L.g2_np), mul(p.twoa, r));
+        bool obs = (c0 == c0) && (r == r);
+        int pair = 0;
+        if (obs) {
+            const double c = c0 > 1.0 ? 1.0 : (c0 < -1.0 ? -1.0 : c0);
+            const double el = div(mul(sub(acos(c), kHalfPi), 180.0), kPi);
+            if (ne == 1) {
+                obs = (fabs(sub(el, p.sweeps[0].elev)) <= p.beam_half) && (r >= p.sweeps[0].r_first) &&
+                      (r <= p.sweeps[0].r_last);
+            } else {
+                obs = (el >= p.sweeps[0].elev) && (el <= p.sweeps[ne - 1].elev);
+                if (obs) {
+                    int lo = 0, hi = ne;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (el < p.sweeps[mid].elev) hi = mid; else lo = mid + 1; }
+                    pair = (lo < 1 ? 1 : (lo > ne - 1 ? ne - 1 : lo)) - 1;
+                    obs = (r >= p.pairs[pair].obs_first) && (r <= p.pairs[pair].obs_last);
+                }
+            }
+        }
+        const size_t o = (size_t)iz * (size_t)p.ncol + (size_t)col;
+        if (p.mask) p.mask[o] = obs ? 1 : 0;
+        if (p.quality) {
+            double w = 0.0;
+            if (obs) {
+                w = 1.0;
+                if (p.terms & kTermRange) { const double t = div(r, p.range_decay); w = mul(w, exp(-mul(t, t))); }
+                if (p.terms & kTermBeam) {
+                    const double b = div(mul(r, p.beam_tan[pair]), p.beam_ref);
+                    w = mul(w, div(1.0, add(1.0, mul(b, b))));
+                }
+                if ((p.terms & kTermVertical) && ne > 1) {
+                    const double gq = div(p.gap_half[pair], p.gap_ref);
+                    w = mul(w, div(1.0, add(1.0, mul(gq, gq))));
+                }
+            }
+            p.quality[o] = w;
+        }
+    }
+}
+
 // min / max / count of the valid (finite, != fill) source values of one sweep tile: the window of
 // the range-sanity filter (RadarInterp.py:1003-1007).  Doubles are ordered through their bit
 // patterns (sign-flipped) so unsigned atomics implement min / max.
