@@ -193,6 +193,137 @@ def run_reference(args):
     return 0
 
 
+
+# --------------------------------------------------------------------------------------------
+# network composite (BASELINE config C4): 32 radars -> 3000 x 3000 x 30, row slabs over the ranks
+# --------------------------------------------------------------------------------------------
+
+def bench_network(args, torch, dist, dev, rank, world):
+    """Fused network kernel on this rank's row slab (inputs resident in HBM), then the NCCL gather
+    of the finished composite slabs.  Returns the `network` object of the JSON line (rank 0)."""
+    import ctypes
+
+    from pycwr_b200 import _lib, sharding, synth
+    from pycwr_b200.runtime import DeviceVolume
+
+    import numpy as _np
+    # sites / grid first (cheap); volumes only for the radars that reach this rank's slab
+    meta = synth.network_config(style="stress", scale=args.network_scale, nradar=args.network_radars,
+                                with_volumes=False)
+    gx_h, gy_h, levels = meta["GridX"], meta["GridY"], meta["levels"]
+    sites = _np.stack([meta["radar_x"], meta["radar_y"]], axis=1)
+    sites_cfg = {"alt": meta["radar_alt"]}
+    nlat, nlon = gx_h.shape
+    nz = int(levels.size)
+    bounds = sharding.slab_bounds(nlat, world)
+    r0, r1 = bounds[rank]
+    reach = [460e3 * 1.002 / 0.999 + 1000.0] * len(sites)
+    mine = sharding.radars_reaching(gx_h[r0:r1], gy_h[r0:r1], sites, reach)
+    vols, heights, bws = [], [], []
+    for k in mine:
+        v = synth.make_volume(synth.BASE_SEED + 104 + k, fields=("dBZ",), style="stress",
+                              radar_height=sites_cfg["alt"][k])
+        vols.append(DeviceVolume(v["vol_azimuth"], v["vol_range"], v["fix_elevation"], v["vol_value"]["dBZ"],
+                                 fillvalue=FILL, value_dtype="f32"))
+        heights.append(v["radar_height"])
+        bws.append(_np.ascontiguousarray(v["beam_widths"]))
+        del v
+    n = len(mine)
+    rows = r1 - r0
+    gx = torch.from_numpy(gx_h[r0:r1]).to(dev)
+    gy = torch.from_numpy(gy_h[r0:r1]).to(dev)
+    comp = torch.empty((nz, rows, nlon), dtype=torch.float64, device=dev)
+    cov = torch.empty((nz, rows, nlon), dtype=torch.int16, device=dev)
+    blind = torch.empty((nz, rows, nlon), dtype=torch.int8, device=dev)
+    cr = torch.empty((rows, nlon), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+    prm = _lib.NetworkParams(_lib.NET_METHODS["quality_weighted"], 3, 7, 1, 300000.0, 230000.0, 3000.0, 0.5)
+    handles = (ctypes.c_void_p * max(n, 1))(*[v.handle for v in vols])
+    rx = _np.ascontiguousarray(sites[mine, 0]) if n else _np.zeros(1)
+    ry = _np.ascontiguousarray(sites[mine, 1]) if n else _np.zeros(1)
+    rh = _np.ascontiguousarray(_np.array(heights, dtype=_np.float64)) if n else _np.zeros(1)
+    re = _np.full(max(n, 1), 8494666.6666666661)
+    bwp = (_lib.c_double_p * max(n, 1))(*[b.ctypes.data_as(_lib.c_double_p) for b in bws]) if n else None
+    dp = _lib.c_double_p
+
+    def launch():
+        if n == 0 or rows == 0:
+            return
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.pcg_network_compose_dev(
+            n, handles, rx.ctypes.data_as(dp), ry.ctypes.data_as(dp), rh.ctypes.data_as(dp), re.ctypes.data_as(dp),
+            bwp, ctypes.byref(prm), gx.data_ptr(), gy.data_ptr(), rows, nlon, levels.ctypes.data_as(dp), nz, FILL,
+            comp.data_ptr(), None, cov.data_ptr(), blind.data_ptr(), cr.data_ptr(), None, st))
+
+    steps = max(2, min(args.steps, 5))
+    for _ in range(3):
+        launch()
+        flush.zero_()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    l0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        launch()
+        b.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    # gather of the finished composite slabs (NCCL all_gather, padded slabs), timed on the device
+    gather_ms = 0.0
+    if dist is not None:
+        maxrows = max(b[1] - b[0] for b in bounds)
+        padded = torch.zeros((nz, maxrows, nlon), dtype=torch.float64, device=dev)
+        padded[:, :rows] = comp
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(steps):
+            dist.all_gather(parts, padded)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = float(g0.elapsed_time(g1))
+        t = torch.tensor([ms, gather_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, gather_ms = float(t[0].item()), float(t[1].item())
+        del parts, padded
+    nrad = torch.tensor([n], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(nrad, op=dist.ReduceOp.SUM)
+    voxels = nz * nlat * nlon
+    valid_frac = float((comp != FILL).double().mean().item()) if rows else 0.0
+    for v in vols:
+        v.close()
+    del comp, cov, blind, cr, flush
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, _ = read_peaks()
+    # algorithmic bytes (SURVEY.md 8d, network): composite + coverage + blind per voxel, grid + CR per
+    # column, every radar volume once
+    balg = voxels * (8 + 2 + 1) + nlat * nlon * (16 + 8) + args.network_radars * 8 * 9 * 366 * 1840
+    kern_s = ms * 1e-3 / steps
+    return {
+        "workload": "C4_network_%dr_%dx%dx%d" % (args.network_radars, nlat, nlon, nz),
+        "value": voxels * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+        "value_with_gather": voxels * steps / ((ms + gather_ms) * 1e-3), "gather_ms_per_step": gather_ms / steps,
+        "n_gpus": world, "scaling": "strong", "partition": "row slabs of the output grid, radars culled per slab",
+        "collective": "all_gather of finished composite slabs (NCCL)" if world > 1 else "none",
+        "radars_per_rank_mean": float(nrad.item()) / world, "composite_method": "quality_weighted",
+        "blind_method": "hybrid", "style": "stress", "gpu_launches": int(launches),
+        "valid_fraction_rank0": valid_frac,
+        "roofline": {"bound": "hbm", "achieved": balg / kern_s / 1e9, "peak": peak * world, "unit": "GB/s",
+                     "frac": balg / kern_s / 1e9 / (peak * world), "algorithmic_bytes": int(balg),
+                     "kernel": "pcg::network_kernel<3>"},
+    }
+
 # --------------------------------------------------------------------------------------------
 # product arm
 # --------------------------------------------------------------------------------------------
@@ -340,6 +471,14 @@ def run_product(args):
     h2d = 8 * nfield * dv.nvalues + dv.table_bytes + 16 * nx * ny
     d2h = 8 * voxels
 
+    # free the single-radar buffers before the network leg
+    del out, flush
+    dv.close()
+    torch.cuda.empty_cache()
+    net = None
+    if args.network:
+        net = bench_network(args, torch, dist, dev, rank, world)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -382,6 +521,8 @@ def run_product(args):
                      "kernel_ms": kern_ms},
         "cpu_baseline": cpu,
     }
+    if net is not None:
+        line["network"] = net
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -402,6 +543,11 @@ def main():
                     help="levels of the full grid timed on 1 host core (40 = all of C3, about 11 s)")
     ap.add_argument("--ref-levels", type=int, default=2, help="levels per worker for --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--network", dest="network", action="store_true", default=True,
+                    help="also run the C4 network composite sharded over the ranks (default)")
+    ap.add_argument("--no-network", dest="network", action="store_false")
+    ap.add_argument("--network-radars", type=int, default=32)
+    ap.add_argument("--network-scale", type=float, default=1.0, help="1.0 = 3000 x 3000 x 30")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -266,14 +266,16 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
                     method="quality_weighted", influence_radius_m=300000.0, blind_method="hybrid",
                     quality_weight_terms=("range", "beam", "vertical"), range_decay_m=230000.0,
                     beam_radius_ref_m=3000.0, vertical_gap_ref_deg=0.5, beam_widths=None, effective_earth_radius=None,
-                    sanity_filter=True, outputs=("valid_count", "coverage_count", "blind_mask", "CR"), rows=None):
+                    sanity_filter=True, outputs=("valid_count", "coverage_count", "blind_mask", "CR"), rows=None,
+                    allow_empty=False):
     """All radars of one field merged in one fused kernel launch.
 
     ``volumes``: packed :class:`DeviceVolume` per radar (field 0 is used).  ``rows=(r0, r1)``
     restricts the work to a row slab of the grid (multi-GPU sharding); the returned arrays then
     have ``r1 - r0`` rows.  Returns a dict with ``composite`` and the requested ``outputs``
     (``valid_count`` int16, ``coverage_count`` int16, ``blind_mask`` int8, ``CR`` with NaN where
-    no echo, ``quality`` = weight of the last radar) plus ``tie_voxels``.
+    no echo, ``quality`` = weight of the last radar) plus ``tie_voxels``.  ``allow_empty``: an empty
+    radar list (a slab no radar reaches) yields the all-fill result instead of the reference's error.
     """
     method = _check_method(method)
     gx = _f64_2d(grid_x, "grid_x")
@@ -287,7 +289,21 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
     levels = np.ascontiguousarray(np.asarray(level_heights, dtype=np.float64).ravel())
     n = len(volumes)
     if n == 0:
-        raise ValueError("radar_volumes must contain at least one volume.")
+        if not allow_empty:
+            raise ValueError("radar_volumes must contain at least one volume.")
+        shape = (int(levels.size),) + gx.shape
+        want = set(outputs or ())
+        res = {"composite": np.full(shape, float(fillvalue)), "tie_voxels": 0}
+        if "valid_count" in want:
+            res["valid_count"] = np.zeros(shape, dtype=np.int16)
+        if "coverage_count" in want or "blind_mask" in want:
+            res["coverage_count"] = np.zeros(shape, dtype=np.int16)
+            res["blind_mask"] = np.ones(shape, dtype=np.int8)
+        if "CR" in want:
+            res["CR"] = np.full(gx.shape, np.nan)
+        if "quality" in want:
+            res["quality"] = np.zeros(shape)
+        return res
     sites = np.asarray(radar_sites_xy, dtype=np.float64).reshape(n, 2)
     rx = np.ascontiguousarray(sites[:, 0])
     ry = np.ascontiguousarray(sites[:, 1])

@@ -1,0 +1,107 @@
+"""Multi-GPU sharding of the network composite: one process per GPU, the output
+grid split into contiguous ROW slabs, no data-path collective until the finished slabs are gathered.
+
+Every output voxel depends only on read-only radar volumes, so rank ``r`` runs the fused network
+kernel over rows ``[r0, r1)`` of the grid with the radars whose range disc can reach that slab and
+owns its slab of ``composite``, ``coverage_count``, ``blind_mask`` and ``CR``.  The only exchange is
+``gather_slabs`` (``torch.distributed.all_gather`` — NCCL over NVLink on the GPU box, gloo in the
+CPU tests).  The reference's counterpart is the fork pool over radars
+(``pycwr/interp/RadarInterp.py:1816-1861``), which returns whole per-radar volumes through pipes.
+"""
+import numpy as np
+
+
+def slab_bounds(nrows, world):
+    """Balanced contiguous row slabs: ``[(r0, r1)] * world`` (empty slabs when world > nrows)."""
+    nrows, world = int(nrows), int(world)
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    base, extra = divmod(nrows, world)
+    bounds, r0 = [], 0
+    for r in range(world):
+        r1 = r0 + base + (1 if r < extra else 0)
+        bounds.append((r0, r1))
+        r0 = r1
+    return bounds
+
+
+def radar_reach_m(vol_range, margin=1.002, extra_m=1000.0):
+    """Ground distance beyond which no gate of the radar can be reached (slant range >= 0.999 x
+    ground distance for |z|, |h| << Re; the kernel applies the same cull per block)."""
+    return max(float(r[-1]) for r in vol_range) * margin / 0.999 + extra_m
+
+
+def radars_reaching(grid_x, grid_y, sites_xy, reach_m):
+    """Indices of the radars whose disc of radius ``reach_m[i]`` intersects the bounding box of the
+    (slab of the) grid — conservative, so dropping the others cannot change any output."""
+    gx = np.asarray(grid_x)
+    gy = np.asarray(grid_y)
+    if gx.size == 0:
+        return []
+    x0, x1, y0, y1 = float(gx.min()), float(gx.max()), float(gy.min()), float(gy.max())
+    keep = []
+    for i, (sx, sy) in enumerate(np.asarray(sites_xy, dtype=np.float64)):
+        dx = max(x0 - sx, 0.0, sx - x1)
+        dy = max(y0 - sy, 0.0, sy - y1)
+        if dx * dx + dy * dy <= float(reach_m[i]) ** 2:
+            keep.append(i)
+    return keep
+
+
+def gather_slabs(local, bounds, dist=None, group=None, device=None):
+    """All-gather row slabs of an array whose axis -2 is the sharded row axis ((nz, rows, ny) volumes
+    or (rows, ny) planes).  ``local`` is this rank's slab (numpy or torch); returns the full numpy
+    array on every rank.  Slabs may have different row counts: they are padded to the largest."""
+    import torch
+
+    if dist is None:
+        import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if isinstance(local, torch.Tensor):
+        t = local.contiguous()
+        np_dtype = np.dtype(str(t.dtype).replace("torch.", ""))
+    else:
+        arr = np.ascontiguousarray(local)
+        np_dtype = arr.dtype
+        t = torch.from_numpy(arr)
+    # transported as bytes along the last axis: every dtype (int16 / int8 included) works on NCCL and gloo
+    t = t.view(torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    rows = [b[1] - b[0] for b in bounds]
+    if t.shape[-2] != rows[rank]:
+        raise ValueError("local slab has %d rows, expected %d" % (t.shape[-2], rows[rank]))
+    maxrows = max(rows)
+    pad_shape = list(t.shape)
+    pad_shape[-2] = maxrows
+    padded = torch.zeros(pad_shape, dtype=t.dtype, device=t.device)
+    padded[..., : rows[rank], :] = t
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    full = torch.cat([p[..., : rows[r], :] for r, p in enumerate(parts)], dim=-2)
+    return np.ascontiguousarray(full.cpu().numpy()).view(np_dtype)
+
+
+def network_compose_sharded(compute, grid_x, grid_y, sites_xy, reach_m, dist=None, group=None, device=None,
+                            keys=("composite", "valid_count", "coverage_count", "blind_mask", "CR"), gather=True):
+    """Run ``compute(rows, radar_indices) -> dict`` on this rank's slab and gather the results.
+
+    ``compute`` is the per-slab worker (``pycwr_b200.interp.network_compose`` bound to its
+    volumes on the GPU box).  Returns ``(result, (r0, r1), radar_indices)``; with ``gather`` the
+    result holds full-grid arrays on every rank, otherwise this rank's slab only."""
+    if dist is None:
+        import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    bounds = slab_bounds(np.asarray(grid_x).shape[0], world)
+    r0, r1 = bounds[rank]
+    radars = radars_reaching(np.asarray(grid_x)[r0:r1], np.asarray(grid_y)[r0:r1], sites_xy, reach_m)
+    local = compute((r0, r1), radars)
+    if not gather:
+        return local, (r0, r1), radars
+    out = {}
+    for key in keys:
+        if key in local:
+            out[key] = gather_slabs(np.asarray(local[key]), bounds, dist=dist, group=group, device=device)
+    return out, (r0, r1), radars

@@ -193,7 +193,7 @@ def config(cid, style="stress", scale=1.0, nradar=None):
 
 
 def network_config(style="storm", scale=1.0, nradar=32, nlon=3000, nlat=3000, nz=30,
-                   share_volume=False):
+                   share_volume=False, with_volumes=True):
     """C4: ``nradar`` S-band sites on a jittered 4x8 lattice in 100-130E / 20-50N, 0.01 deg grid.
 
     ``scale`` shrinks the number of grid points (coarser resolution over the same domain).
@@ -219,7 +219,7 @@ def network_config(style="storm", scale=1.0, nradar=32, nlon=3000, nlat=3000, nz
     gx, gy = aeqd_forward(glon, glat, lon_0, lat_0)
     volumes = []
     base = None
-    for k, (slon, slat, alt) in enumerate(sites):
+    for k, (slon, slat, alt) in enumerate(sites if with_volumes else []):
         if share_volume and base is not None:
             vol = dict(base)
             vol["radar_height"] = alt
@@ -234,6 +234,7 @@ def network_config(style="storm", scale=1.0, nradar=32, nlon=3000, nlat=3000, nz
             "volumes": volumes, "fields": ["dBZ"], "lon": lon, "lat": lat,
             "GridX": np.ascontiguousarray(gx), "GridY": np.ascontiguousarray(gy),
             "radar_x": np.asarray(sx, dtype=np.float64), "radar_y": np.asarray(sy, dtype=np.float64),
+            "radar_alt": np.array([s[2] for s in sites], dtype=np.float64),
             "levels": levels, "blind_method": "hybrid", "composite_method": "quality_weighted",
             "max_range_km": 460.0, "influence_radius_m": 300000.0,
             "quality_weight_terms": ["range", "beam", "vertical", "qc", "blockage"]}
