@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpycwr_b200.so")
+# PYCWR_B200_LIB selects another build of the same library (kernel tuning variants)
+LIB_PATH = os.environ.get("PYCWR_B200_LIB") or os.path.join(_HERE, "libpycwr_b200.so")
 
 PCG_OK, PCG_ERR_ARG, PCG_ERR_CUDA, PCG_ERR_NOMEM = 0, -1, -2, -3
 IDX_STRIDE = 10

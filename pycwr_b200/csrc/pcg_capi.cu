@@ -18,6 +18,7 @@
 #include "../../include/pycwr_b200.h"
 #include "pcg_fast.cuh"
 #include "pcg_kernels.cuh"
+#include "pcg_r2.cuh"
 #include "pcg_network.cuh"
 #include "pcg_products.cuh"
 
@@ -99,7 +100,20 @@ struct pcg_volume {
     void* d_val[kMaxFields] = {nullptr, nullptr, nullptr, nullptr};
     SweepDesc* d_sweeps = nullptr;
     PairDesc* d_pairs = nullptr;     // [ne-1], packed (F32) volumes only
+    FastSweep* d_fs = nullptr;       // [ne]   r2-space descriptors (packed volumes only)
+    double2* d_gt = nullptr;         // gate thresholds in r2 space, same offsets as the range arena
+    GateAux* d_ht = nullptr;
+    // last (height, Re, levels) threshold table: rebuilt only when the call geometry changes
+    mutable std::mutex ls_mutex;
+    mutable std::vector<double> ls_key;
+    mutable LevelSweep* d_ls = nullptr;
+    mutable std::vector<unsigned char> ls_slow;
+    bool uniform = false;            // one range table shared by every sweep, every sweep / pair usable + validated
+    unsigned uni_rng_off = 0;
+    int uni_ngm1 = 0;
+    float uni_inv_step = 0.f, uni_c0 = 0.f;
     std::vector<SweepDesc> sweeps;
+    std::vector<PairDesc> pairs;     // host copy of d_pairs (the network path rescales it per call)
     double fill = -999.0;            // the missing-value marker the moments were packed with
     size_t bytes = 0;
     // valid (finite, != fill) source values per moment: the range-sanity window of the network path
@@ -214,23 +228,148 @@ void fit_pair(PairDesc* pr, double e0, double e1, double c0, double c1) {
     if (worst <= 1e-9L) pr->flags |= kPairPolyOk;
 }
 
-template <int NF, bool EMIT>
-int launch_fast_one(const FastArgs& args, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+
+// ---- r2-space tables (pcg_r2.cuh) ----------------------------------------------------------------
+
+// smallest double t with sqrt(t) >= R  (r >= R  <=>  r2 >= t: the IEEE square root is monotone)
+double sqrt_threshold_ge(double R) {
+    if (!(R > 0.0)) return 0.0;
+    volatile double t = R * R;
+    while (sqrt((double)t) >= R) t = nextafter((double)t, -HUGE_VAL);
+    while (sqrt((double)t) < R) t = nextafter((double)t, HUGE_VAL);
+    return t;
+}
+
+// smallest double t with sqrt(t) > R   (r <= R  <=>  r2 < t)
+double sqrt_threshold_gt(double R) {
+    if (!(R >= 0.0)) return 0.0;
+    volatile double t = R * R;
+    while (sqrt((double)t) > R) t = nextafter((double)t, -HUGE_VAL);
+    while (!(sqrt((double)t) > R)) t = nextafter((double)t, HUGE_VAL);
+    return t;
+}
+
+// w(u) = (el(C_k + u) - e_k) / (e_{k+1} - e_k), el(c) = -asin(c) in degrees, as u * (q1 + .. + q5 u^4):
+// interpolated at Chebyshev nodes in long double, validated with the float-rounded coefficients.
+bool fit_pair_r2(FastSweep* f, double e0, double e1) {
+    const long double pi = 3.14159265358979323846264338327950288L;
+    const long double c0 = -sinl((long double)e0 * pi / 180.0L), c1 = -sinl((long double)e1 * pi / 180.0L);
+    if (!(e1 > e0) || !(c0 > c1)) return false;
+    const long double span = (c1 - c0);                 // < 0
+    auto wfun = [&](long double u) -> long double {
+        long double c = c0 + u;
+        if (c > 1.0L) c = 1.0L;
+        if (c < -1.0L) c = -1.0L;
+        return (-asinl(c) * 180.0L / pi - (long double)e0) / ((long double)e1 - (long double)e0);
+    };
+    const int n = 5;
+    long double A[n][n + 1];
+    for (int j = 0; j < n; ++j) {
+        // nodes t in (0, 1.02): u = t * span
+        const long double t = 0.51L * (1.0L + cosl((2 * j + 1) * pi / (2 * n)));
+        long double pw = 1.0L;
+        for (int i = 0; i < n; ++i) { A[j][i] = pw; pw *= t; }
+        A[j][n] = wfun(t * span) / (t * span);
+    }
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r) if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+        for (int k = 0; k <= n; ++k) { long double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const long double g = A[r][c] / A[c][c];
+            for (int k = c; k <= n; ++k) A[r][k] -= g * A[c][k];
+        }
+    }
+    float q[n];
+    long double sp = 1.0L;
+    for (int i = 0; i < n; ++i) { q[i] = (float)(A[i][n] / A[i][i] / sp); sp *= span; }
+    long double worst = 0.0L;
+    for (int j = 0; j <= 256; ++j) {
+        const long double u = span * 1.01L * j / 256.0L;
+        long double v = 0.0L;
+        for (int i = n - 1; i >= 0; --i) v = v * u + (long double)q[i];
+        v *= u;
+        const long double e = fabsl(v - wfun(u));
+        if (e > worst) worst = e;
+    }
+    f->q1 = q[0]; f->q2 = q[1]; f->q3 = q[2]; f->q4 = q[3]; f->q5 = q[4];
+    return worst <= 1e-7L;
+}
+
+// Per (level, sweep) thresholds for one radar: ls[(nz)][ne + 2], flags in slow_bits (bit per level).
+void build_level_sweeps(const pcg_volume* v, double Re, double av, const double* levels, int nz,
+                        LevelSweep* ls, std::vector<unsigned char>* slow) {
+    const int ne = v->ne;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    const long double a = (long double)av;
+    slow->assign(nz, 0);
+    long double cmax = -2.0L;                                  // C_k = -sin(e_k) of the LOWEST sweep
+    for (int k = 0; k < ne; ++k) {
+        const long double ck = -sinl((long double)v->sweeps[k].elev * pi / 180.0L);
+        if (ck > cmax) cmax = ck;
+    }
+    const double inf = HUGE_VAL;
+    for (int iz = 0; iz < nz; ++iz) {
+        LevelSweep* row = ls + (size_t)iz * (ne + 2);
+        memset(row, 0, sizeof(LevelSweep) * (ne + 2));
+        row[0].t_lo = inf; row[0].t_hi = inf;                  // "sweep -1": always el >= e_-1, never below it
+
+        row[ne + 1].t_lo = -inf; row[ne + 1].t_hi = -inf;      // "sweep ne": never reached
+        volatile double gd = Re + levels[iz];                  // the reference's gate radius
+        const long double g = (long double)gd;
+        if (g > a) {
+            const long double D = (g - a) * (g + a) / (2.0L * a);
+            for (int k = 0; k < ne; ++k) {
+                const long double e = (long double)v->sweeps[k].elev * pi / 180.0L;
+                const long double se = sinl(e), ce = cosl(e);
+                const long double rho = -a * se + sqrtl((g - a * ce) * (g + a * ce));
+                LevelSweep& L = row[k + 1];
+                if (!(rho > 0.0L) || !(fabsl(e) < 1.55L)) { (*slow)[iz] = 1; continue; }
+                const long double rho2 = rho * rho;
+                // bound on |r2_ref-equivalent - r2_exact| at the decision point: see pcg_r2.cuh
+                const long double margin = 0.25L + 1e-7L * rho + 1e-14L * rho2;
+                L.t_lo = nextafter((double)(rho2 - margin), -HUGE_VAL);
+                L.t_hi = nextafter((double)(rho2 + margin), HUGE_VAL);
+                L.rho2 = (double)rho2;
+                L.rho = (float)rho;
+                L.b1 = (float)(D / rho);
+            }
+        } else {
+            // level at or below the antenna: el <= 0 everywhere; if the lowest sweep is clearly above the
+            // largest reachable elevation every voxel is "below the lowest sweep", else take the slow chain
+            const long double d2 = (a - g) * (a + g);
+            const long double cmin = sqrtl(d2 > 0.0L ? d2 : 0.0L) / a;
+            if (cmin - cmax > 1e-6L) {
+                for (int k = 0; k < ne; ++k) { row[k + 1].t_lo = -1.0; row[k + 1].t_hi = -1.0; }
+            } else {
+                (*slow)[iz] = 1;
+            }
+        }
+    }
+}
+
+template <int NF, bool EMIT, bool UNI>
+int launch_fast_one(const R2Args& args, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024)   // opt in to large dynamic shared memory (per device, cheap)
-        CUDA_TRY(cudaFuncSetAttribute(cappi3d_fast_kernel<NF, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(cappi3d_r2_kernel<NF, EMIT, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-    cappi3d_fast_kernel<NF, EMIT><<<grid, block, smem, st>>>(args);
+    cappi3d_r2_kernel<NF, EMIT, UNI><<<grid, block, smem, st>>>(args);
     return PCG_OK;
 }
 
 template <bool EMIT>
-int launch_fast_nf(const FastArgs& args, int nf, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+int launch_fast_nf(const R2Args& args, int nf, bool uni, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
     int rc;
-    switch (nf) {
-        case 1: rc = launch_fast_one<1, EMIT>(args, grid, block, smem, st); break;
-        case 2: rc = launch_fast_one<2, EMIT>(args, grid, block, smem, st); break;
-        case 3: rc = launch_fast_one<3, EMIT>(args, grid, block, smem, st); break;
-        case 4: rc = launch_fast_one<4, EMIT>(args, grid, block, smem, st); break;
+    switch (nf * 2 + (uni ? 1 : 0)) {
+        case 2: rc = launch_fast_one<1, EMIT, false>(args, grid, block, smem, st); break;
+        case 3: rc = launch_fast_one<1, EMIT, true>(args, grid, block, smem, st); break;
+        case 4: rc = launch_fast_one<2, EMIT, false>(args, grid, block, smem, st); break;
+        case 5: rc = launch_fast_one<2, EMIT, true>(args, grid, block, smem, st); break;
+        case 6: rc = launch_fast_one<3, EMIT, false>(args, grid, block, smem, st); break;
+        case 7: rc = launch_fast_one<3, EMIT, true>(args, grid, block, smem, st); break;
+        case 8: rc = launch_fast_one<4, EMIT, false>(args, grid, block, smem, st); break;
+        case 9: rc = launch_fast_one<4, EMIT, true>(args, grid, block, smem, st); break;
         default: return fail(PCG_ERR_ARG, "nfield must be 1..%d", kMaxFields);
     }
     if (rc != PCG_OK) return rc;
@@ -246,8 +385,9 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     if (!(fill == vol->fill))
         return fail(PCG_ERR_ARG, "fillvalue %.17g differs from the value the volume was packed with (%.17g)",
                     fill, vol->fill);
-    FastArgs A;
-    memset(&A, 0, sizeof(A));
+    R2Args RA;
+    memset(&RA, 0, sizeof(RA));
+    FastArgs& A = RA.base;
     A.vol = view_of(vol);
     A.pairs = vol->d_pairs;
     A.grid.gx = d_gx; A.grid.gy = d_gy; A.grid.ncol = ncol;
@@ -263,26 +403,62 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     A.highest_sweep = (blind_code == 4);
     A.merge_max = merge_max;
     A.field_stride = (unsigned long long)nz * (unsigned long long)ncol;
-    // shared memory: descriptors + the per-thread azimuth table [sweep][thread]; pick the block
+    // r2-space thresholds of this (radar height, level set): built on the host, stream-ordered upload
+    const int ne = vol->ne;
+    std::vector<unsigned char> slow;
+    LevelSweep* d_ls = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(vol->ls_mutex);
+        std::vector<double> key;
+        key.reserve(nz + 3);
+        key.push_back(h); key.push_back(Re); key.push_back((double)nz);
+        key.insert(key.end(), levels, levels + nz);
+        if (!vol->d_ls || key.size() != vol->ls_key.size() ||
+            memcmp(key.data(), vol->ls_key.data(), key.size() * sizeof(double)) != 0) {
+            std::vector<LevelSweep> ls((size_t)nz * (ne + 2));
+            build_level_sweeps(vol, Re, av, levels, nz, ls.data(), &vol->ls_slow);
+            LevelSweep* fresh = nullptr;
+            CUDA_TRY(cudaMalloc((void**)&fresh, ls.size() * sizeof(LevelSweep)));
+            cudaError_t e = cudaMemcpy(fresh, ls.data(), ls.size() * sizeof(LevelSweep), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(fresh); return fail(PCG_ERR_CUDA, "threshold upload failed: %s", cudaGetErrorString(e)); }
+            cudaFree(vol->d_ls);          // waits for kernels still reading the previous table
+            vol->d_ls = fresh;
+            vol->ls_key.swap(key);
+        }
+        d_ls = vol->d_ls;
+        slow = vol->ls_slow;
+    }
+    RA.r2.fs = vol->d_fs;
+    RA.r2.g_t = vol->d_gt;
+    RA.r2.h_t = vol->d_ht;
+    RA.r2.inv2a = (float)(1.0 / twoa);
+    RA.r2.u_rng_off = vol->uni_rng_off; RA.r2.u_ngm1 = vol->uni_ngm1;
+    RA.r2.u_inv_step = vol->uni_inv_step; RA.r2.u_c0 = vol->uni_c0;
+    // shared memory: descriptors + the per-thread azimuth table [thread][sweep]; pick the block
     // size so that several blocks still fit an SM (227 KB)
-    const size_t fixed = (size_t)vol->ne * sizeof(SweepDesc) + (size_t)(vol->ne - 1) * sizeof(PairDesc);
+    const size_t fixed = (size_t)vol->ne * (sizeof(SweepDesc) + sizeof(FastSweep)) + (size_t)(vol->ne - 1) * sizeof(PairDesc);
     const size_t per_thread = (size_t)vol->ne * (sizeof(AzEntry) + (d_idx ? sizeof(int) : 0));
     int threads = 256;
     while (threads > 32 && fixed + per_thread * threads > 56 * 1024) threads >>= 1;
     const size_t smem = fixed + per_thread * threads;
     const dim3 block(threads);
     const dim3 grid((unsigned)((ncol + threads - 1) / threads));
-    for (int z0 = 0; z0 < nz; z0 += kMaxLevelsPerLaunch) {
+    int rc = PCG_OK;
+    for (int z0 = 0; z0 < nz && rc == PCG_OK; z0 += kMaxLevelsPerLaunch) {
         const int cnt = (nz - z0 < kMaxLevelsPerLaunch) ? nz - z0 : kMaxLevelsPerLaunch;
         A.nz = cnt;
-        for (int k = 0; k < cnt; ++k) fill_level(&A.levels[k], levels[z0 + k], Re, a2, twoa);
+        RA.level_slow = 0;
+        for (int k = 0; k < cnt; ++k) {
+            fill_level(&A.levels[k], levels[z0 + k], Re, a2, twoa);
+            if (slow[z0 + k]) RA.level_slow |= 1ull << k;
+        }
+        RA.r2.ls = d_ls + (size_t)z0 * (ne + 2);
         A.out = d_out + (size_t)z0 * (size_t)ncol;
         A.idx = d_idx ? d_idx + (size_t)z0 * (size_t)ncol * kIdxStride : nullptr;
-        const int rc = d_idx ? launch_fast_nf<true>(A, nfield, grid, block, smem, st)
-                             : launch_fast_nf<false>(A, nfield, grid, block, smem, st);
-        if (rc != PCG_OK) return rc;
+        rc = d_idx ? launch_fast_nf<true>(RA, nfield, vol->uniform, grid, block, smem, st)
+                   : launch_fast_nf<false>(RA, nfield, vol->uniform, grid, block, smem, st);
     }
-    return PCG_OK;
+    return rc;
 }
 
 int enqueue_cappi(const pcg_volume* vol, double h, double Re, const double* d_gx, const double* d_gy,
@@ -468,6 +644,7 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         d.tan_e = tan(fix_elev[s] * kDeg2Rad);     // RadarGridC.pyx:110,113 (host glibc)
         d.cthr = -sin(fix_elev[s] * kDeg2Rad);     // cos(pi/2 + el): elevation threshold in cosine space
         d.sorted = 1;
+        d.sec_e = (float)(1.0 / cos(fix_elev[s] * kDeg2Rad));
         if (s > 0 && !(fix_elev[s - 1] <= fix_elev[s])) strict = false;   // packer sorts by fixed angle
         if (naz[s] > 0) {
             d.az_first = az[s][0];
@@ -606,6 +783,63 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
             if (d0.rng_off == d1.rng_off && d0.ng == d1.ng && d0.naz >= 2 && d1.naz >= 2 && d0.ng >= 2)
                 pairs[k].flags |= kPairShared;
         }
+        v->pairs = pairs;
+        {   // r2-space descriptors: gate thresholds per range table, per-sweep / per-pair constants
+            std::vector<double2> gt(n_rng ? n_rng : 1);
+            std::vector<GateAux> ht(n_rng ? n_rng : 1);
+            std::vector<FastSweep> fs(ne);
+            memset(fs.data(), 0, fs.size() * sizeof(FastSweep));
+            for (int s = 0; s < ne; ++s) {
+                const SweepDesc& d = v->sweeps[s];
+                FastSweep& f = fs[s];
+                f.rng_off = d.rng_off;
+                f.ngm1 = d.ng - 1;
+                f.inv_step = (float)d.rng_inv_step;
+                f.c0 = (float)(1.0 - d.r_first * d.rng_inv_step);
+                if (d.naz >= 2 && d.ng >= 2) f.flags |= kFsUsable;
+                if (d.ng > 0) {
+                    f.tg_first = sqrt_threshold_ge(d.r_first);
+                    f.tg_gt_last = sqrt_threshold_gt(d.r_last);
+                }
+                if (rng_owner[s] == s) {
+                    double prev = d.ng > 0 ? sqrt_threshold_ge(rng[s][0]) : 0.0;
+                    for (int j = 0; j < d.ng; ++j) {
+                        // interval j serves r in [R[j], R[j+1]); the last usable one (j = ng-2) extends to
+                        // r <= R[ng-1], the reference's clamp of the gate index (RadarGridC.pyx:291-295)
+                        const double next = (j + 2 < d.ng) ? sqrt_threshold_ge(rng[s][j + 1]) : f.tg_gt_last;
+                        gt[d.rng_off + j] = make_double2(prev, next);
+                        GateAux& hA = ht[d.rng_off + j];
+                        volatile double rs = rng[s][j] * rng[s][j];
+                        hA.rsq = rs;
+                        hA.r = (float)rng[s][j];
+                        hA.inv_dr = (j + 1 < d.ng) ? (float)(1.0 / (rng[s][j + 1] - rng[s][j])) : 0.f;
+                        prev = next;
+                    }
+                }
+                if (s + 1 < ne) {
+                    const SweepDesc& d1 = v->sweeps[s + 1];
+                    if (fit_pair_r2(&f, d.elev, d1.elev)) f.flags |= kFsPolyOk;
+                    if (d.rng_off == d1.rng_off && d.ng == d1.ng && d.naz >= 2 && d1.naz >= 2 && d.ng >= 2)
+                        f.flags |= kFsShared;
+                }
+            }
+            bool uni = ne >= 2;
+            for (int s = 0; s < ne && uni; ++s) {
+                const int need = (s + 1 < ne) ? (kFsPolyOk | kFsShared | kFsUsable) : kFsUsable;
+                if ((fs[s].flags & need) != need || fs[s].rng_off != fs[0].rng_off || fs[s].ngm1 != fs[0].ngm1) uni = false;
+            }
+            v->uniform = uni;
+            v->uni_rng_off = fs[0].rng_off; v->uni_ngm1 = fs[0].ngm1;
+            v->uni_inv_step = fs[0].inv_step; v->uni_c0 = fs[0].c0;
+            VOL_TRY(cudaMalloc((void**)&v->d_fs, fs.size() * sizeof(FastSweep)));
+            VOL_TRY(cudaMalloc((void**)&v->d_gt, gt.size() * sizeof(double2)));
+            VOL_TRY(cudaMalloc((void**)&v->d_ht, ht.size() * sizeof(GateAux)));
+            VOL_TRY(cudaMemcpyAsync(v->d_fs, fs.data(), fs.size() * sizeof(FastSweep), cudaMemcpyHostToDevice, st));
+            VOL_TRY(cudaMemcpyAsync(v->d_gt, gt.data(), gt.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
+            VOL_TRY(cudaMemcpyAsync(v->d_ht, ht.data(), ht.size() * sizeof(GateAux), cudaMemcpyHostToDevice, st));
+            VOL_TRY(cudaStreamSynchronize(st));      // the host vectors die with this block
+            v->bytes += fs.size() * sizeof(FastSweep) + gt.size() * sizeof(double2) + ht.size() * sizeof(GateAux);
+        }
         VOL_TRY(cudaMalloc((void**)&v->d_pairs, pairs.size() * sizeof(PairDesc)));
         VOL_TRY(cudaMemcpyAsync(v->d_pairs, pairs.data(), pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
         v->bytes += pairs.size() * sizeof(PairDesc);
@@ -637,6 +871,10 @@ int pcg_volume_destroy(pcg_volume* v) {
     cudaFree(v->d_rng);
     cudaFree(v->d_sweeps);
     cudaFree(v->d_pairs);
+    cudaFree(v->d_fs);
+    cudaFree(v->d_ls);
+    cudaFree(v->d_gt);
+    cudaFree(v->d_ht);
     for (int f = 0; f < kMaxFields; ++f) cudaFree(v->d_val[f]);
     delete v;
     return PCG_OK;
@@ -915,6 +1153,7 @@ struct NetHostTables {
     std::vector<NetRadar> radars;
     std::vector<NetPair> npairs;
     std::vector<NetLevel> levels;
+    std::vector<PairDesc> pairs;     // per radar, thresholds scaled by 2a
 };
 
 int launch_network(const NetArgs& a, int method, dim3 grid, size_t smem, cudaStream_t st) {
@@ -975,6 +1214,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     size_t npair_total = 0;
     for (int i = 0; i < nradar; ++i) npair_total += (size_t)(vols[i]->ne - 1);
     T.npairs.resize(npair_total);
+    T.pairs.resize(npair_total);
     T.levels.resize((size_t)nradar * nz);
     double zmin = levels[0];
     for (int k = 1; k < nz; ++k) zmin = levels[k] < zmin ? levels[k] : zmin;
@@ -982,10 +1222,12 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     const size_t bytes_radars = sizeof(NetRadar) * (size_t)nradar;
     const size_t bytes_pairs = sizeof(NetPair) * npair_total;
     const size_t bytes_levels = sizeof(NetLevel) * T.levels.size();
-    if ((rc = g_scratch[S_NET].ensure(bytes_radars + bytes_pairs + bytes_levels + 64))) return rc;
+    const size_t bytes_spairs = sizeof(PairDesc) * npair_total;
+    if ((rc = g_scratch[S_NET].ensure(bytes_radars + bytes_pairs + bytes_levels + bytes_spairs + 64))) return rc;
     char* d_base = (char*)g_scratch[S_NET].ptr;
     const NetPair* d_pairs = (const NetPair*)(d_base + bytes_radars);
     const NetLevel* d_levels = (const NetLevel*)(d_base + bytes_radars + bytes_pairs);
+    const PairDesc* d_spairs = (const PairDesc*)(d_base + bytes_radars + bytes_pairs + bytes_levels);
 
     size_t poff = 0;
     for (int i = 0; i < nradar; ++i) {
@@ -993,7 +1235,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
         NetRadar& R = T.radars[i];
         memset(&R, 0, sizeof(R));
         R.vol = view_of(v);
-        R.pairs = v->d_pairs;
+        R.pairs = d_spairs + poff;
         R.npairs = d_pairs + poff;
         R.levels = d_levels + (size_t)i * nz;
         R.x = radar_x[i];
@@ -1042,6 +1284,10 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
             const double gap_half = 0.5 * (d1.elev - d0.elev);
             const double gq = gap_half / prm->vertical_gap_ref_deg;
             np.vert_w = (prm->quality_terms & kTermVertical) ? (float)(1.0 / (1.0 + gq * gq)) : 1.f;
+            PairDesc sp = v->pairs[k];          // what stage_pairs does for the single-radar kernel
+            volatile double s_lo = sp.c_lo * (double)twoa, s_hi = sp.c_hi * (double)twoa, s_mid = sp.c_mid * (double)twoa;
+            sp.c_lo = s_lo; sp.c_hi = s_hi; sp.c_mid = s_mid;
+            T.pairs[poff + k] = sp;
         }
         poff += (size_t)(v->ne - 1);
         for (int k = 0; k < nz; ++k) {
@@ -1059,6 +1305,9 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     if (bytes_pairs)
         CUDA_TRY(cudaMemcpyAsync(d_base + bytes_radars, T.npairs.data(), bytes_pairs, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_base + bytes_radars + bytes_pairs, T.levels.data(), bytes_levels, cudaMemcpyHostToDevice, st));
+    if (bytes_spairs)
+        CUDA_TRY(cudaMemcpyAsync(d_base + bytes_radars + bytes_pairs + bytes_levels, T.pairs.data(), bytes_spairs,
+                                 cudaMemcpyHostToDevice, st));
     // the host vectors die with this frame: make the uploads complete before returning
     CUDA_TRY(cudaStreamSynchronize(st));
 
@@ -1074,16 +1323,14 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     A.nearest_gate = (prm->blind_code == 1 || prm->blind_code == 3 || prm->blind_code == 4);
     A.lowest_sweep = (prm->blind_code == 2 || prm->blind_code == 3 || prm->blind_code == 4);
     A.highest_sweep = (prm->blind_code == 4);
-    size_t desc = (size_t)max_ne * sizeof(SweepDesc) + (size_t)(max_ne - 1) * (sizeof(PairDesc) + sizeof(NetPair)) +
-                  (size_t)kNetZC * sizeof(NetLevel);
-    desc = (desc + 15) & ~(size_t)15;
-    A.smem_desc_bytes = (int)desc;
+    A.smem_desc_bytes = 0;
     A.max_ne = max_ne;
     A.composite = d_comp; A.valid_count = d_valid; A.coverage = d_cov; A.blind = d_blind; A.cr = d_cr;
     A.quality_out = d_quality; A.tie_count = d_ties;
-    // descriptors + azimuth table [sweep][thread] + accumulators (2 float + 1 double per level and thread)
-    const size_t smem = desc + (size_t)max_ne * kNetThreads * sizeof(AzEntry) +
-                        (size_t)kNetZC * kNetThreads * (2 * sizeof(float) + sizeof(double));
+    // per-thread state: azimuth table [sweep][thread] + accumulators (2 float, 2 uint8, 1 double per level)
+    const size_t smem = (size_t)max_ne * kNetThreads * sizeof(AzEntry) +
+                        (size_t)kNetZC * kNetThreads *
+                            (2 * sizeof(float) + 2 + (prm->method == kNetNearest ? sizeof(double) : 0));
     const dim3 grid((unsigned)((ncol + kNetThreads - 1) / kNetThreads), (unsigned)((nz + kNetZC - 1) / kNetZC));
     return launch_network(A, prm->method, grid, smem, st);
 }

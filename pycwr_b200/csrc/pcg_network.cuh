@@ -27,7 +27,13 @@
 
 namespace pcg {
 
-constexpr int kNetZC = 8;            // levels per thread (register accumulators)
+#ifndef NET_ZC
+#define NET_ZC 16
+#endif
+#ifndef NET_MINB
+#define NET_MINB 6
+#endif
+constexpr int kNetZC = NET_ZC;       // levels per block (per-thread accumulators in shared memory)
 constexpr int kNetThreads = 128;
 constexpr int kNetMaxSweeps = 32;    // per radar, bounded by the shared-memory azimuth table
 
@@ -47,7 +53,7 @@ struct NetLevel {                    // per (radar, level) constants, host-evalu
 
 struct NetRadar {
     VolumeView vol;
-    const PairDesc* pairs;
+    const PairDesc* pairs;           // thresholds pre-scaled by 2a (this radar's height)
     const NetPair* npairs;
     const NetLevel* levels;          // [nz]
     double x, y;                     // site on the common grid (m)
@@ -123,31 +129,64 @@ __device__ __noinline__ bool twin_observable(double x, double y, const NetRadar&
 }
 
 template <int METHOD>
-__global__ void __launch_bounds__(kNetThreads) network_kernel(const __grid_constant__ NetArgs p) {
+__global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __grid_constant__ NetArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // descriptor area (re-staged per radar) followed by the per-thread azimuth table
-    AzEntry* s_az = reinterpret_cast<AzEntry*>(smem_raw + p.smem_desc_bytes);
+    // shared memory holds PER-THREAD state only ([row][thread] arrays, conflict free, never read by
+    // another thread), so the radar loop needs no barrier: the column's azimuth table of the current
+    // radar, and the per-level accumulators that keep the level loop rolled.
+    const unsigned T = blockDim.x;
+    AzEntry* my_az = reinterpret_cast<AzEntry*>(smem_raw) + threadIdx.x;                       // [max_ne][T]
+    float* acc_wv = reinterpret_cast<float*>(smem_raw + (size_t)p.max_ne * T * sizeof(AzEntry)) + threadIdx.x;
+    float* acc_w = acc_wv + (size_t)kNetZC * T;                                                // [kNetZC][T] each
+    unsigned char* cnt8 = reinterpret_cast<unsigned char*>(acc_wv - threadIdx.x + (size_t)2 * kNetZC * T) + threadIdx.x;
+    unsigned char* cov8 = cnt8 + (size_t)kNetZC * T;
+    double* best_d2 = reinterpret_cast<double*>(cnt8 - threadIdx.x + (size_t)2 * kNetZC * T) + threadIdx.x;  // nearest only
+    __shared__ double s_box[4];
 
-    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long col0 = (long long)blockIdx.x * T;
+    const long long col = col0 + threadIdx.x;
     const bool active = col < p.ncol;
     const int z0 = blockIdx.y * kNetZC;
     const int nzc = min(kNetZC, p.nz - z0);
     const bool do_cr = (p.cr != nullptr) && (blockIdx.y == 0);
     const float fill32 = p.fill32;
 
-    double gx = 0.0, gy = 0.0;
-    if (active) { gx = p.gx[col]; gy = p.gy[col]; }
+    // bounding box of the block's columns: one reduction, then every radar is culled block-uniformly
+    const long long lastc = min(col0 + (long long)T, p.ncol) - 1;
+    const long long cc = active ? col : lastc;
+    const double gx = p.gx[cc], gy = p.gy[cc];
+    {
+        double x0 = gx, x1 = gx, y0 = gy, y1 = gy;
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+            x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+            y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        double* s_red = reinterpret_cast<double*>(smem_raw);      // reused before any per-thread state is written
+        if ((threadIdx.x & 31) == 0) {
+            const int w = threadIdx.x >> 5;
+            s_red[4 * w] = x0; s_red[4 * w + 1] = x1; s_red[4 * w + 2] = y0; s_red[4 * w + 3] = y1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(T >> 5); ++w) {
+                x0 = fmin(x0, s_red[4 * w]); x1 = fmax(x1, s_red[4 * w + 1]);
+                y0 = fmin(y0, s_red[4 * w + 2]); y1 = fmax(y1, s_red[4 * w + 3]);
+            }
+            s_box[0] = x0; s_box[1] = x1; s_box[2] = y0; s_box[3] = y1;
+        }
+        __syncthreads();
+    }
+    const double bx0 = s_box[0], bx1 = s_box[1], by0 = s_box[2], by1 = s_box[3];
+    __syncthreads();          // s_red aliases the azimuth table
 
-    // per-thread accumulators live in shared memory ([level][thread], conflict free) so the level
-    // loop stays rolled: weighted: sum w*v, sum w;  max / nearest: chosen value, has-data flag
-    float* acc_wv = reinterpret_cast<float*>(s_az + (size_t)p.max_ne * blockDim.x) + threadIdx.x;
-    float* acc_w = acc_wv + (size_t)kNetZC * blockDim.x;
-    double* best_d2 = reinterpret_cast<double*>(acc_wv - threadIdx.x + (size_t)2 * kNetZC * blockDim.x) + threadIdx.x;
-    unsigned long long cnt = 0, cov = 0;       // valid_count / coverage_count, 8 bits per level
     for (int i = 0; i < kNetZC; ++i) {
-        acc_wv[i * blockDim.x] = 0.f;
-        acc_w[i * blockDim.x] = 0.f;
-        if (METHOD == kNetNearest) best_d2[i * blockDim.x] = __longlong_as_double(0x7ff0000000000000LL);
+        acc_wv[i * T] = 0.f;
+        acc_w[i * T] = 0.f;
+        cnt8[i * T] = 0;
+        cov8[i * T] = 0;
+        if (METHOD == kNetNearest) best_d2[i * T] = __longlong_as_double(0x7ff0000000000000LL);
         if (p.quality_out && active && i < nzc) p.quality_out[(size_t)(z0 + i) * (size_t)p.ncol + (size_t)col] = 0.0;
     }
     float cr_best = 0.f;
@@ -156,141 +195,151 @@ __global__ void __launch_bounds__(kNetThreads) network_kernel(const __grid_const
 
     for (int ir = 0; ir < p.nradar; ++ir) {
         const NetRadar& R = p.radars[ir];
+        {   // block-uniform cull: distance from the site to the block's bounding box
+            const double ddx = fmax(fmax(bx0 - R.x, R.x - bx1), 0.0);
+            const double ddy = fmax(fmax(by0 - R.y, R.y - by1), 0.0);
+            if (ddx * ddx + ddy * ddy > R.cull2) continue;
+        }
         // radar-local coordinates (RadarInterp.py:990-991) and the 2-D distance of the weight cache
         const double x = sub(gx, R.x), y = sub(gy, R.y);
         const double d2 = add(mul(x, x), mul(y, y));
-        const bool reach = active && (d2 <= R.cull2);
-        if (!__syncthreads_or(reach)) continue;
+        if (!active || !(d2 <= R.cull2)) continue;
 
         const int ne = R.ne;
-        SweepDesc* s_sw = reinterpret_cast<SweepDesc*>(smem_raw);
-        PairDesc* s_pr = reinterpret_cast<PairDesc*>(s_sw + ne);
-        NetPair* s_np = reinterpret_cast<NetPair*>(s_pr + (ne - 1));
-        NetLevel* s_lv = reinterpret_cast<NetLevel*>(s_np + (ne - 1));
-        stage_sweeps(s_sw, R.vol.sweeps, ne);
-        stage_pairs(s_pr, R.pairs, ne - 1, R.twoa);
-        for (int i = threadIdx.x; i < ne - 1; i += blockDim.x) s_np[i] = R.npairs[i];
-        for (int i = threadIdx.x; i < nzc; i += blockDim.x) s_lv[i] = R.levels[z0 + i];
-        __syncthreads();
-
-        if (reach) {
-            // column invariants of this radar (RadarGridC.pyx:142-146,158)
-            const double s = sqrt_rn(d2);
-            const double phi = div(s, R.Re);
-            const double cphi = cos_small(phi);
-            const double az = azimuth_from_xy(x, y);
-            column_azimuth_table<false>(s_sw, ne, R.vol.az, az, s_az + threadIdx.x, nullptr, blockDim.x);
-            ColumnCtx c;
-            c.s_sw = s_sw; c.s_pr = s_pr;
-            c.my_az = s_az + threadIdx.x; c.my_iaz = nullptr; c.az_stride = blockDim.x;
-            c.ne = ne;
-            c.rg_t = reinterpret_cast<const double2*>(R.vol.rng);
-            c.a2 = R.a2; c.twoa = R.twoa; c.guard = R.guard; c.inv_twoa = R.inv_twoa;
-            c.fill32 = fill32;
-            c.nearest_gate = p.nearest_gate != 0; c.lowest_sweep = p.lowest_sweep != 0;
-            c.highest_sweep = p.highest_sweep != 0;
-            // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
-            const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? expf(-(float)d2 * R.inv_r2inf4) : 1.f;
-
-            int k = 0;
-#pragma unroll 1
-            for (int i = 0; i < nzc; ++i) {
-                float res[1];
-                VoxelInfo vi;
-                fast_voxel<1, false>(c, R.vol.val, s_lv[i].cy, cphi, k, res, vi);
-                float v = res[0];
-                // range-sanity filter (RadarInterp.py:1003-1014), compared in double like the reference
-                if (p.sanity && v != fill32) {
-                    const double vd = (double)v;
-                    if (!(R.src_lo <= R.src_hi) || vd < R.src_lo || vd > R.src_hi) v = fill32;
-                }
-                const bool valid = (v != fill32) && (v == v) && (fabsf(v) != __int_as_float(0x7f800000));
-                // observability (RadarInterp.py:566-599 / 636-684)
-                const int kk = vi.lower < ne - 1 ? vi.lower : ne - 2;
-                const NetPair& np = s_np[vi.bracket == kPair ? kk : 0];
-                bool obs = (vi.bracket == kPair) && (vi.r >= np.obs_first) && (vi.r <= np.obs_last);
-                const double tol = mul(vi.r, 1e-12);
-                const bool near_gate = (vi.bracket == kPair) &&
-                                       ((fabs(sub(vi.r, np.obs_first)) <= tol) || (fabs(sub(vi.r, np.obs_last)) <= tol));
-                if (vi.tie || near_gate || !(vi.r > 0.0)) {
-                    obs = twin_observable(x, y, R, s_lv[i], s_sw, s_np, ne);
-                    ++ties;
-                }
-                float q = 0.f;
-                if (obs) {
-                    // RadarInterp.py:687-695
-                    const float rf = (float)vi.r;
-                    const float t = rf * R.inv_decay;
-                    const float b = rf * np.beam_k;
-                    q = expf(-t * t) * __frcp_rn(fmaf(b, b, 1.f)) * np.vert_w;
-                    cov += 1ull << (8 * i);
-                }
-                if (p.quality_out) p.quality_out[(size_t)(z0 + i) * (size_t)p.ncol + (size_t)col] = (double)q;
-                if (valid) {
-                    cnt += 1ull << (8 * i);
-                    float& awv = acc_wv[i * blockDim.x];
-                    float& aw = acc_w[i * blockDim.x];
-                    if (METHOD == kNetMax) {
-                        if (aw == 0.f || v > awv) awv = v;
-                        aw = 1.f;
-                    } else if (METHOD == kNetNearest) {
-                        double& bd = best_d2[i * blockDim.x];
-                        if (d2 < bd) { bd = d2; awv = v; aw = 1.f; }
-                    } else {
-                        const float w = (METHOD == kNetQuality && p.quality) ? w2d * q : w2d;
-                        awv = fmaf(w, v, awv);
-                        aw += w;
-                    }
-                }
+        const SweepDesc* s_sw = R.vol.sweeps;         // descriptor tables stay in global memory (L1-resident)
+        const NetPair* s_np = R.npairs;
+        const NetLevel* s_lv = R.levels + z0;
+        // column invariants of this radar (RadarGridC.pyx:142-146,158)
+        const double s = sqrt_rn(d2);
+        const double phi = div(s, R.Re);
+        const double cphi = cos_small(phi);
+        const double az = azimuth_from_xy(x, y);
+        column_azimuth_table<false>(s_sw, ne, R.vol.az, az, my_az, nullptr, T);
+#ifndef NET_NO_PREFETCH
+        {   // every level of this column samples sweep k within a few gates of where beam k passes over
+            // the column (slant range ~ s / cos e_k): warm those sectors now so that the level loop's
+            // gathers overlap instead of missing one after the other
+            const float sf = (float)s;
+            const float2* val = static_cast<const float2*>(R.vol.val[0]);
+            for (int sw = 0; sw < ne; ++sw) {
+                const SweepDesc& d = s_sw[sw];
+                const AzEntry e = my_az[(size_t)sw * T];
+                if (e.row == 0xffffffffu) continue;
+                const float rk = sf * d.sec_e;
+                int gi = __float2int_rd((rk - (float)d.r_first) * (float)d.rng_inv_step) + 1;
+                gi = min(max(gi, 1), d.ng - 1);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(val + e.row + gi));
             }
+        }
+#endif
+        ColumnCtx c;
+        c.s_sw = s_sw; c.s_pr = R.pairs;              // pair thresholds pre-scaled by 2a on the host
+        c.my_az = my_az; c.my_iaz = nullptr; c.az_stride = T;
+        c.ne = ne;
+        c.rg_t = reinterpret_cast<const double2*>(R.vol.rng);
+        c.a2 = R.a2; c.twoa = R.twoa; c.guard = R.guard; c.inv_twoa = R.inv_twoa;
+        c.fill32 = fill32;
+        c.nearest_gate = p.nearest_gate != 0; c.lowest_sweep = p.lowest_sweep != 0;
+        c.highest_sweep = p.highest_sweep != 0;
+        // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
+        const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? expf(-(float)d2 * R.inv_r2inf4) : 1.f;
 
-            if (do_cr) {
-                // get_CR_xy on the local grid: every sweep at its fixed elevation, blind "mask"
-                // (RadarGridC.pyx:596-624), then the NaN-aware max over radars (RadarInterp.py:2047-2063)
-                const double sphi = sin_small(phi);
-                const double2* rg_t = reinterpret_cast<const double2*>(R.vol.rng);
-                const float2* val = static_cast<const float2*>(R.vol.val[0]);
-                for (int ie = 0; ie < ne; ++ie) {
-                    const SweepDesc& d = s_sw[ie];
-                    if (d.naz < 2 || d.ng < 2) continue;
-                    const double denom = sub(cphi, mul(sphi, d.tan_e));
-                    if (denom == 0.0) continue;
-                    const double g = div(R.a, denom);
-                    double r2 = sub(add(R.a2, mul(g, g)), mul(mul(R.twoa, g), cphi));
-                    if (r2 < 0.0) r2 = 0.0;
-                    const double r = sqrt_rn(r2);
-                    if (r != r) continue;
-                    const RangeBracket rb = range_bracket(d, rg_t, r, false);
-                    const float v = sample_pairs(val, s_az[(size_t)ie * blockDim.x + threadIdx.x], rb, fill32);
-                    if (v == fill32 || v != v) continue;
-                    if (!cr_any || v > cr_best) cr_best = v;
-                    cr_any = true;
+        int k = 0;
+#pragma unroll 1
+        for (int i = 0; i < nzc; ++i) {
+            float res[1];
+            VoxelInfo vi;
+            fast_voxel<1, false>(c, R.vol.val, s_lv[i].cy, cphi, k, res, vi);
+            float v = res[0];
+            // range-sanity filter (RadarInterp.py:1003-1014), compared in double like the reference
+            if (p.sanity && v != fill32) {
+                const double vd = (double)v;
+                if (!(R.src_lo <= R.src_hi) || vd < R.src_lo || vd > R.src_hi) v = fill32;
+            }
+            const bool valid = (v != fill32) && (v == v) && (fabsf(v) != __int_as_float(0x7f800000));
+            // observability (RadarInterp.py:566-599 / 636-684)
+            const int kk = vi.lower < ne - 1 ? vi.lower : ne - 2;
+            const NetPair np = s_np[vi.bracket == kPair ? kk : 0];
+            bool obs = (vi.bracket == kPair) && (vi.r >= np.obs_first) && (vi.r <= np.obs_last);
+            const double tol = mul(vi.r, 1e-12);
+            const bool near_gate = (vi.bracket == kPair) &&
+                                   ((fabs(sub(vi.r, np.obs_first)) <= tol) || (fabs(sub(vi.r, np.obs_last)) <= tol));
+            if (vi.tie || near_gate || !(vi.r > 0.0)) {
+                obs = twin_observable(x, y, R, s_lv[i], s_sw, s_np, ne);
+                ++ties;
+            }
+            float q = 0.f;
+            if (obs) {
+                // RadarInterp.py:687-695
+                const float rf = (float)vi.r;
+                const float t = rf * R.inv_decay;
+                const float b = rf * np.beam_k;
+                q = expf(-t * t) * __frcp_rn(fmaf(b, b, 1.f)) * np.vert_w;
+                cov8[i * T] += 1;
+            }
+            if (p.quality_out) p.quality_out[(size_t)(z0 + i) * (size_t)p.ncol + (size_t)col] = (double)q;
+            if (valid) {
+                cnt8[i * T] += 1;
+                float& awv = acc_wv[i * T];
+                float& aw = acc_w[i * T];
+                if (METHOD == kNetMax) {
+                    if (aw == 0.f || v > awv) awv = v;
+                    aw = 1.f;
+                } else if (METHOD == kNetNearest) {
+                    double& bd = best_d2[i * T];
+                    if (d2 < bd) { bd = d2; awv = v; aw = 1.f; }
+                } else {
+                    const float w = (METHOD == kNetQuality && p.quality) ? w2d * q : w2d;
+                    awv = fmaf(w, v, awv);
+                    aw += w;
                 }
             }
         }
-        __syncthreads();     // the descriptor area is re-staged by the next radar
+
+        if (do_cr) {
+            // get_CR_xy on the local grid: every sweep at its fixed elevation, blind "mask"
+            // (RadarGridC.pyx:596-624), then the NaN-aware max over radars (RadarInterp.py:2047-2063)
+            const double sphi = sin_small(phi);
+            const double2* rg_t = reinterpret_cast<const double2*>(R.vol.rng);
+            const float2* val = static_cast<const float2*>(R.vol.val[0]);
+            for (int ie = 0; ie < ne; ++ie) {
+                const SweepDesc d = s_sw[ie];
+                if (d.naz < 2 || d.ng < 2) continue;
+                const double denom = sub(cphi, mul(sphi, d.tan_e));
+                if (denom == 0.0) continue;
+                const double g = div(R.a, denom);
+                double r2 = sub(add(R.a2, mul(g, g)), mul(mul(R.twoa, g), cphi));
+                if (r2 < 0.0) r2 = 0.0;
+                const double r = sqrt_rn(r2);
+                if (r != r) continue;
+                const RangeBracket rb = range_bracket(d, rg_t, r, false);
+                const float v = sample_pairs(val, my_az[(size_t)ie * T], rb, fill32);
+                if (v == fill32 || v != v) continue;
+                if (!cr_any || v > cr_best) cr_best = v;
+                cr_any = true;
+            }
+        }
     }
 
     if (!active) return;
     for (int i = 0; i < nzc; ++i) {
         const size_t o = (size_t)(z0 + i) * (size_t)p.ncol + (size_t)col;
-        const float awv = acc_wv[i * blockDim.x], aw = acc_w[i * blockDim.x];
+        const float awv = acc_wv[i * T], aw = acc_w[i * T];
         double out = p.fill;
         if (METHOD == kNetMax || METHOD == kNetNearest) {
             if (aw != 0.f) out = (double)awv;
         } else {
             if (aw > 0.f) out = (double)awv / (double)aw;            // has_data = total_weight > 0
         }
-        const unsigned c8 = (unsigned)(cov >> (8 * i)) & 0xffu;
+        const unsigned c8 = cov8[i * T];
         p.composite[o] = out;
-        if (p.valid_count) p.valid_count[o] = (int16_t)((unsigned)(cnt >> (8 * i)) & 0xffu);
+        if (p.valid_count) p.valid_count[o] = (int16_t)cnt8[i * T];
         if (p.coverage) p.coverage[o] = (int16_t)c8;
         if (p.blind) p.blind[o] = (int8_t)(c8 == 0u);
     }
     if (do_cr) p.cr[col] = cr_any ? (double)cr_best : __longlong_as_double(0x7ff8000000000000LL);
     if (ties && p.tie_count) atomicAdd(p.tie_count, ties);
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // gates_kernel — _compute_observability_mask (RadarInterp.py:540-600) and
