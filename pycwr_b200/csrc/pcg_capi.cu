@@ -103,6 +103,7 @@ struct pcg_volume {
     FastSweep* d_fs = nullptr;       // [ne]   r2-space descriptors (packed volumes only)
     double2* d_gt = nullptr;         // gate thresholds in r2 space, same offsets as the range arena
     GateAux* d_ht = nullptr;
+    double2* d_azt = nullptr;        // {A[i], 1 / gap_i} per ray, same offsets as the azimuth arena
     // last (height, Re, levels) threshold table: rebuilt only when the call geometry changes
     mutable std::mutex ls_mutex;
     mutable std::vector<double> ls_key;
@@ -379,7 +380,7 @@ int launch_fast_nf(const R2Args& args, int nf, bool uni, dim3 grid, dim3 block, 
 }
 
 int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double* d_gx, const double* d_gy,
-                       long long ncol, const double* levels, int nz, double fill, int blind_code,
+                       long long ncol, int ny, const double* levels, int nz, double fill, int blind_code,
                        double radar_x, double radar_y, int shift, int merge_max, double* d_out,
                        int32_t* d_idx, cudaStream_t st, int nfield) {
     if (!(fill == vol->fill))
@@ -392,6 +393,11 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     A.pairs = vol->d_pairs;
     A.grid.gx = d_gx; A.grid.gy = d_gy; A.grid.ncol = ncol;
     A.grid.radar_x = radar_x; A.grid.radar_y = radar_y; A.grid.shift = shift;
+    // warp footprint on the (nx, ny) grid: 4 rows x 8 columns when the grid is at least 4 rows tall (a compact
+    // patch touches fewer rays / gate lines per gather), else 1 x 32
+    const int nxg = (int)(ncol / (ny > 0 ? ny : 1));
+    A.grid.ny = ny; A.grid.nx = nxg;
+    A.grid.py_log2 = (nxg >= 4 && ny >= 8) ? 3 : 5;
     volatile double av = Re + h;
     volatile double a2 = av * av;
     volatile double twoa = 2.0 * av;
@@ -431,6 +437,7 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     RA.r2.fs = vol->d_fs;
     RA.r2.g_t = vol->d_gt;
     RA.r2.h_t = vol->d_ht;
+    RA.r2.az_t = vol->d_azt;
     RA.r2.inv2a = (float)(1.0 / twoa);
     RA.r2.u_rng_off = vol->uni_rng_off; RA.r2.u_ngm1 = vol->uni_ngm1;
     RA.r2.u_inv_step = vol->uni_inv_step; RA.r2.u_c0 = vol->uni_c0;
@@ -442,7 +449,13 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     while (threads > 32 && fixed + per_thread * threads > 56 * 1024) threads >>= 1;
     const size_t smem = fixed + per_thread * threads;
     const dim3 block(threads);
-    const dim3 grid((unsigned)((ncol + threads - 1) / threads));
+    // block tile: (warps/2 ... ) see cappi3d_r2_kernel: tile_y = 4 warps x PY columns, tile_x = rest
+    const int PY = 1 << A.grid.py_log2, PX = 32 / PY, warps = threads / 32;
+    const int wy = warps >= 4 ? 4 : warps, wx = warps / wy;
+    const long long tiles_y = (ny + (long long)wy * PY - 1) / ((long long)wy * PY);
+    const long long tiles_x = (nxg + (long long)wx * PX - 1) / ((long long)wx * PX);
+    A.grid.tiles_y = (int)tiles_y;
+    const dim3 grid((unsigned)(tiles_x * tiles_y));
     int rc = PCG_OK;
     for (int z0 = 0; z0 < nz && rc == PCG_OK; z0 += kMaxLevelsPerLaunch) {
         const int cnt = (nz - z0 < kMaxLevelsPerLaunch) ? nz - z0 : kMaxLevelsPerLaunch;
@@ -462,7 +475,7 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
 }
 
 int enqueue_cappi(const pcg_volume* vol, double h, double Re, const double* d_gx, const double* d_gy,
-                  long long ncol, const double* levels, int nz, double fill, int blind_code,
+                  long long ncol, int ny, const double* levels, int nz, double fill, int blind_code,
                   double beam_width_deg, double radar_x, double radar_y, int shift, int merge_max,
                   double* d_out, int32_t* d_idx, cudaStream_t st, int nfield_override = 0) {
     const int nfield = nfield_override > 0 ? nfield_override : vol->nfield;
@@ -474,7 +487,7 @@ int enqueue_cappi(const pcg_volume* vol, double h, double Re, const double* d_gx
     if (ncol == 0 || nz == 0) return PCG_OK;
     if (vol->ne > kMaxSweeps) return fail(PCG_ERR_ARG, "at most %d sweeps are supported", kMaxSweeps);
     if (vol->dtype == PCG_VALUE_F32)
-        return enqueue_cappi_fast(vol, h, Re, d_gx, d_gy, ncol, levels, nz, fill, blind_code, radar_x, radar_y,
+        return enqueue_cappi_fast(vol, h, Re, d_gx, d_gy, ncol, ny, levels, nz, fill, blind_code, radar_x, radar_y,
                                   shift, merge_max, d_out, d_idx, st, nfield);
     CappiArgs a;
     memset(&a, 0, sizeof(a));
@@ -688,9 +701,11 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
 
     // packed (fast) storage needs >= 2 sweeps and clean tables; anything else keeps the float64
     // layout and runs the kernels that restate the reference operation by operation.
-    const bool packed = (value_dtype == PCG_VALUE_F32) && ne >= 2 && ne <= 120 && strict && fits32;
+    // (the packed kernels widen float results back to double: the fill marker must survive the round trip)
+    const bool packed = (value_dtype == PCG_VALUE_F32) && ne >= 2 && ne <= 120 && strict && fits32 &&
+                        ((double)(float)fill == fill);
     v->dtype = packed ? PCG_VALUE_F32 : PCG_VALUE_F64;
-    const size_t vsz = sizeof(double);                       // float2 pair == 8 bytes as well
+    const size_t vsz = packed ? sizeof(float4) : sizeof(double);   // quad {A,B}[g-1], {A,B}[g] per (radial pair, gate)
     const size_t rsz = packed ? sizeof(double2) : sizeof(double);
 
     auto cleanup = [&]() { pcg_volume_destroy(v); };
@@ -752,7 +767,7 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
             if (packed) {
                 VOL_TRY(cudaMemcpyAsync(tmp, val[f][s], cnt * sizeof(double), cudaMemcpyHostToDevice, st));
                 const unsigned blocks = (unsigned)((cnt + 255) / 256 < 148 * 16 ? (cnt + 255) / 256 : 148 * 16);
-                pack_pairs_kernel<<<blocks, 256, 0, st>>>(tmp, (float2*)v->d_val[f] + d.val_off, d.naz, d.ng,
+                pack_quads_kernel<<<blocks, 256, 0, st>>>(tmp, (float4*)v->d_val[f] + d.val_off, d.naz, d.ng,
                                                           fill, (float)fill);
                 minmax_kernel<<<blocks, 256, 0, st>>>(tmp, cnt, fill, d_mm + 3 * f);
                 g_launches.fetch_add(2);
@@ -823,6 +838,17 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
                         f.flags |= kFsShared;
                 }
             }
+            std::vector<double2> azt(n_az ? n_az : 1);
+            for (int s = 0; s < ne; ++s) {
+                const SweepDesc& d = v->sweeps[s];
+                for (int i = 0; i < d.naz; ++i) {
+                    const double gap = (i + 1 < d.naz) ? az[s][i + 1] - az[s][i] : az[s][0] + 360.0 - az[s][i];
+                    azt[d.az_off + i] = make_double2(az[s][i], gap > 0.0 ? 1.0 / gap : 0.0);
+                }
+            }
+            VOL_TRY(cudaMalloc((void**)&v->d_azt, azt.size() * sizeof(double2)));
+            VOL_TRY(cudaMemcpy(v->d_azt, azt.data(), azt.size() * sizeof(double2), cudaMemcpyHostToDevice));
+            v->bytes += azt.size() * sizeof(double2);
             bool uni = ne >= 2;
             for (int s = 0; s < ne && uni; ++s) {
                 const int need = (s + 1 < ne) ? (kFsPolyOk | kFsShared | kFsUsable) : kFsUsable;
@@ -872,6 +898,7 @@ int pcg_volume_destroy(pcg_volume* v) {
     cudaFree(v->d_sweeps);
     cudaFree(v->d_pairs);
     cudaFree(v->d_fs);
+    cudaFree(v->d_azt);
     cudaFree(v->d_ls);
     cudaFree(v->d_gt);
     cudaFree(v->d_ht);
@@ -900,7 +927,7 @@ int pcg_get_cappi3d_dev(const pcg_volume* vol, double radar_height, double effec
     if (rc) return rc;
     const int shift = (radar_x != 0.0 || radar_y != 0.0 || merge_max) ? 1 : 0;
     return enqueue_cappi(vol, radar_height, resolve_re(effective_earth_radius), d_grid_x, d_grid_y,
-                         (long long)nx * ny, level_heights, nz, fill, blind_code, beam_width_deg,
+                         (long long)nx * ny, ny, level_heights, nz, fill, blind_code, beam_width_deg,
                          radar_x, radar_y, shift, merge_max, d_out, d_index_out, (cudaStream_t)stream);
 }
 
@@ -941,7 +968,7 @@ int pcg_get_cappi3d(const pcg_volume* vol, double radar_height, double effective
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
     rc = enqueue_cappi(vol, radar_height, effective_earth_radius, (const double*)g_scratch[S_GX].ptr,
-                       (const double*)g_scratch[S_GY].ptr, (long long)ncol, level_heights, nz, fill,
+                       (const double*)g_scratch[S_GY].ptr, (long long)ncol, ny, level_heights, nz, fill,
                        blind_code, beam_width_deg, 0.0, 0.0, 0, 0, (double*)g_scratch[S_OUT].ptr, d_idx, st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, g_scratch[S_OUT].ptr, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1047,7 +1074,7 @@ int pcg_get_mosaic_cappi3d(int nradar, const pcg_volume* const* vols, const doub
     for (int i = 0; i < nradar; ++i) {
         // get_mosaic_CAPPI_3d uses field 0 of each radar, blind "mask", default beam width
         rc = enqueue_cappi(vols[i], radar_height[i], effective_earth_radius[i], (const double*)g_scratch[S_GX].ptr,
-                           (const double*)g_scratch[S_GY].ptr, (long long)ncol, level_heights, nz, fill, 0,
+                           (const double*)g_scratch[S_GY].ptr, (long long)ncol, ny, level_heights, nz, fill, 0,
                            1.0, radar_x[i], radar_y[i], 1, i > 0 ? 1 : 0, (double*)g_scratch[S_OUT].ptr, nullptr,
                            st, 1);
         if (rc) return rc;

@@ -59,6 +59,9 @@ struct GridArgs {
     long long ncol;
     double radar_x, radar_y;         // local = grid - radar (RadarGridC.pyx:571-572)
     int shift;                       // apply the subtraction (0: use the grid as is)
+    int nx, ny;                      // grid shape (ny fastest); r2 kernel: 2-D warp footprints
+    int py_log2;                     // a warp covers 2^py_log2 consecutive columns of (32 >> py_log2) rows
+    int tiles_y;
 };
 
 constexpr int kMaxLevelsPerLaunch = 64;   // level constants travel in the kernel parameters

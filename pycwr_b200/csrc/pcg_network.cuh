@@ -215,23 +215,6 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __
         const double cphi = cos_small(phi);
         const double az = azimuth_from_xy(x, y);
         column_azimuth_table<false>(s_sw, ne, R.vol.az, az, my_az, nullptr, T);
-#ifndef NET_NO_PREFETCH
-        {   // every level of this column samples sweep k within a few gates of where beam k passes over
-            // the column (slant range ~ s / cos e_k): warm those sectors now so that the level loop's
-            // gathers overlap instead of missing one after the other
-            const float sf = (float)s;
-            const float2* val = static_cast<const float2*>(R.vol.val[0]);
-            for (int sw = 0; sw < ne; ++sw) {
-                const SweepDesc& d = s_sw[sw];
-                const AzEntry e = my_az[(size_t)sw * T];
-                if (e.row == 0xffffffffu) continue;
-                const float rk = sf * d.sec_e;
-                int gi = __float2int_rd((rk - (float)d.r_first) * (float)d.rng_inv_step) + 1;
-                gi = min(max(gi, 1), d.ng - 1);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(val + e.row + gi));
-            }
-        }
-#endif
         ColumnCtx c;
         c.s_sw = s_sw; c.s_pr = R.pairs;              // pair thresholds pre-scaled by 2a on the host
         c.my_az = my_az; c.my_iaz = nullptr; c.az_stride = T;
@@ -301,7 +284,7 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __
             // (RadarGridC.pyx:596-624), then the NaN-aware max over radars (RadarInterp.py:2047-2063)
             const double sphi = sin_small(phi);
             const double2* rg_t = reinterpret_cast<const double2*>(R.vol.rng);
-            const float2* val = static_cast<const float2*>(R.vol.val[0]);
+            const float4* val = static_cast<const float4*>(R.vol.val[0]);
             for (int ie = 0; ie < ne; ++ie) {
                 const SweepDesc d = s_sw[ie];
                 if (d.naz < 2 || d.ng < 2) continue;

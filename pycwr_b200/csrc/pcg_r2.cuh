@@ -52,6 +52,7 @@ struct R2Ctx {
     const FastSweep* fs;          // [ne]
     const double2* g_t;           // {tg[j], tg[j+1]} per gate (tg_gt_last at the end)
     const GateAux* h_t;
+    const double2* az_t;          // {A[i], 1 / (A[i+1] - A[i])} per ray, same offsets as the azimuth arena
     float inv2a;
     // UNI kernels: the one range table every sweep shares
     unsigned u_rng_off;
@@ -85,6 +86,56 @@ __device__ __noinline__ void slow_voxel(SlowFrame* fr, const void* const* val, d
     fast_voxel<NF, EMIT>(fr->c, val, fr->lc, cphi, fr->k6, tmp, fr->vi);
 #pragma unroll
     for (int f = 0; f < NF; ++f) res[f] = tmp[f];
+}
+
+// Azimuth bracket of every sweep for one column (RadarGridC.pyx:282-289) from the {A[i], 1 / gap_i}
+// table (gap_i = A[i+1] - A[i], the last entry holds the wrap interval A[0] + 360 - A[naz-1]): the
+// arithmetic guess is verified against the two entries it brackets and repaired by +-1 steps or the
+// reference's bisection, so iaz is exactly bisect_right; the FP32 weight is one multiply.
+template <bool EMIT>
+__device__ __forceinline__ void column_azimuth_table_r2(const SweepDesc* s_sw, int ne, const double2* __restrict__ azt,
+                                                        double az, AzEntry* my_az, int* my_iaz, unsigned stride) {
+#pragma unroll 1
+    for (int sw = 0; sw < ne; ++sw) {
+        const SweepDesc& d = s_sw[sw];
+        AzEntry e;
+        e.row = 0xffffffffu; e.w = 0.f;
+        int rec = -1;
+        const int naz = d.naz;
+        if (naz >= 2 && d.ng >= 2) {
+            const double2* T = azt + d.az_off;
+            int g = __double2int_rd(mul(sub(az, d.az_first), d.az_inv_step)) + 1;
+            g = min(max(g, 0), naz);
+            double2 lo = __ldg(T + max(g - 1, 0));
+            double hi = __ldg(&T[min(g, naz - 1)].x);
+            bool ok = false;
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                const bool lo_ok = (g == 0) | !(az < lo.x);
+                const bool hi_ok = (g == naz) | (az < hi);
+                if (lo_ok & hi_ok) { ok = true; break; }
+                g += lo_ok ? 1 : -1;
+                lo = __ldg(T + max(g - 1, 0));
+                hi = __ldg(&T[min(g, naz - 1)].x);
+            }
+            if (!ok) {                                   // irregular table: the reference's bisection
+                int l = 0, h = naz;
+                while (l < h) { const int m = (l + h) >> 1; if (az < __ldg(&T[m].x)) h = m; else l = m + 1; }
+                g = l;
+            }
+            const bool wrapped = g >= naz;
+            const int iaz = wrapped ? 0 : g;
+            const int row_lo = (iaz == 0) ? naz - 1 : iaz - 1;
+            if (!ok || iaz == 0) lo = __ldg(T + row_lo);
+            // (az - 360) - (A[naz-1] - 360) when wrapped, az - (A[naz-1] - 360) below the first ray
+            const double dlt = (iaz == 0 && !wrapped) ? sub(az, sub(lo.x, 360.0)) : sub(az, lo.x);
+            e.row = (unsigned)d.val_off + (unsigned)row_lo * (unsigned)d.ng;
+            e.w = (float)dlt * (float)lo.y;
+            rec = iaz | (wrapped ? (1 << 30) : 0);
+        }
+        my_az[(size_t)sw * stride] = e;
+        if (EMIT) my_iaz[(size_t)sw * stride] = rec;
+    }
 }
 
 // UNI: every sweep shares ONE range table and every sweep / pair is usable and poly-validated (the
@@ -167,12 +218,10 @@ __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, con
                 const AzEntry eb = az[c.az_stride];
 #pragma unroll
                 for (int fi = 0; fi < NF; ++fi) {
-                    const float2* v = static_cast<const float2*>(val[fi]);
-                    const float2* pa = v + (ea.row + (unsigned)gi);
-                    const float2* pb = v + (eb.row + (unsigned)gi);
-                    const float2 a0 = __ldg(pa - 1), a1 = __ldg(pa), b0 = __ldg(pb - 1), b1 = __ldg(pb);
-                    const float ea0 = fmaf(ea.w, a0.y - a0.x, a0.x), ea1 = fmaf(ea.w, a1.y - a1.x, a1.x);
-                    const float eb0 = fmaf(eb.w, b0.y - b0.x, b0.x), eb1 = fmaf(eb.w, b1.y - b1.x, b1.x);
+                    const float4* v = static_cast<const float4*>(val[fi]);
+                    const float4 qa4 = __ldg(v + (ea.row + (unsigned)gi)), qb4 = __ldg(v + (eb.row + (unsigned)gi));
+                    const float ea0 = fmaf(ea.w, qa4.y - qa4.x, qa4.x), ea1 = fmaf(ea.w, qa4.w - qa4.z, qa4.z);
+                    const float eb0 = fmaf(eb.w, qb4.y - qb4.x, qb4.x), eb1 = fmaf(eb.w, qb4.w - qb4.z, qb4.z);
                     const float v0 = lerp_fill(w_r, ea0, ea1, fill32);
                     const float v1 = lerp_fill(w_r, eb0, eb1, fill32);
                     res[fi] = lerp_fill(w_el, v0, v1, fill32);
@@ -180,10 +229,9 @@ __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, con
             } else {
 #pragma unroll
                 for (int fi = 0; fi < NF; ++fi) {
-                    const float2* v = static_cast<const float2*>(val[fi]);
-                    const float2* pa = v + (ea.row + (unsigned)gi);
-                    const float2 a0 = __ldg(pa - 1), a1 = __ldg(pa);
-                    const float ea0 = fmaf(ea.w, a0.y - a0.x, a0.x), ea1 = fmaf(ea.w, a1.y - a1.x, a1.x);
+                    const float4* v = static_cast<const float4*>(val[fi]);
+                    const float4 qa4 = __ldg(v + (ea.row + (unsigned)gi));
+                    const float ea0 = fmaf(ea.w, qa4.y - qa4.x, qa4.x), ea1 = fmaf(ea.w, qa4.w - qa4.z, qa4.z);
                     res[fi] = lerp_fill(w_r, ea0, ea1, fill32);
                 }
             }
@@ -222,8 +270,11 @@ struct R2Args {
     unsigned long long level_slow;      // bit iz: level takes the reference chain
 };
 
+#ifndef R2_MINB
+#define R2_MINB 5
+#endif
 template <int NF, bool EMIT, bool UNI>
-__global__ void __launch_bounds__(256) cappi3d_r2_kernel(const __grid_constant__ R2Args P) {
+__global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_constant__ R2Args P) {
     const FastArgs& p = P.base;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ne = p.vol.ne;
@@ -244,8 +295,21 @@ __global__ void __launch_bounds__(256) cappi3d_r2_kernel(const __grid_constant__
 
     const float fill32 = p.fill32;
     const long long ncol = p.grid.ncol;
-    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= ncol) return;
+    // 2-D warp footprint: lanes cover PY consecutive columns (the fastest output axis) of 32 / PY rows, so a
+    // warp's gathers stay inside a compact patch of the polar volume (fewer distinct lines per request)
+    // while every row segment still stores PY * 8 contiguous bytes; 4 x (warps / 4) warps tile the block.
+    long long col;
+    {
+        const int pyl = p.grid.py_log2;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+        const int wy = nwarp >= 4 ? 4 : nwarp;
+        const int ly = lane & ((1 << pyl) - 1), lx = lane >> pyl;
+        const int by = blockIdx.x % p.grid.tiles_y, bx = blockIdx.x / p.grid.tiles_y;
+        const int iy = ((by * wy + (warp % wy)) << pyl) + ly;
+        const int ix = (bx * (nwarp / wy) + (warp / wy)) * (32 >> pyl) + lx;
+        if (ix >= p.grid.nx || iy >= p.grid.ny) return;
+        col = (long long)ix * p.grid.ny + iy;
+    }
 
     double x = p.grid.gx[col], y = p.grid.gy[col];
     if (p.grid.shift) { x = sub(x, p.grid.radar_x); y = sub(y, p.grid.radar_y); }
@@ -262,14 +326,15 @@ __global__ void __launch_bounds__(256) cappi3d_r2_kernel(const __grid_constant__
     c.a2 = p.a2; c.twoa = p.twoa; c.guard = p.guard; c.inv_twoa = p.inv_twoa;
     c.fill32 = fill32;
     c.nearest_gate = p.nearest_gate != 0; c.lowest_sweep = p.lowest_sweep != 0; c.highest_sweep = p.highest_sweep != 0;
-    column_azimuth_table<EMIT>(s_sw, ne, p.vol.az, az, s_az + (size_t)threadIdx.x * ne,
-                               s_iaz + (size_t)threadIdx.x * ne, 1);
+    column_azimuth_table_r2<EMIT>(s_sw, ne, P.r2.az_t, az, s_az + (size_t)threadIdx.x * ne,
+                                  s_iaz + (size_t)threadIdx.x * ne, 1);
     R2Ctx q = P.r2;
     q.fs = s_fs;
 
     int k = -1, k6 = 0;
     double* out_col = p.out + col;
     const LevelSweep* ls = P.r2.ls;
+    const bool merge_max = p.merge_max != 0;
 #pragma unroll 1
     for (int iz = 0; iz < p.nz; ++iz) {
         float res[NF];
@@ -278,10 +343,10 @@ __global__ void __launch_bounds__(256) cappi3d_r2_kernel(const __grid_constant__
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             double* dst = out_col + (size_t)f * (size_t)p.field_stride;
-            const bool is_fill = (res[f] == fill32);
-            const double v = is_fill ? p.fill : (double)res[f];
-            if (p.merge_max) {
-                if (!is_fill) {
+            // the fill value is float-representable (checked on the host), so widening res restores it
+            const double v = (double)res[f];
+            if (merge_max) {
+                if (res[f] != fill32) {
                     const double cur = *dst;
                     if (cur == p.fill || v > cur) *dst = v;
                 }
