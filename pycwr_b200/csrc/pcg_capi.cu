@@ -107,12 +107,12 @@ struct pcg_volume {
     // last (height, Re, levels) threshold table: rebuilt only when the call geometry changes
     mutable std::mutex ls_mutex;
     mutable std::vector<double> ls_key;
-    mutable LevelSweep* d_ls = nullptr;
+    mutable LevelSweep* d_ls = nullptr;      // followed in the same allocation by the LevelPair table
     mutable std::vector<unsigned char> ls_slow;
     bool uniform = false;            // one range table shared by every sweep, every sweep / pair usable + validated
     unsigned uni_rng_off = 0;
     int uni_ngm1 = 0;
-    float uni_inv_step = 0.f, uni_c0 = 0.f;
+    float uni_inv_step = 0.f, uni_c0 = 0.f, uni_step = 0.f, uni_r_first = 0.f;
     std::vector<SweepDesc> sweeps;
     std::vector<PairDesc> pairs;     // host copy of d_pairs (the network path rescales it per call)
     double fill = -999.0;            // the missing-value marker the moments were packed with
@@ -350,6 +350,21 @@ void build_level_sweeps(const pcg_volume* v, double Re, double av, const double*
     }
 }
 
+// {t_lo[k], t_hi[k+1], rho2[k], rho[k], b1[k]} per (level, k + 1) from the per-sweep bands
+void build_level_pairs(const LevelSweep* ls, int nz, int ne, LevelPair* lp) {
+    for (int iz = 0; iz < nz; ++iz) {
+        const LevelSweep* row = ls + (size_t)iz * (ne + 2);
+        LevelPair* out = lp + (size_t)iz * (ne + 1);
+        for (int s = 0; s <= ne; ++s) {          // s = k + 1
+            out[s].t_lo = row[s].t_lo;
+            out[s].t_hi = row[s + 1].t_hi;
+            out[s].rho2 = row[s].rho2;
+            out[s].rho = row[s].rho;
+            out[s].b1 = row[s].b1;
+        }
+    }
+}
+
 template <int NF, bool EMIT, bool UNI>
 int launch_fast_one(const R2Args& args, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024)   // opt in to large dynamic shared memory (per device, cheap)
@@ -421,8 +436,11 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
         key.insert(key.end(), levels, levels + nz);
         if (!vol->d_ls || key.size() != vol->ls_key.size() ||
             memcmp(key.data(), vol->ls_key.data(), key.size() * sizeof(double)) != 0) {
-            std::vector<LevelSweep> ls((size_t)nz * (ne + 2));
+            const size_t n_ls = (size_t)nz * (ne + 2), n_lp = (size_t)nz * (ne + 1);
+            static_assert(sizeof(LevelSweep) == 32 && sizeof(LevelPair) == 32, "threshold tables are 32-byte records");
+            std::vector<LevelSweep> ls(n_ls + n_lp);
             build_level_sweeps(vol, Re, av, levels, nz, ls.data(), &vol->ls_slow);
+            build_level_pairs(ls.data(), nz, ne, reinterpret_cast<LevelPair*>(ls.data() + n_ls));
             LevelSweep* fresh = nullptr;
             CUDA_TRY(cudaMalloc((void**)&fresh, ls.size() * sizeof(LevelSweep)));
             cudaError_t e = cudaMemcpy(fresh, ls.data(), ls.size() * sizeof(LevelSweep), cudaMemcpyHostToDevice);
@@ -441,6 +459,7 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     RA.r2.inv2a = (float)(1.0 / twoa);
     RA.r2.u_rng_off = vol->uni_rng_off; RA.r2.u_ngm1 = vol->uni_ngm1;
     RA.r2.u_inv_step = vol->uni_inv_step; RA.r2.u_c0 = vol->uni_c0;
+    RA.r2.u_step = vol->uni_step; RA.r2.u_r_first = vol->uni_r_first;
     // shared memory: descriptors + the per-thread azimuth table [thread][sweep]; pick the block
     // size so that several blocks still fit an SM (227 KB)
     const size_t fixed = (size_t)vol->ne * (sizeof(SweepDesc) + sizeof(FastSweep)) + (size_t)(vol->ne - 1) * sizeof(PairDesc);
@@ -466,6 +485,7 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
             if (slow[z0 + k]) RA.level_slow |= 1ull << k;
         }
         RA.r2.ls = d_ls + (size_t)z0 * (ne + 2);
+        RA.r2.lp = reinterpret_cast<const LevelPair*>(d_ls + (size_t)nz * (ne + 2)) + (size_t)z0 * (ne + 1);
         A.out = d_out + (size_t)z0 * (size_t)ncol;
         A.idx = d_idx ? d_idx + (size_t)z0 * (size_t)ncol * kIdxStride : nullptr;
         rc = d_idx ? launch_fast_nf<true>(RA, nfield, vol->uniform, grid, block, smem, st)
@@ -853,6 +873,15 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
             for (int s = 0; s < ne && uni; ++s) {
                 const int need = (s + 1 < ne) ? (kFsPolyOk | kFsShared | kFsUsable) : kFsUsable;
                 if ((fs[s].flags & need) != need || fs[s].rng_off != fs[0].rng_off || fs[s].ngm1 != fs[0].ngm1) uni = false;
+            }
+            // ... with constant gate spacing: R[j] = R[0] + j * step to within 1e-6 of a step
+            if (uni) {
+                const SweepDesc& d0 = v->sweeps[0];
+                const double step = (d0.r_last - d0.r_first) / (double)(d0.ng - 1);
+                for (int j = 0; j < d0.ng && uni; ++j)
+                    if (fabs(rng[0][j] - (d0.r_first + j * step)) > 1e-6 * step) uni = false;
+                v->uni_step = (float)step;
+                v->uni_r_first = (float)d0.r_first;
             }
             v->uniform = uni;
             v->uni_rng_off = fs[0].rng_off; v->uni_ngm1 = fs[0].ngm1;

@@ -32,6 +32,12 @@ struct LevelSweep {               // per (level, slot); slot k + 1 <-> sweep k, 
     float rho, b1;                // rho_k,  D / rho_k
 };
 
+struct LevelPair {                // per (level, k + 1), k = -1 .. ne-1: what confirms and samples pair k
+    double t_lo, t_hi;            // t_lo[k], t_hi[k+1]: r2 strictly between them <=> certainly e_k <= el < e_{k+1}
+    double rho2;                  // of sweep k
+    float rho, b1;
+};
+
 enum FastSweepFlag { kFsPolyOk = 1, kFsShared = 2, kFsUsable = 4 };
 
 struct FastSweep {                // per sweep k (and the pair (k, k+1)), constant per volume
@@ -49,6 +55,7 @@ struct GateAux { double rsq; float r, inv_dr; };   // R[j]^2, R[j], 1 / (R[j+1] 
 
 struct R2Ctx {
     const LevelSweep* ls;         // [nz][ne + 2]
+    const LevelPair* lp;          // [nz][ne + 1]
     const FastSweep* fs;          // [ne]
     const double2* g_t;           // {tg[j], tg[j+1]} per gate (tg_gt_last at the end)
     const GateAux* h_t;
@@ -57,7 +64,7 @@ struct R2Ctx {
     // UNI kernels: the one range table every sweep shares
     unsigned u_rng_off;
     int u_ngm1;
-    float u_inv_step, u_c0;
+    float u_inv_step, u_c0, u_step, u_r_first;
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -138,31 +145,45 @@ __device__ __forceinline__ void column_azimuth_table_r2(const SweepDesc* s_sw, i
     }
 }
 
-// UNI: every sweep shares ONE range table and every sweep / pair is usable and poly-validated (the
-// common case: PRD.get_vol_data with aligned ranges) — the range-table constants are then kernel
-// uniforms and no per-sweep flag is consulted.  Otherwise they are read per sweep from `q.fs`.
+// what the sampler needs about the column's current sweep pair, kept in registers while k is unchanged
+// (k moves once every few levels): the two azimuth entries and the pair's weight polynomial
+struct PairCache {
+    int k;                        // pair the cache holds (INT_MIN: none)
+    AzEntry ea, eb;
+    float q1, q2, q3, q4, q5;
+};
+
+// UNI: every sweep shares ONE range table with constant gate spacing and every sweep / pair is usable
+// and poly-validated (the common case: PRD.get_vol_data with aligned ranges) — the range-table
+// constants are then kernel uniforms, R[j] is an FMA and no per-sweep flag is consulted.  Otherwise
+// they are read per sweep from `q.fs` and per gate from `q.h_t`.
 template <int NF, bool EMIT, bool UNI>
 __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, const void* const* val,
                                          const LevelConst& lc, const LevelSweep* __restrict__ ls,
-                                         bool level_slow, double cphi, int& k, int& k6,
-                                         float (&res)[NF], VoxelInfo& vi) {
+                                         const LevelPair* __restrict__ lp, bool level_slow, double cphi,
+                                         int& k, int& k6, PairCache& pc, float (&res)[NF], VoxelInfo& vi) {
     const int ne = c.ne;
     const float fill32 = c.fill32;
     // RadarGridC.pyx:146-149 — the reference's own operations: r2 is bit-identical
     const double r2 = sub(lc.a2g2, mul(lc.twoag, cphi));
     bool slow = level_slow | !(r2 > 0.0);
     if (!slow) {
-        // settle k in [-1, ne-1]: e_k <= el < e_{k+1} (k = -1 below the lowest sweep, ne-1 above the highest)
+        // settle k in [-1, ne-1]: e_k <= el < e_{k+1} (k = -1 below the lowest sweep, ne-1 above the highest).
+        // One 16-byte entry {t_lo[k], t_hi[k+1]} confirms the current k; the per-sweep bands are only
+        // read when the column has to move.
+        const double2 cf = __ldg(reinterpret_cast<const double2*>(lp + (k + 1)));
+        if (!((r2 < cf.x) & (r2 > cf.y))) {
 #pragma unroll 1
-        for (;;) {
-            const double2* row = reinterpret_cast<const double2*>(ls + (k + 1));
-            const double2 cur = __ldg(row);
-            const double2 nxt = __ldg(row + 2);
-            if ((r2 < cur.x) & (r2 > nxt.y)) break;
-            if (r2 > cur.y) { --k; continue; }
-            if (r2 < nxt.x) { ++k; continue; }
-            slow = true;                                  // inside a guard band
-            break;
+            for (;;) {
+                const double2* row = reinterpret_cast<const double2*>(ls + (k + 1));
+                const double2 cur = __ldg(row);
+                const double2 nxt = __ldg(row + 2);
+                if ((r2 < cur.x) & (r2 > nxt.y)) break;
+                if (r2 > cur.y) { --k; continue; }
+                if (r2 < nxt.x) { ++k; continue; }
+                slow = true;                                  // inside a guard band
+                break;
+            }
         }
     }
     if (!slow) {
@@ -199,14 +220,21 @@ __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, con
         const unsigned gidx = rng_off + (unsigned)(gi - 1);
         const double2 tg = __ldg(q.g_t + gidx);          // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
         if (usable & (r2 >= tg.x) & (r2 < tg.y)) {
-            const int4 hv = __ldg(reinterpret_cast<const int4*>(q.h_t + gidx));     // {R^2 (lo, hi), R, 1/dR}
-            const float w_r = (float)sub(r2, __hiloint2double(hv.y, hv.x)) * __int_as_float(hv.w) *
-                              rcp_approx(rf + __int_as_float(hv.z));
+            float w_r;
+            if (UNI) {
+                // regular table: R[gi-1] = R[0] + (gi-1) * step, and tg.x is R[gi-1]^2 to within two ulps
+                const float rj = fmaf((float)(gi - 1), q.u_step, q.u_r_first);
+                w_r = (float)sub(r2, tg.x) * q.u_inv_step * rcp_approx(rf + rj);
+            } else {
+                const int4 hv = __ldg(reinterpret_cast<const int4*>(q.h_t + gidx));     // {R^2 (lo, hi), R, 1/dR}
+                w_r = (float)sub(r2, __hiloint2double(hv.y, hv.x)) * __int_as_float(hv.w) *
+                      rcp_approx(rf + __int_as_float(hv.z));
+            }
             const AzEntry* az = c.my_az + (size_t)lower * c.az_stride;
             const AzEntry ea = az[0];
             vi.r = (double)rf;
             if (pair) {
-                const int4 lk = __ldg(reinterpret_cast<const int4*>(ls + (k + 1)) + 1);  // {rho2 (lo, hi), rho, b1}
+                const int4 lk = __ldg(reinterpret_cast<const int4*>(lp + (k + 1)) + 1);  // {rho2 (lo, hi), rho, b1}
                 const float u = (float)sub(r2, __hiloint2double(lk.y, lk.x)) * rcp_approx(rf + __int_as_float(lk.z)) *
                                 fmaf(__int_as_float(lk.w), rinv, q.inv2a);
                 const float4 qa = *reinterpret_cast<const float4*>(&f->q1);
@@ -332,14 +360,18 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
     q.fs = s_fs;
 
     int k = -1, k6 = 0;
+    PairCache pc;
+    pc.k = -0x7fffffff;
     double* out_col = p.out + col;
     const LevelSweep* ls = P.r2.ls;
+    const LevelPair* lp = P.r2.lp;
     const bool merge_max = p.merge_max != 0;
 #pragma unroll 1
     for (int iz = 0; iz < p.nz; ++iz) {
         float res[NF];
         VoxelInfo vi;
-        r2_voxel<NF, EMIT, UNI>(c, q, p.vol.val, p.levels[iz], ls, (P.level_slow >> iz) & 1ull, cphi, k, k6, res, vi);
+        r2_voxel<NF, EMIT, UNI>(c, q, p.vol.val, p.levels[iz], ls, lp, (P.level_slow >> iz) & 1ull, cphi, k, k6, pc,
+                                res, vi);
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             double* dst = out_col + (size_t)f * (size_t)p.field_stride;
@@ -365,6 +397,7 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
         }
         out_col += ncol;
         ls += ne + 2;
+        lp += ne + 1;
     }
 }
 
