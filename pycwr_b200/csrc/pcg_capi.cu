@@ -1212,19 +1212,23 @@ struct NetHostTables {
     std::vector<PairDesc> pairs;     // per radar, thresholds scaled by 2a
 };
 
-int launch_network(const NetArgs& a, int method, dim3 grid, size_t smem, cudaStream_t st) {
-#define NET_CASE(M)                                                                                  \
-    case M:                                                                                          \
+int launch_network(const NetArgs& a, int method, bool uni, dim3 grid, size_t smem, cudaStream_t st) {
+#define NET_CASE(M, U)                                                                               \
+    case (M) * 2 + ((U) ? 1 : 0):                                                                    \
         if (smem > 48 * 1024)                                                                        \
-            CUDA_TRY(cudaFuncSetAttribute(network_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            CUDA_TRY(cudaFuncSetAttribute(network_kernel<M, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                               \
-        network_kernel<M><<<grid, kNetThreads, smem, st>>>(a);                                       \
+        network_kernel<M, U><<<grid, kNetThreads, smem, st>>>(a);                                    \
         break;
-    switch (method) {
-        NET_CASE(kNetMax)
-        NET_CASE(kNetNearest)
-        NET_CASE(kNetExp)
-        NET_CASE(kNetQuality)
+    switch (method * 2 + (uni ? 1 : 0)) {
+        NET_CASE(kNetMax, false)
+        NET_CASE(kNetMax, true)
+        NET_CASE(kNetNearest, false)
+        NET_CASE(kNetNearest, true)
+        NET_CASE(kNetExp, false)
+        NET_CASE(kNetExp, true)
+        NET_CASE(kNetQuality, false)
+        NET_CASE(kNetQuality, true)
         default: return fail(PCG_ERR_ARG, "Unsupported composite_method code %d", method);
     }
 #undef NET_CASE
@@ -1233,10 +1237,20 @@ int launch_network(const NetArgs& a, int method, dim3 grid, size_t smem, cudaStr
     return PCG_OK;
 }
 
-// d_* pointers are DEVICE pointers; tables are built on the host and uploaded through S_NET.
+// d_* pointers are DEVICE pointers; tables are built on the host and uploaded through S_NET.  The blob of
+// the last call is kept: repeated calls with the same radars / geometry / options only launch.
+std::vector<char> g_net_key;
+void* g_net_ptr = nullptr;
+
+template <typename T>
+void key_put(std::vector<char>* key, const T* p, size_t n) {
+    const char* b = reinterpret_cast<const char*>(p);
+    key->insert(key->end(), b, b + n * sizeof(T));
+}
+
 int enqueue_network(int nradar, const pcg_volume* const* vols, const double* radar_x, const double* radar_y,
                     const double* radar_height, const double* re, const double* const* beam_widths,
-                    const pcg_network_params* prm, const double* d_gx, const double* d_gy, long long ncol,
+                    const pcg_network_params* prm, const double* d_gx, const double* d_gy, long long ncol, int ny,
                     const double* levels, int nz, double fill, double* d_comp, int16_t* d_valid,
                     int16_t* d_cov, int8_t* d_blind, double* d_cr, double* d_quality,
                     unsigned long long* d_ties, cudaStream_t st) {
@@ -1253,6 +1267,8 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     if (ncol == 0 || nz == 0) return PCG_OK;
     int rc;
     int max_ne = 2;
+    bool uni = true;
+    size_t npair_total = 0, n_ls = 0, n_lp = 0;
     for (int i = 0; i < nradar; ++i) {
         if ((rc = check_volume(vols[i]))) return rc;
         if (!(re[i] > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
@@ -1264,108 +1280,140 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
             return fail(PCG_ERR_ARG, "fillvalue %.17g differs from the value volume %d was packed with (%.17g)", fill, i,
                         vols[i]->fill);
         if (vols[i]->ne > max_ne) max_ne = vols[i]->ne;
+        uni = uni && vols[i]->uniform;
+        npair_total += (size_t)(vols[i]->ne - 1);
+        n_ls += (size_t)nz * (vols[i]->ne + 2);
+        n_lp += (size_t)nz * (vols[i]->ne + 1);
     }
-    NetHostTables T;
-    T.radars.resize(nradar);
-    size_t npair_total = 0;
-    for (int i = 0; i < nradar; ++i) npair_total += (size_t)(vols[i]->ne - 1);
-    T.npairs.resize(npair_total);
-    T.pairs.resize(npair_total);
-    T.levels.resize((size_t)nradar * nz);
-    double zmin = levels[0];
-    for (int k = 1; k < nz; ++k) zmin = levels[k] < zmin ? levels[k] : zmin;
-
     const size_t bytes_radars = sizeof(NetRadar) * (size_t)nradar;
     const size_t bytes_pairs = sizeof(NetPair) * npair_total;
-    const size_t bytes_levels = sizeof(NetLevel) * T.levels.size();
+    const size_t bytes_levels = sizeof(NetLevel) * (size_t)nradar * nz;
     const size_t bytes_spairs = sizeof(PairDesc) * npair_total;
-    if ((rc = g_scratch[S_NET].ensure(bytes_radars + bytes_pairs + bytes_levels + bytes_spairs + 64))) return rc;
+    const size_t bytes_ls = sizeof(LevelSweep) * n_ls, bytes_lp = sizeof(LevelPair) * n_lp;
+    const size_t off_pairs = bytes_radars, off_levels = off_pairs + bytes_pairs, off_spairs = off_levels + bytes_levels;
+    const size_t off_ls = (off_spairs + bytes_spairs + 31) & ~(size_t)31, off_lp = off_ls + bytes_ls;
+    const size_t total = off_lp + bytes_lp;
+    if ((rc = g_scratch[S_NET].ensure(total + 64))) return rc;
     char* d_base = (char*)g_scratch[S_NET].ptr;
-    const NetPair* d_pairs = (const NetPair*)(d_base + bytes_radars);
-    const NetLevel* d_levels = (const NetLevel*)(d_base + bytes_radars + bytes_pairs);
-    const PairDesc* d_spairs = (const PairDesc*)(d_base + bytes_radars + bytes_pairs + bytes_levels);
 
-    size_t poff = 0;
+    // everything the tables depend on
+    std::vector<char> key;
+    key_put(&key, &nradar, 1); key_put(&key, &nz, 1); key_put(&key, prm, 1); key_put(&key, &fill, 1);
+    key_put(&key, vols, nradar); key_put(&key, radar_x, nradar); key_put(&key, radar_y, nradar);
+    key_put(&key, radar_height, nradar); key_put(&key, re, nradar); key_put(&key, levels, nz);
     for (int i = 0; i < nradar; ++i) {
-        const pcg_volume* v = vols[i];
-        NetRadar& R = T.radars[i];
-        memset(&R, 0, sizeof(R));
-        R.vol = view_of(v);
-        R.pairs = d_spairs + poff;
-        R.npairs = d_pairs + poff;
-        R.levels = d_levels + (size_t)i * nz;
-        R.x = radar_x[i];
-        R.y = radar_y[i];
-        R.Re = re[i];
-        volatile double av = re[i] + radar_height[i];   // RadarGridC.pyx:144
-        volatile double a2 = av * av;
-        volatile double twoa = 2.0 * av;
-        R.a = av; R.a2 = a2; R.twoa = twoa;
-        R.guard = kGuardDelta * twoa;
-        R.inv_twoa = 1.0 / twoa;
-        R.a2_np = pow((double)av, 2.0);                 // radar_radius ** 2 (transforms.py:213)
-        R.ne = v->ne;
-        // range-sanity window (RadarInterp.py:1003-1011)
-        if (v->src_count[0] == 0) {
-            R.src_lo = 1.0; R.src_hi = 0.0;             // no valid source value: everything -> fill
-        } else {
-            const double mn = v->src_min[0], mx = v->src_max[0];
-            double m = fabs(mn) > fabs(mx) ? fabs(mn) : fabs(mx);
-            if (m < 1.0) m = 1.0;
-            double tol = 1e-6 * m;
-            if (tol < 1e-6) tol = 1e-6;
-            R.src_lo = mn - tol;
-            R.src_hi = mx + tol;
-        }
-        R.inv_decay = (prm->quality_terms & kTermRange) ? (float)(1.0 / prm->range_decay_m) : 0.f;
-        R.inv_r2inf4 = (float)(4.0 / (prm->influence_radius_m * prm->influence_radius_m));
-        // reach of the radar: slant range r >= 0.999 * s * min(a, g) / Re for phi < 0.15
-        double rlast = 0.0;
-        for (int k = 0; k < v->ne; ++k) rlast = v->sweeps[k].r_last > rlast ? v->sweeps[k].r_last : rlast;
-        const double min_ag = re[i] + (radar_height[i] < zmin ? radar_height[i] : zmin);
-        const double factor = 0.999 * min_ag / re[i];
-        if (factor < 0.9 || !(rlast < 1.0e6)) R.cull2 = HUGE_VAL;
-        else { const double cr = rlast / factor * 1.001 + 1.0; R.cull2 = cr * cr; }
         const double* bw = beam_widths ? beam_widths[i] : nullptr;
-        for (int k = 0; k + 1 < v->ne; ++k) {
-            NetPair& np = T.npairs[poff + k];
-            const SweepDesc& d0 = v->sweeps[k];
-            const SweepDesc& d1 = v->sweeps[k + 1];
-            np.obs_first = d0.r_first > d1.r_first ? d0.r_first : d1.r_first;
-            np.obs_last = d0.r_last < d1.r_last ? d0.r_last : d1.r_last;
-            const double b0 = bw ? bw[k] : 1.0, b1 = bw ? bw[k + 1] : 1.0;
-            const double rep = 0.5 * (b0 + b1);
-            np.beam_k = (prm->quality_terms & kTermBeam)
-                            ? (float)(tan(rep * kDeg2Rad * 0.5) / prm->beam_radius_ref_m) : 0.f;
-            const double gap_half = 0.5 * (d1.elev - d0.elev);
-            const double gq = gap_half / prm->vertical_gap_ref_deg;
-            np.vert_w = (prm->quality_terms & kTermVertical) ? (float)(1.0 / (1.0 + gq * gq)) : 1.f;
-            PairDesc sp = v->pairs[k];          // what stage_pairs does for the single-radar kernel
-            volatile double s_lo = sp.c_lo * (double)twoa, s_hi = sp.c_hi * (double)twoa, s_mid = sp.c_mid * (double)twoa;
-            sp.c_lo = s_lo; sp.c_hi = s_hi; sp.c_mid = s_mid;
-            T.pairs[poff + k] = sp;
-        }
-        poff += (size_t)(v->ne - 1);
-        for (int k = 0; k < nz; ++k) {
-            NetLevel& L = T.levels[(size_t)i * nz + k];
-            fill_level(&L.cy, levels[k], re[i], a2, twoa);
-            const double g = re[i] + levels[k];
-            L.g2_np = pow(g, 2.0);
-            L.a2g2_np = R.a2_np + L.g2_np;
-            volatile double t = 2.0 * (double)av;
-            volatile double tg = t * g;                 // 2 * radar_radius * gate_radius (left to right)
-            L.twoag_np = tg;
-        }
+        const int has = bw ? 1 : 0;
+        key_put(&key, &has, 1);
+        if (bw) key_put(&key, bw, vols[i]->ne);
+        key_put(&key, &vols[i]->src_min[0], 1); key_put(&key, &vols[i]->src_max[0], 1);
     }
-    CUDA_TRY(cudaMemcpyAsync(d_base, T.radars.data(), bytes_radars, cudaMemcpyHostToDevice, st));
-    if (bytes_pairs)
-        CUDA_TRY(cudaMemcpyAsync(d_base + bytes_radars, T.npairs.data(), bytes_pairs, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_base + bytes_radars + bytes_pairs, T.levels.data(), bytes_levels, cudaMemcpyHostToDevice, st));
-    if (bytes_spairs)
-        CUDA_TRY(cudaMemcpyAsync(d_base + bytes_radars + bytes_pairs + bytes_levels, T.pairs.data(), bytes_spairs,
-                                 cudaMemcpyHostToDevice, st));
-    // the host vectors die with this frame: make the uploads complete before returning
-    CUDA_TRY(cudaStreamSynchronize(st));
+    const bool cached = (g_net_ptr == (void*)d_base) && key.size() == g_net_key.size() &&
+                        memcmp(key.data(), g_net_key.data(), key.size()) == 0;
+    if (!cached) {
+        std::vector<char> blob(total, 0);
+        NetRadar* radars = reinterpret_cast<NetRadar*>(blob.data());
+        NetPair* npairs = reinterpret_cast<NetPair*>(blob.data() + off_pairs);
+        NetLevel* nlevels = reinterpret_cast<NetLevel*>(blob.data() + off_levels);
+        PairDesc* spairs = reinterpret_cast<PairDesc*>(blob.data() + off_spairs);
+        LevelSweep* ls_all = reinterpret_cast<LevelSweep*>(blob.data() + off_ls);
+        LevelPair* lp_all = reinterpret_cast<LevelPair*>(blob.data() + off_lp);
+        double zmin = levels[0];
+        for (int k = 1; k < nz; ++k) zmin = levels[k] < zmin ? levels[k] : zmin;
+        size_t poff = 0, lsoff = 0, lpoff = 0;
+        std::vector<unsigned char> slow;
+        for (int i = 0; i < nradar; ++i) {
+            const pcg_volume* v = vols[i];
+            const int ne = v->ne;
+            NetRadar& R = radars[i];
+            R.vol = view_of(v);
+            R.pairs = reinterpret_cast<const PairDesc*>(d_base + off_spairs) + poff;
+            R.npairs = reinterpret_cast<const NetPair*>(d_base + off_pairs) + poff;
+            R.levels = reinterpret_cast<const NetLevel*>(d_base + off_levels) + (size_t)i * nz;
+            R.x = radar_x[i];
+            R.y = radar_y[i];
+            R.Re = re[i];
+            volatile double av = re[i] + radar_height[i];   // RadarGridC.pyx:144
+            volatile double a2 = av * av;
+            volatile double twoa = 2.0 * av;
+            R.a = av; R.a2 = a2; R.twoa = twoa;
+            R.guard = kGuardDelta * twoa;
+            R.inv_twoa = 1.0 / twoa;
+            R.a2_np = pow((double)av, 2.0);                 // radar_radius ** 2 (transforms.py:213)
+            R.ne = ne;
+            // r2-space tables
+            R.r2.ls = reinterpret_cast<const LevelSweep*>(d_base + off_ls) + lsoff;
+            R.r2.lp = reinterpret_cast<const LevelPair*>(d_base + off_lp) + lpoff;
+            R.r2.fs = v->d_fs; R.r2.g_t = v->d_gt; R.r2.h_t = v->d_ht; R.r2.az_t = v->d_azt;
+            R.r2.inv2a = (float)(1.0 / twoa);
+            R.r2.u_rng_off = v->uni_rng_off; R.r2.u_ngm1 = v->uni_ngm1; R.r2.u_inv_step = v->uni_inv_step;
+            R.r2.u_c0 = v->uni_c0; R.r2.u_step = v->uni_step; R.r2.u_r_first = v->uni_r_first;
+            build_level_sweeps(v, re[i], av, levels, nz, ls_all + lsoff, &slow);
+            build_level_pairs(ls_all + lsoff, nz, ne, lp_all + lpoff);
+            lsoff += (size_t)nz * (ne + 2);
+            lpoff += (size_t)nz * (ne + 1);
+            // range-sanity window (RadarInterp.py:1003-1011)
+            if (v->src_count[0] == 0) {
+                R.src_lo = 1.0; R.src_hi = 0.0;             // no valid source value: everything -> fill
+            } else {
+                const double mn = v->src_min[0], mx = v->src_max[0];
+                double m = fabs(mn) > fabs(mx) ? fabs(mn) : fabs(mx);
+                if (m < 1.0) m = 1.0;
+                double tol = 1e-6 * m;
+                if (tol < 1e-6) tol = 1e-6;
+                R.src_lo = mn - tol;
+                R.src_hi = mx + tol;
+            }
+            R.inv_decay = (prm->quality_terms & kTermRange) ? (float)(1.0 / prm->range_decay_m) : 0.f;
+            R.inv_r2inf4 = (float)(4.0 / (prm->influence_radius_m * prm->influence_radius_m));
+            // reach of the radar: slant range r >= 0.999 * s * min(a, g) / Re for phi < 0.15
+            double rlast = 0.0;
+            for (int k = 0; k < ne; ++k) rlast = v->sweeps[k].r_last > rlast ? v->sweeps[k].r_last : rlast;
+            const double min_ag = re[i] + (radar_height[i] < zmin ? radar_height[i] : zmin);
+            const double factor = 0.999 * min_ag / re[i];
+            if (factor < 0.9 || !(rlast < 1.0e6)) R.cull2 = HUGE_VAL;
+            else { const double cr = rlast / factor * 1.001 + 1.0; R.cull2 = cr * cr; }
+            const double* bw = beam_widths ? beam_widths[i] : nullptr;
+            for (int k = 0; k + 1 < ne; ++k) {
+                NetPair& np = npairs[poff + k];
+                const SweepDesc& d0 = v->sweeps[k];
+                const SweepDesc& d1 = v->sweeps[k + 1];
+                np.obs_first = d0.r_first > d1.r_first ? d0.r_first : d1.r_first;
+                np.obs_last = d0.r_last < d1.r_last ? d0.r_last : d1.r_last;
+                const double f2 = np.obs_first * np.obs_first, l2 = np.obs_last * np.obs_last;
+                np.of2_lo = f2 * (1.0 - 1e-9); np.of2_hi = f2 * (1.0 + 1e-9);
+                np.ol2_lo = l2 * (1.0 - 1e-9); np.ol2_hi = l2 * (1.0 + 1e-9);
+                const double b0 = bw ? bw[k] : 1.0, b1 = bw ? bw[k + 1] : 1.0;
+                const double rep = 0.5 * (b0 + b1);
+                np.beam_k = (prm->quality_terms & kTermBeam)
+                                ? (float)(tan(rep * kDeg2Rad * 0.5) / prm->beam_radius_ref_m) : 0.f;
+                const double gap_half = 0.5 * (d1.elev - d0.elev);
+                const double gq = gap_half / prm->vertical_gap_ref_deg;
+                np.vert_w = (prm->quality_terms & kTermVertical) ? (float)(1.0 / (1.0 + gq * gq)) : 1.f;
+                PairDesc sp = v->pairs[k];          // what stage_pairs does for the single-radar kernel
+                volatile double s_lo = sp.c_lo * (double)twoa, s_hi = sp.c_hi * (double)twoa, s_mid = sp.c_mid * (double)twoa;
+                sp.c_lo = s_lo; sp.c_hi = s_hi; sp.c_mid = s_mid;
+                spairs[poff + k] = sp;
+            }
+            poff += (size_t)(ne - 1);
+            for (int k = 0; k < nz; ++k) {
+                NetLevel& L = nlevels[(size_t)i * nz + k];
+                fill_level(&L.cy, levels[k], re[i], a2, twoa);
+                const double g = re[i] + levels[k];
+                L.g2_np = pow(g, 2.0);
+                L.a2g2_np = R.a2_np + L.g2_np;
+                volatile double t = 2.0 * (double)av;
+                volatile double tg = t * g;                 // 2 * radar_radius * gate_radius (left to right)
+                L.twoag_np = tg;
+                L.slow = slow[k];
+            }
+        }
+        // the previous launch may still be reading the old tables
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(d_base, blob.data(), total, cudaMemcpyHostToDevice));
+        g_net_key.swap(key);
+        g_net_ptr = (void*)d_base;
+    }
 
     NetArgs A;
     memset(&A, 0, sizeof(A));
@@ -1373,6 +1421,11 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     A.nradar = nradar;
     A.nz = nz;
     A.gx = d_gx; A.gy = d_gy; A.ncol = ncol;
+    A.ny = ny; A.nx = (int)(ncol / (ny > 0 ? ny : 1));
+    A.py_log2 = (A.nx >= 4 && ny >= 8) ? 3 : 5;
+    const int PY = 1 << A.py_log2, PX = 32 / PY, nwarp = kNetThreads / 32;
+    A.tiles_y = (int)((ny + (long long)nwarp * PY - 1) / ((long long)nwarp * PY));
+    const long long tiles_x = (A.nx + PX - 1) / PX;
     A.fill = fill; A.fill32 = (float)fill;
     A.quality = 1;
     A.sanity = prm->sanity_filter ? 1 : 0;
@@ -1387,8 +1440,8 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     const size_t smem = (size_t)max_ne * kNetThreads * sizeof(AzEntry) +
                         (size_t)kNetZC * kNetThreads *
                             (2 * sizeof(float) + 2 + (prm->method == kNetNearest ? sizeof(double) : 0));
-    const dim3 grid((unsigned)((ncol + kNetThreads - 1) / kNetThreads), (unsigned)((nz + kNetZC - 1) / kNetZC));
-    return launch_network(A, prm->method, grid, smem, st);
+    const dim3 grid((unsigned)(tiles_x * A.tiles_y), (unsigned)((nz + kNetZC - 1) / kNetZC));
+    return launch_network(A, prm->method, uni, grid, smem, st);
 }
 
 }  // namespace
@@ -1413,7 +1466,7 @@ extern "C" int pcg_network_compose_dev(int nradar, const pcg_volume* const* vols
     if (nx < 0 || ny < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
     std::lock_guard<std::mutex> lock(g_mutex);   // the table scratch is shared
     return enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
-                           d_grid_x, d_grid_y, (long long)nx * ny, level_heights, nz, fill, d_composite,
+                           d_grid_x, d_grid_y, (long long)nx * ny, ny, level_heights, nz, fill, d_composite,
                            d_valid_count, d_coverage_count, d_blind_mask, d_cr, d_quality, nullptr,
                            (cudaStream_t)stream);
 }
@@ -1448,7 +1501,7 @@ extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, co
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(g_scratch[S_TMP2].ptr, 0, sizeof(unsigned long long), st));
     rc = enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
-                         (const double*)g_scratch[S_GX].ptr, (const double*)g_scratch[S_GY].ptr, (long long)ncol,
+                         (const double*)g_scratch[S_GX].ptr, (const double*)g_scratch[S_GY].ptr, (long long)ncol, ny,
                          level_heights, nz, fill, (double*)g_scratch[S_OUT].ptr,
                          valid_count ? (int16_t*)g_scratch[S_AUX0].ptr : nullptr,
                          coverage_count ? (int16_t*)g_scratch[S_AUX1].ptr : nullptr,

@@ -23,7 +23,7 @@
 // to a few ulps, so a voxel is decided from the gridding's r / elevation bracket unless it lies
 // within a guard distance of a gate, in which case the twin chain itself is evaluated.
 #pragma once
-#include "pcg_fast.cuh"
+#include "pcg_r2.cuh"
 
 namespace pcg {
 
@@ -42,6 +42,10 @@ enum NetTerm { kTermRange = 1, kTermBeam = 2, kTermVertical = 4 };
 
 struct NetPair {                     // sweep pair (k, k+1) of one radar
     double obs_first, obs_last;      // max(first gates), min(last gates) (RadarInterp.py:671-672)
+    // the same two gates in r2 space with a relative guard of 1e-9 (the NumPy twin's r agrees with the
+    // gridding's to a few ulps): r2 inside (of2_hi, ol2_lo) is certainly observable, outside
+    // [of2_lo, ol2_hi] certainly not, anything else is decided by the twin chain itself
+    double of2_lo, of2_hi, ol2_lo, ol2_hi;
     float beam_k;                    // tan(deg2rad(0.5*(bw_k + bw_k+1)) * 0.5) / beam_radius_ref (0: term off)
     float vert_w;                    // 1 / (1 + (gap_half / vertical_gap_ref)^2)             (1: term off)
 };
@@ -49,6 +53,8 @@ struct NetPair {                     // sweep pair (k, k+1) of one radar
 struct NetLevel {                    // per (radar, level) constants, host-evaluated
     LevelConst cy;                   // the gridding chain (RadarGridC.pyx:145-146)
     double a2g2_np, twoag_np, g2_np; // the NumPy twin: a**2 + g**2, 2*a*g, g**2 (transforms.py:213-218)
+    int slow;                        // level takes the reference chain on the r2 path (pcg_r2.cuh)
+    int pad;
 };
 
 struct NetRadar {
@@ -56,6 +62,7 @@ struct NetRadar {
     const PairDesc* pairs;           // thresholds pre-scaled by 2a (this radar's height)
     const NetPair* npairs;
     const NetLevel* levels;          // [nz]
+    R2Ctx r2;                        // r2-space tables of this radar (ls / lp: [nz][ne + 2] / [nz][ne + 1])
     double x, y;                     // site on the common grid (m)
     double Re, a, a2, twoa, guard, inv_twoa;
     double a2_np;                    // a**2 as Python evaluates it
@@ -74,6 +81,8 @@ struct NetArgs {
     const double* gx;
     const double* gy;
     long long ncol;
+    int nx, ny;                      // grid shape (ny fastest)
+    int py_log2, tiles_y;            // warp footprint: 2^py_log2 columns x (32 >> py_log2) rows; blocks per grid row band
     double fill;
     float fill32;
     int quality;                     // multiply the 2-D weight by the geometric quality weight
@@ -128,7 +137,7 @@ __device__ __noinline__ bool twin_observable(double x, double y, const NetRadar&
     return (r >= np.obs_first) && (r <= np.obs_last);
 }
 
-template <int METHOD>
+template <int METHOD, bool UNI>
 __global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __grid_constant__ NetArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared memory holds PER-THREAD state only ([row][thread] arrays, conflict free, never read by
@@ -143,18 +152,28 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __
     double* best_d2 = reinterpret_cast<double*>(cnt8 - threadIdx.x + (size_t)2 * kNetZC * T) + threadIdx.x;  // nearest only
     __shared__ double s_box[4];
 
-    const long long col0 = (long long)blockIdx.x * T;
-    const long long col = col0 + threadIdx.x;
-    const bool active = col < p.ncol;
+    // 2-D warp footprint (see cappi3d_r2_kernel): 2^py_log2 consecutive columns x (32 >> py_log2) rows per
+    // warp, the block's warps side by side along the row
+    bool active;
+    long long col;
+    {
+        const int pyl = p.py_log2;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = T >> 5;
+        const int ly = lane & ((1 << pyl) - 1), lx = lane >> pyl;
+        const int by = blockIdx.x % p.tiles_y, bx = blockIdx.x / p.tiles_y;
+        int iy = ((by * nwarp + warp) << pyl) + ly;
+        int ix = bx * (32 >> pyl) + lx;
+        active = (ix < p.nx) & (iy < p.ny);
+        ix = min(ix, p.nx - 1); iy = min(iy, p.ny - 1);      // inactive lanes read a valid column for the bbox
+        col = (long long)ix * p.ny + iy;
+    }
     const int z0 = blockIdx.y * kNetZC;
     const int nzc = min(kNetZC, p.nz - z0);
     const bool do_cr = (p.cr != nullptr) && (blockIdx.y == 0);
     const float fill32 = p.fill32;
 
     // bounding box of the block's columns: one reduction, then every radar is culled block-uniformly
-    const long long lastc = min(col0 + (long long)T, p.ncol) - 1;
-    const long long cc = active ? col : lastc;
-    const double gx = p.gx[cc], gy = p.gy[cc];
+    const double gx = p.gx[col], gy = p.gy[col];
     {
         double x0 = gx, x1 = gx, y0 = gy, y1 = gy;
         for (int o = 16; o > 0; o >>= 1) {
@@ -214,7 +233,7 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __
         const double phi = div(s, R.Re);
         const double cphi = cos_small(phi);
         const double az = azimuth_from_xy(x, y);
-        column_azimuth_table<false>(s_sw, ne, R.vol.az, az, my_az, nullptr, T);
+        column_azimuth_table_r2<false>(s_sw, ne, R.r2.az_t, az, my_az, nullptr, T);
         ColumnCtx c;
         c.s_sw = s_sw; c.s_pr = R.pairs;              // pair thresholds pre-scaled by 2a on the host
         c.my_az = my_az; c.my_iaz = nullptr; c.az_stride = T;
@@ -227,12 +246,16 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __
         // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
         const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? expf(-(float)d2 * R.inv_r2inf4) : 1.f;
 
-        int k = 0;
+        int k = -1, k6 = 0;
+        const LevelSweep* ls = R.r2.ls + (size_t)z0 * (ne + 2);
+        const LevelPair* lp = R.r2.lp + (size_t)z0 * (ne + 1);
 #pragma unroll 1
         for (int i = 0; i < nzc; ++i) {
             float res[1];
             VoxelInfo vi;
-            fast_voxel<1, false>(c, R.vol.val, s_lv[i].cy, cphi, k, res, vi);
+            r2_voxel<1, false, UNI>(c, R.r2, R.vol.val, s_lv[i].cy, ls, lp, s_lv[i].slow != 0, cphi, k, k6, res, vi);
+            ls += ne + 2;
+            lp += ne + 1;
             float v = res[0];
             // range-sanity filter (RadarInterp.py:1003-1014), compared in double like the reference
             if (p.sanity && v != fill32) {
@@ -243,11 +266,11 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __
             // observability (RadarInterp.py:566-599 / 636-684)
             const int kk = vi.lower < ne - 1 ? vi.lower : ne - 2;
             const NetPair np = s_np[vi.bracket == kPair ? kk : 0];
-            bool obs = (vi.bracket == kPair) && (vi.r >= np.obs_first) && (vi.r <= np.obs_last);
-            const double tol = mul(vi.r, 1e-12);
-            const bool near_gate = (vi.bracket == kPair) &&
-                                   ((fabs(sub(vi.r, np.obs_first)) <= tol) || (fabs(sub(vi.r, np.obs_last)) <= tol));
-            if (vi.tie || near_gate || !(vi.r > 0.0)) {
+            const double r2 = vi.r2;
+            const bool is_pair = vi.bracket == kPair;
+            bool obs = is_pair & (r2 > np.of2_hi) & (r2 < np.ol2_lo);
+            const bool sure_out = (r2 < np.of2_lo) | (r2 > np.ol2_hi);
+            if (vi.tie || (is_pair & !obs & !sure_out) || !(r2 > 0.0)) {
                 obs = twin_observable(x, y, R, s_lv[i], s_sw, s_np, ne);
                 ++ties;
             }

@@ -145,14 +145,6 @@ __device__ __forceinline__ void column_azimuth_table_r2(const SweepDesc* s_sw, i
     }
 }
 
-// what the sampler needs about the column's current sweep pair, kept in registers while k is unchanged
-// (k moves once every few levels): the two azimuth entries and the pair's weight polynomial
-struct PairCache {
-    int k;                        // pair the cache holds (INT_MIN: none)
-    AzEntry ea, eb;
-    float q1, q2, q3, q4, q5;
-};
-
 // UNI: every sweep shares ONE range table with constant gate spacing and every sweep / pair is usable
 // and poly-validated (the common case: PRD.get_vol_data with aligned ranges) — the range-table
 // constants are then kernel uniforms, R[j] is an FMA and no per-sweep flag is consulted.  Otherwise
@@ -161,7 +153,7 @@ template <int NF, bool EMIT, bool UNI>
 __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, const void* const* val,
                                          const LevelConst& lc, const LevelSweep* __restrict__ ls,
                                          const LevelPair* __restrict__ lp, bool level_slow, double cphi,
-                                         int& k, int& k6, PairCache& pc, float (&res)[NF], VoxelInfo& vi) {
+                                         int& k, int& k6, float (&res)[NF], VoxelInfo& vi) {
     const int ne = c.ne;
     const float fill32 = c.fill32;
     // RadarGridC.pyx:146-149 — the reference's own operations: r2 is bit-identical
@@ -360,8 +352,6 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
     q.fs = s_fs;
 
     int k = -1, k6 = 0;
-    PairCache pc;
-    pc.k = -0x7fffffff;
     double* out_col = p.out + col;
     const LevelSweep* ls = P.r2.ls;
     const LevelPair* lp = P.r2.lp;
@@ -370,8 +360,7 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
     for (int iz = 0; iz < p.nz; ++iz) {
         float res[NF];
         VoxelInfo vi;
-        r2_voxel<NF, EMIT, UNI>(c, q, p.vol.val, p.levels[iz], ls, lp, (P.level_slow >> iz) & 1ull, cphi, k, k6, pc,
-                                res, vi);
+        r2_voxel<NF, EMIT, UNI>(c, q, p.vol.val, p.levels[iz], ls, lp, (P.level_slow >> iz) & 1ull, cphi, k, k6, res, vi);
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             double* dst = out_col + (size_t)f * (size_t)p.field_stride;
