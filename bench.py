@@ -122,6 +122,14 @@ def _cpu_impl():
     return port, "port"
 
 
+_SHARED = {}      # inherited by forked workers: no pickling of the 48 MB volume per task
+
+
+def _cpu_chunk_shared(levels):
+    a = _SHARED["args"]
+    return _cpu_chunk((a[0], a[1], a[2], a[3], a[4], levels, a[5]))
+
+
 def _cpu_chunk(args):
     mod_kind, vol, h, gx, gy, levels, blind = args
     mod, _ = _cpu_impl()
@@ -151,11 +159,13 @@ def cpu_sample(cfg, nlevels, workers):
         lv = np.ascontiguousarray(levels[(w * nlevels) % levels.size:][:nlevels])
         if lv.size == 0:
             lv = np.ascontiguousarray(levels[:nlevels])
-        chunks.append((kind, (va, vr, fe, vv), h, gx, gy, lv, blind))
-    t0 = time.perf_counter()
+        chunks.append(lv)
+    _SHARED["args"] = (kind, (va, vr, fe, vv), h, gx, gy, blind)
     with ctx.Pool(workers) as pool:
-        res = pool.map(_cpu_chunk, chunks)
-    wall = time.perf_counter() - t0
+        pool.map(_cpu_chunk_shared, [np.ascontiguousarray(levels[:1])] * workers)   # start the workers
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_chunk_shared, chunks, chunksize=1)
+        wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     return total / wall, kind, workers, "%s: %d workers x %d levels, %dx%d grid" % (
         cfg["name"], workers, nlevels, gx.shape[0], gx.shape[1])
@@ -171,8 +181,6 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
     vals = []
-    for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
-        cpu_sample(cfg, 1, workers)
     t_all = time.perf_counter()
     desc = kind = None
     for _ in range(args.steps):
@@ -541,7 +549,7 @@ def main():
                     help="device moment layout: f32 = production pair layout, f64 = reference arithmetic")
     ap.add_argument("--cpu-levels", type=int, default=40,
                     help="levels of the full grid timed on 1 host core (40 = all of C3, about 11 s)")
-    ap.add_argument("--ref-levels", type=int, default=2, help="levels per worker for --impl reference")
+    ap.add_argument("--ref-levels", type=int, default=3, help="levels per worker for --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--network", dest="network", action="store_true", default=True,
                     help="also run the C4 network composite sharded over the ranks (default)")
