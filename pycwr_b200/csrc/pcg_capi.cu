@@ -365,27 +365,32 @@ void build_level_pairs(const LevelSweep* ls, int nz, int ne, LevelPair* lp) {
     }
 }
 
-template <int NF, bool EMIT, bool UNI>
+template <int NF, bool EMIT, bool UNI, bool LAZY>
 int launch_fast_one(const R2Args& args, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024)   // opt in to large dynamic shared memory (per device, cheap)
-        CUDA_TRY(cudaFuncSetAttribute(cappi3d_r2_kernel<NF, EMIT, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    cappi3d_r2_kernel<NF, EMIT, UNI><<<grid, block, smem, st>>>(args);
+        CUDA_TRY(cudaFuncSetAttribute(cappi3d_r2_kernel<NF, EMIT, UNI, LAZY>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cappi3d_r2_kernel<NF, EMIT, UNI, LAZY><<<grid, block, smem, st>>>(args);
     return PCG_OK;
+}
+
+template <int NF, bool EMIT>
+int launch_fast_flags(const R2Args& args, bool uni, bool lazy, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    if (uni) return lazy ? launch_fast_one<NF, EMIT, true, true>(args, grid, block, smem, st)
+                         : launch_fast_one<NF, EMIT, true, false>(args, grid, block, smem, st);
+    return lazy ? launch_fast_one<NF, EMIT, false, true>(args, grid, block, smem, st)
+                : launch_fast_one<NF, EMIT, false, false>(args, grid, block, smem, st);
 }
 
 template <bool EMIT>
 int launch_fast_nf(const R2Args& args, int nf, bool uni, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    const bool lazy = args.lazy_az != 0;
     int rc;
-    switch (nf * 2 + (uni ? 1 : 0)) {
-        case 2: rc = launch_fast_one<1, EMIT, false>(args, grid, block, smem, st); break;
-        case 3: rc = launch_fast_one<1, EMIT, true>(args, grid, block, smem, st); break;
-        case 4: rc = launch_fast_one<2, EMIT, false>(args, grid, block, smem, st); break;
-        case 5: rc = launch_fast_one<2, EMIT, true>(args, grid, block, smem, st); break;
-        case 6: rc = launch_fast_one<3, EMIT, false>(args, grid, block, smem, st); break;
-        case 7: rc = launch_fast_one<3, EMIT, true>(args, grid, block, smem, st); break;
-        case 8: rc = launch_fast_one<4, EMIT, false>(args, grid, block, smem, st); break;
-        case 9: rc = launch_fast_one<4, EMIT, true>(args, grid, block, smem, st); break;
+    switch (nf) {
+        case 1: rc = launch_fast_flags<1, EMIT>(args, uni, lazy, grid, block, smem, st); break;
+        case 2: rc = launch_fast_flags<2, EMIT>(args, uni, lazy, grid, block, smem, st); break;
+        case 3: rc = launch_fast_flags<3, EMIT>(args, uni, lazy, grid, block, smem, st); break;
+        case 4: rc = launch_fast_flags<4, EMIT>(args, uni, lazy, grid, block, smem, st); break;
         default: return fail(PCG_ERR_ARG, "nfield must be 1..%d", kMaxFields);
     }
     if (rc != PCG_OK) return rc;
@@ -463,7 +468,10 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     // shared memory: descriptors + the per-thread azimuth table [thread][sweep]; pick the block
     // size so that several blocks still fit an SM (227 KB)
     const size_t fixed = (size_t)vol->ne * (sizeof(SweepDesc) + sizeof(FastSweep)) + (size_t)(vol->ne - 1) * sizeof(PairDesc);
-    const size_t per_thread = (size_t)vol->ne * (sizeof(AzEntry) + (d_idx ? sizeof(int) : 0));
+    // azimuth brackets: a [sweep] table per column up to 16 sweeps, on demand (2-entry cache) beyond
+    RA.lazy_az = vol->ne > 16 ? 1 : 0;
+    const size_t per_thread = RA.lazy_az ? 2 * (sizeof(AzEntry) + sizeof(int) + (d_idx ? sizeof(int) : 0))
+                                         : (size_t)vol->ne * (sizeof(AzEntry) + (d_idx ? sizeof(int) : 0));
     int threads = 256;
     while (threads > 32 && fixed + per_thread * threads > 56 * 1024) threads >>= 1;
     const size_t smem = fixed + per_thread * threads;

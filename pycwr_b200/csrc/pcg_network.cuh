@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __
         c.fill32 = fill32;
         c.nearest_gate = p.nearest_gate != 0; c.lowest_sweep = p.lowest_sweep != 0;
         c.highest_sweep = p.highest_sweep != 0;
+        c.my_tag = nullptr; c.azt = nullptr; c.az = 0.0;
         // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
         const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? expf(-(float)d2 * R.inv_r2inf4) : 1.f;
 

@@ -87,59 +87,23 @@ struct SlowFrame {
     int k6;
 };
 
-template <int NF, bool EMIT>
+template <int NF, bool EMIT, bool LAZY>
 __device__ __noinline__ void slow_voxel(SlowFrame* fr, const void* const* val, double cphi, float* res) {
     float tmp[NF];
-    fast_voxel<NF, EMIT>(fr->c, val, fr->lc, cphi, fr->k6, tmp, fr->vi);
+    fast_voxel<NF, EMIT, LAZY>(fr->c, val, fr->lc, cphi, fr->k6, tmp, fr->vi);
 #pragma unroll
     for (int f = 0; f < NF; ++f) res[f] = tmp[f];
 }
 
-// Azimuth bracket of every sweep for one column (RadarGridC.pyx:282-289) from the {A[i], 1 / gap_i}
-// table (gap_i = A[i+1] - A[i], the last entry holds the wrap interval A[0] + 360 - A[naz-1]): the
-// arithmetic guess is verified against the two entries it brackets and repaired by +-1 steps or the
-// reference's bisection, so iaz is exactly bisect_right; the FP32 weight is one multiply.
+// azimuth bracket of every sweep for one column, eagerly ([sweep] table per column)
 template <bool EMIT>
 __device__ __forceinline__ void column_azimuth_table_r2(const SweepDesc* s_sw, int ne, const double2* __restrict__ azt,
                                                         double az, AzEntry* my_az, int* my_iaz, unsigned stride) {
 #pragma unroll 1
     for (int sw = 0; sw < ne; ++sw) {
-        const SweepDesc& d = s_sw[sw];
         AzEntry e;
-        e.row = 0xffffffffu; e.w = 0.f;
-        int rec = -1;
-        const int naz = d.naz;
-        if (naz >= 2 && d.ng >= 2) {
-            const double2* T = azt + d.az_off;
-            int g = __double2int_rd(mul(sub(az, d.az_first), d.az_inv_step)) + 1;
-            g = min(max(g, 0), naz);
-            double2 lo = __ldg(T + max(g - 1, 0));
-            double hi = __ldg(&T[min(g, naz - 1)].x);
-            bool ok = false;
-#pragma unroll 1
-            for (int it = 0; it < 4; ++it) {
-                const bool lo_ok = (g == 0) | !(az < lo.x);
-                const bool hi_ok = (g == naz) | (az < hi);
-                if (lo_ok & hi_ok) { ok = true; break; }
-                g += lo_ok ? 1 : -1;
-                lo = __ldg(T + max(g - 1, 0));
-                hi = __ldg(&T[min(g, naz - 1)].x);
-            }
-            if (!ok) {                                   // irregular table: the reference's bisection
-                int l = 0, h = naz;
-                while (l < h) { const int m = (l + h) >> 1; if (az < __ldg(&T[m].x)) h = m; else l = m + 1; }
-                g = l;
-            }
-            const bool wrapped = g >= naz;
-            const int iaz = wrapped ? 0 : g;
-            const int row_lo = (iaz == 0) ? naz - 1 : iaz - 1;
-            if (!ok || iaz == 0) lo = __ldg(T + row_lo);
-            // (az - 360) - (A[naz-1] - 360) when wrapped, az - (A[naz-1] - 360) below the first ray
-            const double dlt = (iaz == 0 && !wrapped) ? sub(az, sub(lo.x, 360.0)) : sub(az, lo.x);
-            e.row = (unsigned)d.val_off + (unsigned)row_lo * (unsigned)d.ng;
-            e.w = (float)dlt * (float)lo.y;
-            rec = iaz | (wrapped ? (1 << 30) : 0);
-        }
+        int rec;
+        az_bracket_one(s_sw[sw], azt, az, e, rec);
         my_az[(size_t)sw * stride] = e;
         if (EMIT) my_iaz[(size_t)sw * stride] = rec;
     }
@@ -149,7 +113,7 @@ __device__ __forceinline__ void column_azimuth_table_r2(const SweepDesc* s_sw, i
 // and poly-validated (the common case: PRD.get_vol_data with aligned ranges) — the range-table
 // constants are then kernel uniforms, R[j] is an FMA and no per-sweep flag is consulted.  Otherwise
 // they are read per sweep from `q.fs` and per gate from `q.h_t`.
-template <int NF, bool EMIT, bool UNI>
+template <int NF, bool EMIT, bool UNI, bool LAZY = false>
 __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, const void* const* val,
                                          const LevelConst& lc, const LevelSweep* __restrict__ ls,
                                          const LevelPair* __restrict__ lp, bool level_slow, double cphi,
@@ -222,8 +186,7 @@ __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, con
                 w_r = (float)sub(r2, __hiloint2double(hv.y, hv.x)) * __int_as_float(hv.w) *
                       rcp_approx(rf + __int_as_float(hv.z));
             }
-            const AzEntry* az = c.my_az + (size_t)lower * c.az_stride;
-            const AzEntry ea = az[0];
+            const AzEntry ea = az_entry<LAZY>(c, lower);
             vi.r = (double)rf;
             if (pair) {
                 const int4 lk = __ldg(reinterpret_cast<const int4*>(lp + (k + 1)) + 1);  // {rho2 (lo, hi), rho, b1}
@@ -235,7 +198,7 @@ __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, con
                 w_el = fmaf(w_el, u, qa.y);
                 w_el = fmaf(w_el, u, qa.x);
                 w_el *= u;
-                const AzEntry eb = az[c.az_stride];
+                const AzEntry eb = az_entry<LAZY>(c, lower + 1);
 #pragma unroll
                 for (int fi = 0; fi < NF; ++fi) {
                     const float4* v = static_cast<const float4*>(val[fi]);
@@ -256,12 +219,11 @@ __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, con
                 }
             }
             if (EMIT) {
-                const int* ia = c.my_iaz + (size_t)lower * c.az_stride;
-                const int ra = ia[0];
+                const int ra = az_record<LAZY>(c, lower);
                 vi.ir0 = gi; vi.iaz0 = ra & 0x3fffffff; vi.fl0 = (ra >> 30) & 1;
                 vi.iaz1 = vi.ir1 = vi.fl1 = -1;
                 if (pair) {
-                    const int rb2 = ia[c.az_stride];
+                    const int rb2 = az_record<LAZY>(c, lower + 1);
                     vi.ir1 = gi; vi.iaz1 = rb2 & 0x3fffffff; vi.fl1 = (rb2 >> 30) & 1;
                 }
             }
@@ -273,7 +235,7 @@ __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, con
     SlowFrame fr;
     fr.c = c; fr.lc = lc; fr.k6 = k6;
     float tmp[NF];
-    slow_voxel<NF, EMIT>(&fr, val, cphi, tmp);
+    slow_voxel<NF, EMIT, LAZY>(&fr, val, cphi, tmp);
 #pragma unroll
     for (int f = 0; f < NF; ++f) res[f] = tmp[f];
     k6 = fr.k6;
@@ -288,12 +250,13 @@ struct R2Args {
     FastArgs base;
     R2Ctx r2;
     unsigned long long level_slow;      // bit iz: level takes the reference chain
+    int lazy_az;                        // many-sweep volume: azimuth brackets on demand (2-entry cache per column)
 };
 
 #ifndef R2_MINB
 #define R2_MINB 5
 #endif
-template <int NF, bool EMIT, bool UNI>
+template <int NF, bool EMIT, bool UNI, bool LAZY>
 __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_constant__ R2Args P) {
     const FastArgs& p = P.base;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -301,8 +264,12 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
     SweepDesc* s_sw = reinterpret_cast<SweepDesc*>(smem_raw);
     PairDesc* s_pr = reinterpret_cast<PairDesc*>(s_sw + ne);
     FastSweep* s_fs = reinterpret_cast<FastSweep*>(s_pr + (ne - 1));
-    AzEntry* s_az = reinterpret_cast<AzEntry*>(s_fs + ne);                 // [thread][sweep]
-    int* s_iaz = reinterpret_cast<int*>(s_az + (size_t)ne * blockDim.x);   // EMIT only, [thread][sweep]
+    // azimuth entries per thread: [thread][sweep] (eager), or a tagged 2-entry cache [thread][2] (lazy)
+    constexpr bool lazy = LAZY;
+    const int nslot = lazy ? 2 : ne;
+    AzEntry* s_az = reinterpret_cast<AzEntry*>(s_fs + ne);
+    int* s_tag = reinterpret_cast<int*>(s_az + (size_t)nslot * blockDim.x);          // lazy only
+    int* s_iaz = s_tag + (lazy ? (size_t)nslot * blockDim.x : 0);                   // EMIT only
     stage_sweeps(s_sw, p.vol.sweeps, ne);
     stage_pairs(s_pr, p.pairs, ne - 1, p.twoa);
     {
@@ -340,14 +307,20 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
 
     ColumnCtx c;
     c.s_sw = s_sw; c.s_pr = s_pr;
-    c.my_az = s_az + (size_t)threadIdx.x * ne; c.my_iaz = s_iaz + (size_t)threadIdx.x * ne; c.az_stride = 1;
+    c.my_az = s_az + (size_t)threadIdx.x * nslot; c.my_iaz = EMIT ? s_iaz + (size_t)threadIdx.x * nslot : nullptr;
+    c.az_stride = 1;
+    // (only the lazy variant reads these: constants otherwise, so they cost no registers)
+    c.my_tag = LAZY ? s_tag + (size_t)threadIdx.x * nslot : nullptr;
+    c.azt = LAZY ? P.r2.az_t : nullptr;
+    c.az = LAZY ? az : 0.0;
     c.ne = ne;
     c.rg_t = reinterpret_cast<const double2*>(p.vol.rng);
     c.a2 = p.a2; c.twoa = p.twoa; c.guard = p.guard; c.inv_twoa = p.inv_twoa;
     c.fill32 = fill32;
     c.nearest_gate = p.nearest_gate != 0; c.lowest_sweep = p.lowest_sweep != 0; c.highest_sweep = p.highest_sweep != 0;
-    column_azimuth_table_r2<EMIT>(s_sw, ne, P.r2.az_t, az, s_az + (size_t)threadIdx.x * ne,
-                                  s_iaz + (size_t)threadIdx.x * ne, 1);
+    if (lazy) { c.my_tag[0] = -1; c.my_tag[1] = -1; }
+    else column_azimuth_table_r2<EMIT>(s_sw, ne, P.r2.az_t, az, s_az + (size_t)threadIdx.x * ne,
+                                       s_iaz + (size_t)threadIdx.x * ne, 1);
     R2Ctx q = P.r2;
     q.fs = s_fs;
 
@@ -360,7 +333,7 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
     for (int iz = 0; iz < p.nz; ++iz) {
         float res[NF];
         VoxelInfo vi;
-        r2_voxel<NF, EMIT, UNI>(c, q, p.vol.val, p.levels[iz], ls, lp, (P.level_slow >> iz) & 1ull, cphi, k, k6, res, vi);
+        r2_voxel<NF, EMIT, UNI, LAZY>(c, q, p.vol.val, p.levels[iz], ls, lp, (P.level_slow >> iz) & 1ull, cphi, k, k6, res, vi);
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             double* dst = out_col + (size_t)f * (size_t)p.field_stride;
