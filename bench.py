@@ -287,14 +287,14 @@ def bench_network(args, torch, dist, dev, rank, world):
         maxrows = max(b[1] - b[0] for b in bounds)
         padded = torch.zeros((nz, maxrows, nlon), dtype=torch.float64, device=dev)
         padded[:, :rows] = comp
-        parts = [torch.empty_like(padded) for _ in range(world)]
-        dist.all_gather(parts, padded)
+        parts = torch.empty((world, nz, maxrows, nlon), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(parts, padded)
         torch.cuda.synchronize()
         dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(steps):
-            dist.all_gather(parts, padded)
+            dist.all_gather_into_tensor(parts, padded)
         g1.record()
         torch.cuda.synchronize()
         gather_ms = float(g0.elapsed_time(g1))
