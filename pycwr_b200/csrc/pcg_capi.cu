@@ -747,7 +747,9 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         }                                                                                      \
     } while (0)
     VOL_TRY(cudaMalloc((void**)&v->d_az, (n_az ? n_az : 1) * sizeof(double)));
-    VOL_TRY(cudaMalloc((void**)&v->d_rng, (n_rng ? n_rng : 1) * rsz));
+    // (+2 entries: the straight-line samplers read entries gi-1 and gi before they know the sweep is usable)
+    VOL_TRY(cudaMalloc((void**)&v->d_rng, (n_rng + 2) * rsz));
+    VOL_TRY(cudaMemset(v->d_rng, 0, (n_rng + 2) * rsz));
     VOL_TRY(cudaMalloc((void**)&v->d_sweeps, v->sweeps.size() * sizeof(SweepDesc)));
     for (int f = 0; f < nfield; ++f) VOL_TRY(cudaMalloc(&v->d_val[f], (n_val ? n_val : 1) * vsz));
     v->bytes = n_az * sizeof(double) + n_rng * rsz + v->sweeps.size() * sizeof(SweepDesc) +
@@ -828,8 +830,9 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         }
         v->pairs = pairs;
         {   // r2-space descriptors: gate thresholds per range table, per-sweep / per-pair constants
-            std::vector<double2> gt(n_rng ? n_rng : 1);
-            std::vector<GateAux> ht(n_rng ? n_rng : 1);
+            std::vector<double2> gt(n_rng + 2, make_double2(0.0, 0.0));
+            std::vector<GateAux> ht(n_rng + 2);
+            memset(ht.data(), 0, ht.size() * sizeof(GateAux));
             std::vector<FastSweep> fs(ne);
             memset(fs.data(), 0, fs.size() * sizeof(FastSweep));
             for (int s = 0; s < ne; ++s) {

@@ -172,8 +172,9 @@ __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, con
         const float r2f = (float)r2;
         const float rinv = rsqrt_approx(r2f);
         const float rf = r2f * rinv;
-        const int gi = min(max(__float2int_rd(fmaf(rf, inv_step, c0)), 1), ngm1);
-        const unsigned gidx = rng_off + (unsigned)(gi - 1);
+        // (a degenerate sweep has no gate interval to index: nothing is loaded for it)
+        const int gi = usable ? min(max(__float2int_rd(fmaf(rf, inv_step, c0)), 1), ngm1) : 1;
+        const unsigned gidx = usable ? rng_off + (unsigned)(gi - 1) : q.u_rng_off;
         const double2 tg = __ldg(q.g_t + gidx);          // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
         if (usable & (r2 >= tg.x) & (r2 < tg.y)) {
             float w_r;

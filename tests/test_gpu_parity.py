@@ -209,6 +209,43 @@ def test_edge_cases():
     assert_parity(got, want, what="80 levels")
 
 
+def test_packed_volume_with_degenerate_and_ragged_sweeps():
+    """Sweeps with a single gate / a single ray and per-sweep range tables inside a packed volume:
+    the r2 path must route them to the reference chain (no table is indexed for a degenerate sweep)."""
+    rng = np.random.default_rng(5)
+    az = [synth.azimuth_table(rng, n) for n in (24, 1, 30, 24, 28)]
+    rg = [np.arange(1, 41) * 500.0, np.arange(1, 31) * 500.0, np.array([700.0]), np.arange(1, 36) * 600.0,
+          np.arange(1, 41) * 500.0]
+    fe = np.array([0.5, 1.5, 3.0, 6.0, 12.0])
+    vv = [synth.stress_moment(rng, a.size, r.size, -5.0, 70.0) for a, r in zip(az, rg)]
+    g = rng.uniform(-22e3, 22e3, (23, 2, 19)).transpose(1, 0, 2)
+    gx, gy = np.ascontiguousarray(g[0]), np.ascontiguousarray(g[1])
+    lv = np.linspace(100.0, 6000.0, 13)
+    for blind in ("mask", "hybrid", "nearest_valid"):
+        got, gi = G.get_CAPPI_3d(az, rg, fe, vv, 35.0, gx, gy, lv, FILL, None, blind, return_index=True)
+        want, wi = O.get_CAPPI_3d(az, rg, fe, vv, 35.0, gx, gy, lv, FILL, None, blind, return_index=True)
+        assert_parity(got, want, gi, wi, "degenerate/ragged " + blind)
+    assert_parity(G.get_CR_xy(az, rg, fe, vv, 35.0, gx, gy, FILL), O.get_CR_xy(az, rg, fe, vv, 35.0, gx, gy, FILL),
+                  what="degenerate/ragged CR")
+
+
+def test_levels_below_the_antenna_and_negative_elevations():
+    """Levels at / below the radar height and a negative lowest elevation (mountain radar): the r2
+    thresholds are monotone only above the antenna, everything else must take the reference chain."""
+    rng = np.random.default_rng(9)
+    ne = 4
+    az = [synth.azimuth_table(rng, 36) for _ in range(ne)]
+    rg = [np.arange(1, 61) * 1000.0] * ne
+    vv = [synth.stress_moment(rng, 36, 60, -5.0, 70.0) for _ in range(ne)]
+    gx, gy = np.meshgrid(np.linspace(-50e3, 50e3, 37), np.linspace(-48e3, 48e3, 33), indexing="ij")
+    lv = np.array([-200.0, 0.0, 1500.0, 2499.0, 2500.0, 2501.0, 3000.0, 4000.0, 7000.0])
+    for fe in (np.array([-0.8, 0.0, 1.0, 3.0]), np.array([0.0, 0.7, 2.0, 5.0]), np.array([0.5, 1.5, 2.5, 4.0])):
+        for blind in ("mask", "hybrid"):
+            got, gi = G.get_CAPPI_3d(az, rg, fe, vv, 2500.0, gx, gy, lv, FILL, None, blind, return_index=True)
+            want, wi = O.get_CAPPI_3d(az, rg, fe, vv, 2500.0, gx, gy, lv, FILL, None, blind, return_index=True)
+            assert_parity(got, want, gi, wi, "antenna-level %s %s" % (fe[0], blind))
+
+
 def test_inputs_not_mutated_and_output_owned():
     cfg = synth.config(1, scale=0.1)
     va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
