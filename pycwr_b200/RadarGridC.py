@@ -182,11 +182,16 @@ def interp_ppi(az, r, az_0, az_1, r_0, r_1, mat_00, mat_01, mat_10, mat_11, fill
 VALUE_DTYPE = "f32"
 
 
-def _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue):
+def _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue, *grids):
     if isinstance(vol_value, DeviceVolume):
         return vol_value, False
+    dtype = VALUE_DTYPE
+    # NaN / inf target coordinates: the reference's result then hinges on how every comparison and
+    # lerp treats NaN operand by operand; only the float64 layout restates it operation by operation
+    if dtype == "f32" and any(not np.isfinite(g.sum()) for g in grids):     # one pass, no temporaries
+        dtype = "f64"
     return DeviceVolume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue=float(fillvalue),
-                        value_dtype=VALUE_DTYPE), True
+                        value_dtype=dtype), True
 
 
 def _new_output(shape):
@@ -234,7 +239,7 @@ def get_CR_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height, Gr
     gx = _f64_2d(GridX, "GridX")
     gy = _f64_2d(GridY, "GridY")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
-    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue)
+    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue, gx, gy)
     nx, ny = gx.shape[0], gy.shape[1]
     out = _new_output((nx, ny))
     try:
@@ -273,7 +278,7 @@ def get_CAPPI_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height,
     gy = _f64_2d(GridY, "GridY")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
     blind_code = _resolve_blind_code(blind_method)
-    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue)
+    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue, gx, gy)
     try:
         levels = np.array([float(level_height)], dtype=np.float64)
         out, idx = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code,
@@ -295,7 +300,7 @@ def get_CAPPI_3d(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height,
     levels = _f64_1d(level_heights, "level_heights")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
     blind_code = _resolve_blind_code(blind_method)
-    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue)
+    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue, gx, gy, levels)
     try:
         out, idx = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code, 1.0,
                           return_index)

@@ -246,6 +246,36 @@ def test_levels_below_the_antenna_and_negative_elevations():
             assert_parity(got, want, gi, wi, "antenna-level %s %s" % (fe[0], blind))
 
 
+@pytest.mark.parametrize("shape", [(1, 50), (50, 1), (3, 7), (5, 3), (4, 8), (9, 33)])
+def test_odd_grid_shapes(shape):
+    """Every warp-footprint variant (4 x 8 patches, 1 x 32 rows) and partially filled tiles."""
+    cfg = synth.config(3, style="stress", scale=0.02)
+    va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    gx, gy = rng.uniform(-140e3, 140e3, shape), rng.uniform(-140e3, 140e3, shape)
+    lv = cfg["levels"][::5]
+    got, gi = G.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, "hybrid", return_index=True)
+    want, wi = O.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, "hybrid", return_index=True)
+    assert_parity(got, want, gi, wi, "grid %dx%d" % shape)
+    assert_parity(G.get_CR_xy(va, vr, fe, vv, h, gx, gy, FILL), O.get_CR_xy(va, vr, fe, vv, h, gx, gy, FILL),
+                  what="CR grid %dx%d" % shape)
+
+
+def test_non_finite_grid_coordinates():
+    """NaN / inf grid coordinates follow the reference's comparisons (every test on NaN is false)."""
+    cfg = synth.config(1, style="stress", scale=0.05)
+    va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
+    gx, gy = cfg["GridX"].copy(), cfg["GridY"].copy()
+    gx[2, 3] = np.nan
+    gy[5, 1] = np.inf
+    gx[7, 7] = -np.inf
+    gy[9, 2] = np.nan
+    lv = np.array([800.0, 2500.0, 6000.0])
+    got = G.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, "hybrid")
+    want = O.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, "hybrid")
+    assert_parity(got, want, what="non-finite grid")
+
+
 def test_inputs_not_mutated_and_output_owned():
     cfg = synth.config(1, scale=0.1)
     va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
