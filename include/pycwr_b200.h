@@ -204,6 +204,25 @@ int pcg_column_products_dev(const double *d_volume, const double *d_levels, int 
                             double *d_cr, double *d_vil, double *d_et, unsigned char *d_topped,
                             void *stream);
 
+/* ---- the gridding step of retrieve_wind_volume_xy (`pycwr/retrieve/WindField.py`) ----------
+ * pcg_wind_gather: _grid_vvp_retrieval_xy (:629-689) with _aggregate_neighbors (:597-626) for one sweep.
+ *   samples: [10][ns] float64 structure of arrays in the order x, y, z, u, v, fit_rmse, valid_count,
+ *   valid_fraction, condition_number, azimuth_sector_count (already reduced to the finite samples,
+ *   _flatten_valid_vvp_samples :561-594); targets [nt]; max_radius_m <= radius_m disables the expansion.
+ *   out_f64: [5][nt] u, v, z, fit_rmse, condition_number (NaN where undefined); out_i32: [3][nt]
+ *   valid_count, neighbor_count, azimuth_sector_count; expanded: [nt] uint8.
+ * pcg_wind_vertical: _vertical_profile_from_sweeps (:692-810) + _compute_voxel_quality (:813-851) for
+ *   every column (_reconstruct_wind_volume_chunk :1183-1229).  sweeps: [7][nsweep][ncol] float64 in the
+ *   order z, u, v, fit_rmse, valid_count, neighbor_count, expanded_radius; out_f64: [5][nz][ncol] u, v,
+ *   fit_rmse, sweep_spread_m, quality_score; out_i32: [4][nz][ncol] valid_count, source_sweep_count,
+ *   neighbor_count, effective_vertical_support; quality_flag: [nz][ncol] uint8. */
+int pcg_wind_gather(const double *samples, long long ns, const double *target_x, const double *target_y,
+                    long long nt, double radius_m, double max_radius_m, int min_neighbors, double power,
+                    double *out_f64, int32_t *out_i32, unsigned char *expanded);
+int pcg_wind_vertical(const double *sweeps, int nsweep, long long ncol, const double *level_heights, int nz,
+                      double vertical_tolerance_m, double max_vertical_gap_m, double *out_f64,
+                      int32_t *out_i32, unsigned char *quality_flag);
+
 /* ---- diagnostics: the device's geometry inversion for a list of points (one level), used by
  *      the tests to measure bit-agreement of the device math with glibc. ------------------- */
 int pcg_debug_cartesian_to_antenna(const double *x, const double *y, size_t n, double z, double h,

@@ -21,6 +21,7 @@
 #include "pcg_r2.cuh"
 #include "pcg_network.cuh"
 #include "pcg_products.cuh"
+#include "pcg_wind.cuh"
 
 using namespace pcg;
 
@@ -1729,6 +1730,90 @@ extern "C" int pcg_network_gates(int ne, const double* fix_elev, const double* f
     CUDA_TRY(cudaGetLastError());
     if (mask) CUDA_TRY(cudaMemcpyAsync(mask, A.mask, nvox, cudaMemcpyDeviceToHost, st));
     if (quality) CUDA_TRY(cudaMemcpyAsync(quality, A.quality, nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+// ---- wind-volume gridding step (retrieve_wind_volume_xy) ------------------------------------------
+
+extern "C" int pcg_wind_gather(const double* samples, long long ns, const double* target_x, const double* target_y,
+                               long long nt, double radius_m, double max_radius_m, int min_neighbors, double power,
+                               double* out_f64, int32_t* out_i32, unsigned char* expanded) {
+    if (ns < 0 || nt < 0) return fail(PCG_ERR_ARG, "sizes must be non-negative");
+    if (!out_f64 || !out_i32 || !expanded) return fail(PCG_ERR_ARG, "NULL output pointer");
+    if (nt == 0) return PCG_OK;
+    int rc;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    const size_t b_s = (size_t)kWindFields * (size_t)(ns ? ns : 1) * sizeof(double), b_t = (size_t)nt * sizeof(double);
+    if ((rc = g_scratch[S_AUX4].ensure(b_s))) return rc;
+    if ((rc = g_scratch[S_GX].ensure(b_t)) || (rc = g_scratch[S_GY].ensure(b_t))) return rc;
+    if ((rc = g_scratch[S_OUT].ensure(5 * b_t)) || (rc = g_scratch[S_IDX].ensure(3 * (size_t)nt * sizeof(int))) ||
+        (rc = g_scratch[S_AUX2].ensure((size_t)nt)))
+        return rc;
+    if (ns) CUDA_TRY(cudaMemcpyAsync(g_scratch[S_AUX4].ptr, samples, (size_t)kWindFields * ns * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, target_x, b_t, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, target_y, b_t, cudaMemcpyHostToDevice, st));
+    WindGatherArgs A;
+    A.samples = (const double*)g_scratch[S_AUX4].ptr; A.ns = ns;
+    A.tx = (const double*)g_scratch[S_GX].ptr; A.ty = (const double*)g_scratch[S_GY].ptr; A.nt = nt;
+    A.r1sq = radius_m * radius_m;
+    A.r2sq = max_radius_m * max_radius_m;
+    A.min_neighbors = min_neighbors; A.power = power;
+    double* o = (double*)g_scratch[S_OUT].ptr;
+    A.u = o; A.v = o + nt; A.z = o + 2 * nt; A.rmse = o + 3 * nt; A.cond = o + 4 * nt;
+    int* oi = (int*)g_scratch[S_IDX].ptr;
+    A.valid_count = oi; A.neighbor_count = oi + nt; A.azsec = oi + 2 * nt;
+    A.expanded = (unsigned char*)g_scratch[S_AUX2].ptr;
+    wind_gather_kernel<<<(unsigned)((nt + kWindTile - 1) / kWindTile), kWindTile, 0, st>>>(A);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_f64, o, 5 * b_t, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_i32, oi, 3 * (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(expanded, A.expanded, (size_t)nt, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+extern "C" int pcg_wind_vertical(const double* sweeps, int nsweep, long long ncol, const double* level_heights, int nz,
+                                 double vertical_tolerance_m, double max_vertical_gap_m, double* out_f64,
+                                 int32_t* out_i32, unsigned char* quality_flag) {
+    if (nsweep < 0 || nsweep > kWindMaxSweeps) return fail(PCG_ERR_ARG, "nsweep must be in [0, %d]", kWindMaxSweeps);
+    if (ncol < 0 || nz < 0) return fail(PCG_ERR_ARG, "sizes must be non-negative");
+    if (!out_f64 || !out_i32 || !quality_flag) return fail(PCG_ERR_ARG, "NULL output pointer");
+    const size_t nvox = (size_t)nz * (size_t)ncol;
+    if (nvox == 0) return PCG_OK;
+    int rc;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    const size_t n_in = (size_t)7 * (size_t)(nsweep ? nsweep : 1) * (size_t)ncol;
+    if ((rc = g_scratch[S_AUX4].ensure(n_in * sizeof(double))) || (rc = g_scratch[S_TMP0].ensure((size_t)nz * sizeof(double))) ||
+        (rc = g_scratch[S_OUT].ensure(5 * nvox * sizeof(double))) || (rc = g_scratch[S_IDX].ensure(4 * nvox * sizeof(int))) ||
+        (rc = g_scratch[S_AUX2].ensure(nvox)))
+        return rc;
+    if (nsweep) CUDA_TRY(cudaMemcpyAsync(g_scratch[S_AUX4].ptr, sweeps, (size_t)7 * nsweep * ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_TMP0].ptr, level_heights, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, st));
+    WindVerticalArgs A;
+    const double* in = (const double*)g_scratch[S_AUX4].ptr;
+    const size_t plane = (size_t)nsweep * (size_t)ncol;
+    A.sz = in; A.su = in + plane; A.sv = in + 2 * plane; A.srmse = in + 3 * plane;
+    A.scount = in + 4 * plane; A.sneigh = in + 5 * plane; A.sexp = in + 6 * plane;
+    A.nsweep = nsweep; A.ncol = ncol;
+    A.levels = (const double*)g_scratch[S_TMP0].ptr; A.nz = nz;
+    A.tol = vertical_tolerance_m; A.max_gap = max_vertical_gap_m;
+    double* o = (double*)g_scratch[S_OUT].ptr;
+    A.u = o; A.v = o + nvox; A.rmse = o + 2 * nvox; A.spread = o + 3 * nvox; A.score = o + 4 * nvox;
+    int* oi = (int*)g_scratch[S_IDX].ptr;
+    A.valid_count = oi; A.source_count = oi + nvox; A.neighbor_count = oi + 2 * nvox; A.support = oi + 3 * nvox;
+    A.flag = (unsigned char*)g_scratch[S_AUX2].ptr;
+    wind_vertical_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(A);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_f64, o, 5 * nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_i32, oi, 4 * nvox * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(quality_flag, A.flag, nvox, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return PCG_OK;
 }
