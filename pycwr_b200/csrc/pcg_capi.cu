@@ -301,7 +301,7 @@ bool fit_pair_r2(FastSweep* f, double e0, double e1) {
 
 // Per (level, sweep) thresholds for one radar: ls[(nz)][ne + 2], flags in slow_bits (bit per level).
 void build_level_sweeps(const pcg_volume* v, double Re, double av, const double* levels, int nz,
-                        LevelSweep* ls, std::vector<unsigned char>* slow) {
+                        LevelSweep* ls, size_t row_stride, std::vector<unsigned char>* slow) {
     const int ne = v->ne;
     const long double pi = 3.14159265358979323846264338327950288L;
     const long double a = (long double)av;
@@ -313,11 +313,11 @@ void build_level_sweeps(const pcg_volume* v, double Re, double av, const double*
     }
     const double inf = HUGE_VAL;
     for (int iz = 0; iz < nz; ++iz) {
-        LevelSweep* row = ls + (size_t)iz * (ne + 2);
+        LevelSweep* row = ls + (size_t)iz * row_stride;
         memset(row, 0, sizeof(LevelSweep) * (ne + 2));
         row[0].t_lo = inf; row[0].t_hi = inf;                  // "sweep -1": always el >= e_-1, never below it
 
-        row[ne + 1].t_lo = -inf; row[ne + 1].t_hi = -inf;      // "sweep ne": never reached
+        row[ne + 1].t_lo = -inf; row[ne + 1].t_hi = 0.0;       // "sweep ne": never reached; 0 so that r2 <= 0 confirms nothing
         volatile double gd = Re + levels[iz];                  // the reference's gate radius
         const long double g = (long double)gd;
         if (g > a) {
@@ -352,12 +352,20 @@ void build_level_sweeps(const pcg_volume* v, double Re, double av, const double*
 }
 
 // {t_lo[k], t_hi[k+1], rho2[k], rho[k], b1[k]} per (level, k + 1) from the per-sweep bands
-void build_level_pairs(const LevelSweep* ls, int nz, int ne, LevelPair* lp) {
+// One row per level: [LevelPair x (ne + 1)][LevelSweep x (ne + 2)].  `rows` already holds the LevelSweep
+// halves (build_level_sweeps with row_stride = 2 ne + 3 and ls = rows + ne + 1); this fills the pair halves
+// {t_lo[k], t_hi[k+1], rho2[k], rho[k], b1[k]} and rewrites flagged levels so that nothing is ever confirmed
+// there and the walk ends in the reference chain at once.
+void build_level_pairs(LevelSweep* rows, int nz, int ne, const std::vector<unsigned char>& slow) {
+    static_assert(sizeof(LevelSweep) == 32 && sizeof(LevelPair) == 32, "threshold tables are 32-byte records");
+    const size_t stride = (size_t)2 * ne + 3;
     for (int iz = 0; iz < nz; ++iz) {
-        const LevelSweep* row = ls + (size_t)iz * (ne + 2);
-        LevelPair* out = lp + (size_t)iz * (ne + 1);
+        LevelPair* out = reinterpret_cast<LevelPair*>(rows + (size_t)iz * stride);
+        LevelSweep* row = rows + (size_t)iz * stride + (ne + 1);
+        if (slow[iz])
+            for (int s = 0; s < ne + 2; ++s) { row[s].t_lo = -HUGE_VAL; row[s].t_hi = HUGE_VAL; }
         for (int s = 0; s <= ne; ++s) {          // s = k + 1
-            out[s].t_lo = row[s].t_lo;
+            out[s].t_lo = slow[iz] ? -HUGE_VAL : row[s].t_lo;
             out[s].t_hi = row[s + 1].t_hi;
             out[s].rho2 = row[s].rho2;
             out[s].rho = row[s].rho;
@@ -432,7 +440,6 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     A.field_stride = (unsigned long long)nz * (unsigned long long)ncol;
     // r2-space thresholds of this (radar height, level set): built on the host, stream-ordered upload
     const int ne = vol->ne;
-    std::vector<unsigned char> slow;
     LevelSweep* d_ls = nullptr;
     {
         std::lock_guard<std::mutex> lk(vol->ls_mutex);
@@ -442,11 +449,10 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
         key.insert(key.end(), levels, levels + nz);
         if (!vol->d_ls || key.size() != vol->ls_key.size() ||
             memcmp(key.data(), vol->ls_key.data(), key.size() * sizeof(double)) != 0) {
-            const size_t n_ls = (size_t)nz * (ne + 2), n_lp = (size_t)nz * (ne + 1);
-            static_assert(sizeof(LevelSweep) == 32 && sizeof(LevelPair) == 32, "threshold tables are 32-byte records");
-            std::vector<LevelSweep> ls(n_ls + n_lp);
-            build_level_sweeps(vol, Re, av, levels, nz, ls.data(), &vol->ls_slow);
-            build_level_pairs(ls.data(), nz, ne, reinterpret_cast<LevelPair*>(ls.data() + n_ls));
+            const size_t stride = (size_t)2 * ne + 3;
+            std::vector<LevelSweep> ls((size_t)nz * stride);
+            build_level_sweeps(vol, Re, av, levels, nz, ls.data() + (ne + 1), stride, &vol->ls_slow);
+            build_level_pairs(ls.data(), nz, ne, vol->ls_slow);
             LevelSweep* fresh = nullptr;
             CUDA_TRY(cudaMalloc((void**)&fresh, ls.size() * sizeof(LevelSweep)));
             cudaError_t e = cudaMemcpy(fresh, ls.data(), ls.size() * sizeof(LevelSweep), cudaMemcpyHostToDevice);
@@ -456,7 +462,6 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
             vol->ls_key.swap(key);
         }
         d_ls = vol->d_ls;
-        slow = vol->ls_slow;
     }
     RA.r2.fs = vol->d_fs;
     RA.r2.g_t = vol->d_gt;
@@ -488,13 +493,8 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     for (int z0 = 0; z0 < nz && rc == PCG_OK; z0 += kMaxLevelsPerLaunch) {
         const int cnt = (nz - z0 < kMaxLevelsPerLaunch) ? nz - z0 : kMaxLevelsPerLaunch;
         A.nz = cnt;
-        RA.level_slow = 0;
-        for (int k = 0; k < cnt; ++k) {
-            fill_level(&A.levels[k], levels[z0 + k], Re, a2, twoa);
-            if (slow[z0 + k]) RA.level_slow |= 1ull << k;
-        }
-        RA.r2.ls = d_ls + (size_t)z0 * (ne + 2);
-        RA.r2.lp = reinterpret_cast<const LevelPair*>(d_ls + (size_t)nz * (ne + 2)) + (size_t)z0 * (ne + 1);
+        for (int k = 0; k < cnt; ++k) fill_level(&A.levels[k], levels[z0 + k], Re, a2, twoa);
+        RA.r2.lp = reinterpret_cast<const LevelPair*>(d_ls) + (size_t)z0 * (2 * ne + 3);
         A.out = d_out + (size_t)z0 * (size_t)ncol;
         A.idx = d_idx ? d_idx + (size_t)z0 * (size_t)ncol * kIdxStride : nullptr;
         rc = d_idx ? launch_fast_nf<true>(RA, nfield, vol->uniform, grid, block, smem, st)
@@ -1280,7 +1280,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     int rc;
     int max_ne = 2;
     bool uni = true;
-    size_t npair_total = 0, n_ls = 0, n_lp = 0;
+    size_t npair_total = 0, n_ls = 0;
     for (int i = 0; i < nradar; ++i) {
         if ((rc = check_volume(vols[i]))) return rc;
         if (!(re[i] > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
@@ -1294,14 +1294,13 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
         if (vols[i]->ne > max_ne) max_ne = vols[i]->ne;
         uni = uni && vols[i]->uniform;
         npair_total += (size_t)(vols[i]->ne - 1);
-        n_ls += (size_t)nz * (vols[i]->ne + 2);
-        n_lp += (size_t)nz * (vols[i]->ne + 1);
+        n_ls += (size_t)nz * (2 * vols[i]->ne + 3);
     }
     const size_t bytes_radars = sizeof(NetRadar) * (size_t)nradar;
     const size_t bytes_pairs = sizeof(NetPair) * npair_total;
     const size_t bytes_levels = sizeof(NetLevel) * (size_t)nradar * nz;
     const size_t bytes_spairs = sizeof(PairDesc) * npair_total;
-    const size_t bytes_ls = sizeof(LevelSweep) * n_ls, bytes_lp = sizeof(LevelPair) * n_lp;
+    const size_t bytes_ls = sizeof(LevelSweep) * n_ls, bytes_lp = 0;
     const size_t off_pairs = bytes_radars, off_levels = off_pairs + bytes_pairs, off_spairs = off_levels + bytes_levels;
     const size_t off_ls = (off_spairs + bytes_spairs + 31) & ~(size_t)31, off_lp = off_ls + bytes_ls;
     const size_t total = off_lp + bytes_lp;
@@ -1329,10 +1328,9 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
         NetLevel* nlevels = reinterpret_cast<NetLevel*>(blob.data() + off_levels);
         PairDesc* spairs = reinterpret_cast<PairDesc*>(blob.data() + off_spairs);
         LevelSweep* ls_all = reinterpret_cast<LevelSweep*>(blob.data() + off_ls);
-        LevelPair* lp_all = reinterpret_cast<LevelPair*>(blob.data() + off_lp);
         double zmin = levels[0];
         for (int k = 1; k < nz; ++k) zmin = levels[k] < zmin ? levels[k] : zmin;
-        size_t poff = 0, lsoff = 0, lpoff = 0;
+        size_t poff = 0, lsoff = 0;
         std::vector<unsigned char> slow;
         for (int i = 0; i < nradar; ++i) {
             const pcg_volume* v = vols[i];
@@ -1354,16 +1352,14 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
             R.a2_np = pow((double)av, 2.0);                 // radar_radius ** 2 (transforms.py:213)
             R.ne = ne;
             // r2-space tables
-            R.r2.ls = reinterpret_cast<const LevelSweep*>(d_base + off_ls) + lsoff;
-            R.r2.lp = reinterpret_cast<const LevelPair*>(d_base + off_lp) + lpoff;
+            R.r2.lp = reinterpret_cast<const LevelPair*>(d_base + off_ls) + lsoff;
             R.r2.fs = v->d_fs; R.r2.g_t = v->d_gt; R.r2.h_t = v->d_ht; R.r2.az_t = v->d_azt;
             R.r2.inv2a = (float)(1.0 / twoa);
             R.r2.u_rng_off = v->uni_rng_off; R.r2.u_ngm1 = v->uni_ngm1; R.r2.u_inv_step = v->uni_inv_step;
             R.r2.u_c0 = v->uni_c0; R.r2.u_step = v->uni_step; R.r2.u_r_first = v->uni_r_first;
-            build_level_sweeps(v, re[i], av, levels, nz, ls_all + lsoff, &slow);
-            build_level_pairs(ls_all + lsoff, nz, ne, lp_all + lpoff);
-            lsoff += (size_t)nz * (ne + 2);
-            lpoff += (size_t)nz * (ne + 1);
+            build_level_sweeps(v, re[i], av, levels, nz, ls_all + lsoff + (ne + 1), (size_t)2 * ne + 3, &slow);
+            build_level_pairs(ls_all + lsoff, nz, ne, slow);
+            lsoff += (size_t)nz * (2 * ne + 3);
             // range-sanity window (RadarInterp.py:1003-1011)
             if (v->src_count[0] == 0) {
                 R.src_lo = 1.0; R.src_hi = 0.0;             // no valid source value: everything -> fill
@@ -1417,7 +1413,6 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
                 volatile double t = 2.0 * (double)av;
                 volatile double tg = t * g;                 // 2 * radar_radius * gate_radius (left to right)
                 L.twoag_np = tg;
-                L.slow = slow[k];
             }
         }
         // the previous launch may still be reading the old tables

@@ -53,8 +53,6 @@ struct NetPair {                     // sweep pair (k, k+1) of one radar
 struct NetLevel {                    // per (radar, level) constants, host-evaluated
     LevelConst cy;                   // the gridding chain (RadarGridC.pyx:145-146)
     double a2g2_np, twoag_np, g2_np; // the NumPy twin: a**2 + g**2, 2*a*g, g**2 (transforms.py:213-218)
-    int slow;                        // level takes the reference chain on the r2 path (pcg_r2.cuh)
-    int pad;
 };
 
 struct NetRadar {
@@ -62,7 +60,7 @@ struct NetRadar {
     const PairDesc* pairs;           // thresholds pre-scaled by 2a (this radar's height)
     const NetPair* npairs;
     const NetLevel* levels;          // [nz]
-    R2Ctx r2;                        // r2-space tables of this radar (ls / lp: [nz][ne + 2] / [nz][ne + 1])
+    R2Ctx r2;                        // r2-space tables of this radar (lp: [nz] rows of 2 ne + 3 records)
     double x, y;                     // site on the common grid (m)
     double Re, a, a2, twoa, guard, inv_twoa;
     double a2_np;                    // a**2 as Python evaluates it
@@ -248,15 +246,13 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __
         const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? expf(-(float)d2 * R.inv_r2inf4) : 1.f;
 
         int k = -1, k6 = 0;
-        const LevelSweep* ls = R.r2.ls + (size_t)z0 * (ne + 2);
-        const LevelPair* lp = R.r2.lp + (size_t)z0 * (ne + 1);
+        const LevelPair* lp = R.r2.lp + (size_t)z0 * (2 * ne + 3);
 #pragma unroll 1
         for (int i = 0; i < nzc; ++i) {
             float res[1];
             VoxelInfo vi;
-            r2_voxel<1, false, UNI>(c, R.r2, R.vol.val, s_lv[i].cy, ls, lp, s_lv[i].slow != 0, cphi, k, k6, res, vi);
-            ls += ne + 2;
-            lp += ne + 1;
+            r2_voxel<1, false, UNI>(c, R.r2, R.vol.val, s_lv[i].cy, lp, cphi, k, k6, res, vi);
+            lp += 2 * ne + 3;
             float v = res[0];
             // range-sanity filter (RadarInterp.py:1003-1014), compared in double like the reference
             if (p.sanity && v != fill32) {

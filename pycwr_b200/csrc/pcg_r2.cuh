@@ -54,8 +54,7 @@ struct FastSweep {                // per sweep k (and the pair (k, k+1)), consta
 struct GateAux { double rsq; float r, inv_dr; };   // R[j]^2, R[j], 1 / (R[j+1] - R[j])
 
 struct R2Ctx {
-    const LevelSweep* ls;         // [nz][ne + 2]
-    const LevelPair* lp;          // [nz][ne + 1]
+    const LevelPair* lp;          // [nz] rows of [LevelPair x (ne + 1)][LevelSweep x (ne + 2)] (32-byte records)
     const FastSweep* fs;          // [ne]
     const double2* g_t;           // {tg[j], tg[j+1]} per gate (tg_gt_last at the end)
     const GateAux* h_t;
@@ -115,15 +114,18 @@ __device__ __forceinline__ void column_azimuth_table_r2(const SweepDesc* s_sw, i
 // they are read per sweep from `q.fs` and per gate from `q.h_t`.
 template <int NF, bool EMIT, bool UNI, bool LAZY = false>
 __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, const void* const* val,
-                                         const LevelConst& lc, const LevelSweep* __restrict__ ls,
-                                         const LevelPair* __restrict__ lp, bool level_slow, double cphi,
+                                         const LevelConst& lc, const LevelPair* __restrict__ lp, double cphi,
                                          int& k, int& k6, float (&res)[NF], VoxelInfo& vi) {
     const int ne = c.ne;
     const float fill32 = c.fill32;
     // RadarGridC.pyx:146-149 — the reference's own operations: r2 is bit-identical
     const double r2 = sub(lc.a2g2, mul(lc.twoag, cphi));
-    bool slow = level_slow | !(r2 > 0.0);
-    if (!slow) {
+    // One level row is [LevelPair x (ne + 1)][LevelSweep x (ne + 2)].  r2 <= 0 / NaN and levels flagged
+    // for the reference chain need no test of their own: every threshold is positive (the top sentinel is
+    // 0) and flagged rows hold -inf / +inf, so the confirmation fails and the walk ends in `slow`.
+    const LevelSweep* ls = reinterpret_cast<const LevelSweep*>(lp + (ne + 1));
+    bool slow = false;
+    {
         // settle k in [-1, ne-1]: e_k <= el < e_{k+1} (k = -1 below the lowest sweep, ne-1 above the highest).
         // One 16-byte entry {t_lo[k], t_hi[k+1]} confirms the current k; the per-sweep bands are only
         // read when the column has to move.
@@ -250,7 +252,6 @@ __device__ __forceinline__ void r2_voxel(const ColumnCtx& c, const R2Ctx& q, con
 struct R2Args {
     FastArgs base;
     R2Ctx r2;
-    unsigned long long level_slow;      // bit iz: level takes the reference chain
     int lazy_az;                        // many-sweep volume: azimuth brackets on demand (2-entry cache per column)
 };
 
@@ -327,14 +328,13 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
 
     int k = -1, k6 = 0;
     double* out_col = p.out + col;
-    const LevelSweep* ls = P.r2.ls;
     const LevelPair* lp = P.r2.lp;
     const bool merge_max = p.merge_max != 0;
 #pragma unroll 1
     for (int iz = 0; iz < p.nz; ++iz) {
         float res[NF];
         VoxelInfo vi;
-        r2_voxel<NF, EMIT, UNI, LAZY>(c, q, p.vol.val, p.levels[iz], ls, lp, (P.level_slow >> iz) & 1ull, cphi, k, k6, res, vi);
+        r2_voxel<NF, EMIT, UNI, LAZY>(c, q, p.vol.val, p.levels[iz], lp, cphi, k, k6, res, vi);
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             double* dst = out_col + (size_t)f * (size_t)p.field_stride;
@@ -359,8 +359,7 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
             rec[9] = -1;
         }
         out_col += ncol;
-        ls += ne + 2;
-        lp += ne + 1;
+        lp += 2 * ne + 3;
     }
 }
 
