@@ -74,7 +74,7 @@ struct Scratch {
     }
 };
 
-enum { S_GX = 0, S_GY, S_OUT, S_IDX, S_TMP0, S_TMP1, S_TMP2, S_NET, S_AUX0, S_AUX1, S_AUX2, S_AUX3, S_AUX4, S_COUNT };
+enum { S_GX = 0, S_GY, S_OUT, S_IDX, S_TMP0, S_TMP1, S_TMP2, S_NET, S_AUX0, S_AUX1, S_AUX2, S_AUX3, S_AUX4, S_ACC0, S_ACC1, S_ACC2, S_ACC3, S_ACC4, S_ACC5, S_ACC6, S_COUNT };
 Scratch g_scratch[S_COUNT];
 cudaStream_t g_stream[16] = {};
 
@@ -1224,28 +1224,42 @@ struct NetHostTables {
     std::vector<PairDesc> pairs;     // per radar, thresholds scaled by 2a
 };
 
-int launch_network(const NetArgs& a, int method, bool uni, dim3 grid, size_t smem, cudaStream_t st) {
-#define NET_CASE(M, U)                                                                               \
-    case (M) * 2 + ((U) ? 1 : 0):                                                                    \
-        if (smem > 48 * 1024)                                                                        \
-            CUDA_TRY(cudaFuncSetAttribute(network_kernel<M, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem));                                               \
-        network_kernel<M, U><<<grid, kNetThreads, smem, st>>>(a);                                    \
-        break;
+__global__ void fill_f64_kernel(double* p, size_t n, double v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+template <int M, bool U>
+int launch_radar_pass(const NetArgs& a, const NetAcc& acc, int ir, int ntiles, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(net_radar_kernel<M, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    net_radar_kernel<M, U><<<ntiles, kNetThreads, smem, st>>>(a, acc, ir);
+    return PCG_OK;
+}
+
+int launch_radar_pass_any(const NetArgs& a, const NetAcc& acc, int method, bool uni, int ir, int ntiles, size_t smem,
+                          cudaStream_t st) {
     switch (method * 2 + (uni ? 1 : 0)) {
-        NET_CASE(kNetMax, false)
-        NET_CASE(kNetMax, true)
-        NET_CASE(kNetNearest, false)
-        NET_CASE(kNetNearest, true)
-        NET_CASE(kNetExp, false)
-        NET_CASE(kNetExp, true)
-        NET_CASE(kNetQuality, false)
-        NET_CASE(kNetQuality, true)
+        case kNetMax * 2: return launch_radar_pass<kNetMax, false>(a, acc, ir, ntiles, smem, st);
+        case kNetMax * 2 + 1: return launch_radar_pass<kNetMax, true>(a, acc, ir, ntiles, smem, st);
+        case kNetNearest * 2: return launch_radar_pass<kNetNearest, false>(a, acc, ir, ntiles, smem, st);
+        case kNetNearest * 2 + 1: return launch_radar_pass<kNetNearest, true>(a, acc, ir, ntiles, smem, st);
+        case kNetExp * 2: return launch_radar_pass<kNetExp, false>(a, acc, ir, ntiles, smem, st);
+        case kNetExp * 2 + 1: return launch_radar_pass<kNetExp, true>(a, acc, ir, ntiles, smem, st);
+        case kNetQuality * 2: return launch_radar_pass<kNetQuality, false>(a, acc, ir, ntiles, smem, st);
+        case kNetQuality * 2 + 1: return launch_radar_pass<kNetQuality, true>(a, acc, ir, ntiles, smem, st);
         default: return fail(PCG_ERR_ARG, "Unsupported composite_method code %d", method);
     }
-#undef NET_CASE
-    g_launches.fetch_add(1);
-    CUDA_TRY(cudaGetLastError());
+}
+
+int launch_finalize(const NetArgs& a, const NetAcc& acc, int method, cudaStream_t st) {
+    const size_t nvox = (size_t)a.nz * (size_t)a.ncol;
+    const unsigned blocks = (unsigned)((nvox + 255) / 256 < 148 * 32 ? (nvox + 255) / 256 : 148 * 32);
+    switch (method) {
+        case kNetMax: net_finalize_kernel<kNetMax><<<blocks, 256, 0, st>>>(a, acc); break;
+        case kNetNearest: net_finalize_kernel<kNetNearest><<<blocks, 256, 0, st>>>(a, acc); break;
+        case kNetExp: net_finalize_kernel<kNetExp><<<blocks, 256, 0, st>>>(a, acc); break;
+        default: net_finalize_kernel<kNetQuality><<<blocks, 256, 0, st>>>(a, acc); break;
+    }
     return PCG_OK;
 }
 
@@ -1433,22 +1447,66 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     const int PY = 1 << A.py_log2, PX = 32 / PY, nwarp = kNetThreads / 32;
     A.tiles_y = (int)((ny + (long long)nwarp * PY - 1) / ((long long)nwarp * PY));
     const long long tiles_x = (A.nx + PX - 1) / PX;
+    const long long ntile = tiles_x * A.tiles_y;
+    if (ntile > 0x7fffffffll) return fail(PCG_ERR_ARG, "grid too large for one network call");
     A.fill = fill; A.fill32 = (float)fill;
     A.quality = 1;
     A.sanity = prm->sanity_filter ? 1 : 0;
     A.nearest_gate = (prm->blind_code == 1 || prm->blind_code == 3 || prm->blind_code == 4);
     A.lowest_sweep = (prm->blind_code == 2 || prm->blind_code == 3 || prm->blind_code == 4);
     A.highest_sweep = (prm->blind_code == 4);
-    A.smem_desc_bytes = 0;
     A.max_ne = max_ne;
     A.composite = d_comp; A.valid_count = d_valid; A.coverage = d_cov; A.blind = d_blind; A.cr = d_cr;
     A.quality_out = d_quality; A.tie_count = d_ties;
-    // per-thread state: azimuth table [sweep][thread] + accumulators (2 float, 2 uint8, 1 double per level)
-    const size_t smem = (size_t)max_ne * kNetThreads * sizeof(AzEntry) +
-                        (size_t)kNetZC * kNetThreads *
-                            (2 * sizeof(float) + 2 + (prm->method == kNetNearest ? sizeof(double) : 0));
-    const dim3 grid((unsigned)(tiles_x * A.tiles_y), (unsigned)((nz + kNetZC - 1) / kNetZC));
-    return launch_network(A, prm->method, uni, grid, smem, st);
+
+    // accumulators (10 bytes per voxel) and per-radar tile lists
+    const size_t nvox = (size_t)nz * (size_t)ncol;
+    NetAcc acc;
+    memset(&acc, 0, sizeof(acc));
+    if ((rc = g_scratch[S_ACC0].ensure(nvox * sizeof(float))) || (rc = g_scratch[S_ACC1].ensure(nvox * sizeof(float))) ||
+        (rc = g_scratch[S_ACC2].ensure(nvox)) || (rc = g_scratch[S_ACC3].ensure(nvox)) ||
+        (rc = g_scratch[S_ACC5].ensure((size_t)ncol * sizeof(float))) ||
+        (rc = g_scratch[S_ACC6].ensure(((size_t)nradar * (size_t)ntile + (size_t)nradar) * sizeof(int))))
+        return rc;
+    acc.wv = (float*)g_scratch[S_ACC0].ptr; acc.w = (float*)g_scratch[S_ACC1].ptr;
+    acc.cnt = (unsigned char*)g_scratch[S_ACC2].ptr; acc.cov = (unsigned char*)g_scratch[S_ACC3].ptr;
+    acc.cr = (float*)g_scratch[S_ACC5].ptr;
+    acc.tile_count = (int*)g_scratch[S_ACC6].ptr;
+    acc.tiles = acc.tile_count + nradar;
+    acc.ntile = (int)ntile;
+    if (prm->method == kNetNearest) {
+        if ((rc = g_scratch[S_ACC4].ensure(nvox * sizeof(double)))) return rc;
+        acc.best_d2 = (double*)g_scratch[S_ACC4].ptr;
+        fill_f64_kernel<<<148 * 8, 256, 0, st>>>(acc.best_d2, nvox, HUGE_VAL);
+        g_launches.fetch_add(1);
+    }
+    CUDA_TRY(cudaMemsetAsync(acc.wv, 0, nvox * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(acc.w, 0, nvox * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(acc.cnt, 0, nvox, st));
+    CUDA_TRY(cudaMemsetAsync(acc.cov, 0, nvox, st));
+    CUDA_TRY(cudaMemsetAsync(acc.cr, 0xff, (size_t)ncol * sizeof(float), st));      // 0xffffffff is a NaN: no echo yet
+    CUDA_TRY(cudaMemsetAsync(acc.tile_count, 0, (size_t)nradar * sizeof(int), st));
+    if (d_quality) CUDA_TRY(cudaMemsetAsync(d_quality, 0, nvox * sizeof(double), st));
+    net_cull_kernel<<<(unsigned)ntile, kNetThreads, 0, st>>>(A, acc);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<int> counts(nradar);
+    CUDA_TRY(cudaMemcpyAsync(counts.data(), acc.tile_count, (size_t)nradar * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < nradar; ++i) {
+        if (counts[i] <= 0) continue;
+        const int ne = vols[i]->ne;
+        const size_t smem = (size_t)ne * (sizeof(SweepDesc) + sizeof(FastSweep)) +
+                            (size_t)(ne - 1) * (sizeof(PairDesc) + sizeof(NetPair)) +
+                            (size_t)ne * kNetThreads * sizeof(AzEntry);
+        if ((rc = launch_radar_pass_any(A, acc, prm->method, uni, i, counts[i], smem, st))) return rc;
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if ((rc = launch_finalize(A, acc, prm->method, st))) return rc;
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return PCG_OK;
 }
 
 }  // namespace

@@ -10,12 +10,8 @@
 // The reference materialises an (nradar, nz, nlat, nlon) float64 stack per quantity; here the
 // per-radar values live in registers and only the merged outputs touch HBM.
 //
-// Decomposition: blockIdx.x tiles the grid columns (128 consecutive columns per block, so grid
-// reads and every output plane are coalesced), blockIdx.y tiles the levels in chunks of kNetZC
-// whose accumulators stay in registers.  The radar loop is block-uniform: a radar whose range
-// disc misses every column of the block is skipped by one __syncthreads_or, the others have
-// their descriptor tables staged in shared memory (same layout as the single-radar kernel) and
-// each in-reach column builds its azimuth table once per (radar, level chunk).
+// Decomposition: radar-major passes over per-radar tile lists (see below): the per-radar values live
+// only in registers, the merged accumulators (10 bytes per voxel) in HBM.
 //
 // Exactness: values, valid_count come from the same voxel body as get_CAPPI_3d (indices bit-exact).
 // The observability gates compare the reference's NumPy-twin geometry (np.hypot / ranges**2,
@@ -135,213 +131,236 @@ __device__ __noinline__ bool twin_observable(double x, double y, const NetRadar&
     return (r >= np.obs_first) && (r <= np.obs_last);
 }
 
-template <int METHOD, bool UNI>
-__global__ void __launch_bounds__(kNetThreads, NET_MINB) network_kernel(const __grid_constant__ NetArgs p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // shared memory holds PER-THREAD state only ([row][thread] arrays, conflict free, never read by
-    // another thread), so the radar loop needs no barrier: the column's azimuth table of the current
-    // radar, and the per-level accumulators that keep the level loop rolled.
-    const unsigned T = blockDim.x;
-    AzEntry* my_az = reinterpret_cast<AzEntry*>(smem_raw) + threadIdx.x;                       // [max_ne][T]
-    float* acc_wv = reinterpret_cast<float*>(smem_raw + (size_t)p.max_ne * T * sizeof(AzEntry)) + threadIdx.x;
-    float* acc_w = acc_wv + (size_t)kNetZC * T;                                                // [kNetZC][T] each
-    unsigned char* cnt8 = reinterpret_cast<unsigned char*>(acc_wv - threadIdx.x + (size_t)2 * kNetZC * T) + threadIdx.x;
-    unsigned char* cov8 = cnt8 + (size_t)kNetZC * T;
-    double* best_d2 = reinterpret_cast<double*>(cnt8 - threadIdx.x + (size_t)2 * kNetZC * T) + threadIdx.x;  // nearest only
-    __shared__ double s_box[4];
+// ---------------------------------------------------------------------------------------------
+// Radar-major passes.  One launch per radar over the grid tiles its range disc reaches:
+//   net_cull_kernel      per tile (one block = 128 columns = 4 warps x (8 x 4) footprint): bounding box of
+//                        the tile's columns, tested against every radar's reach -> per-radar tile lists
+//   net_radar_kernel     one radar, its tile list: the column's azimuth table, then every level through the
+//                        r2 voxel path, read-modify-write of the per-voxel accumulators in HBM
+//   net_finalize_kernel  accumulators -> composite / valid_count / coverage_count / blind_mask / CR
+// Within a pass every block gathers from the SAME 97 MB volume, which stays L2-resident (126 MB), the
+// descriptor tables of the radar sit in shared memory, the column prologue runs once per (column, radar)
+// and warps never idle on radars that miss them.  Passes run in radar order on one stream, so the sums
+// accumulate in the reference's order (np.sum over axis 0) without atomics.
+// ---------------------------------------------------------------------------------------------
+struct NetAcc {
+    float* wv;                 // [nz][ncol]  weighted: sum w*v;  max / nearest: the chosen value
+    float* w;                  //             weighted: sum w;    max / nearest: 1 when a value was chosen
+    unsigned char* cnt;        // valid_count
+    unsigned char* cov;        // coverage_count
+    double* best_d2;           // nearest only
+    float* cr;                 // [ncol], NaN = no echo yet
+    int* tiles;                // [nradar][ntile] tile lists
+    int* tile_count;           // [nradar]
+    int ntile;
+};
 
-    // 2-D warp footprint (see cappi3d_r2_kernel): 2^py_log2 consecutive columns x (32 >> py_log2) rows per
-    // warp, the block's warps side by side along the row
+__device__ __forceinline__ void net_tile_column(const NetArgs& p, int tile, bool& active, long long& col) {
+    const int pyl = p.py_log2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int ly = lane & ((1 << pyl) - 1), lx = lane >> pyl;
+    const int by = tile % p.tiles_y, bx = tile / p.tiles_y;
+    int iy = ((by * nwarp + warp) << pyl) + ly;
+    int ix = bx * (32 >> pyl) + lx;
+    active = (ix < p.nx) & (iy < p.ny);
+    ix = min(ix, p.nx - 1); iy = min(iy, p.ny - 1);
+    col = (long long)ix * p.ny + iy;
+}
+
+__global__ void __launch_bounds__(kNetThreads) net_cull_kernel(const __grid_constant__ NetArgs p, const NetAcc acc) {
+    __shared__ double s_red[4 * (kNetThreads / 32)];
     bool active;
     long long col;
-    {
-        const int pyl = p.py_log2;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = T >> 5;
-        const int ly = lane & ((1 << pyl) - 1), lx = lane >> pyl;
-        const int by = blockIdx.x % p.tiles_y, bx = blockIdx.x / p.tiles_y;
-        int iy = ((by * nwarp + warp) << pyl) + ly;
-        int ix = bx * (32 >> pyl) + lx;
-        active = (ix < p.nx) & (iy < p.ny);
-        ix = min(ix, p.nx - 1); iy = min(iy, p.ny - 1);      // inactive lanes read a valid column for the bbox
-        col = (long long)ix * p.ny + iy;
+    net_tile_column(p, blockIdx.x, active, col);
+    const double gx = p.gx[col], gy = p.gy[col];            // inactive lanes repeat a valid column
+    double x0 = gx, x1 = gx, y0 = gy, y1 = gy;
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+        x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
     }
-    const int z0 = blockIdx.y * kNetZC;
-    const int nzc = min(kNetZC, p.nz - z0);
-    const bool do_cr = (p.cr != nullptr) && (blockIdx.y == 0);
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        s_red[4 * w] = x0; s_red[4 * w + 1] = x1; s_red[4 * w + 2] = y0; s_red[4 * w + 3] = y1;
+    }
+    __syncthreads();
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        x0 = fmin(x0, s_red[4 * w]); x1 = fmax(x1, s_red[4 * w + 1]);
+        y0 = fmin(y0, s_red[4 * w + 2]); y1 = fmax(y1, s_red[4 * w + 3]);
+    }
+    // NaN coordinates poison fmin / fmax silently: a tile holding one is handed to every radar
+    const bool odd = __syncthreads_or(!(gx == gx) || !(gy == gy));
+    for (int ir = threadIdx.x; ir < p.nradar; ir += blockDim.x) {
+        const NetRadar& R = p.radars[ir];
+        const double ddx = fmax(fmax(x0 - R.x, R.x - x1), 0.0);
+        const double ddy = fmax(fmax(y0 - R.y, R.y - y1), 0.0);
+        if (odd || !(ddx * ddx + ddy * ddy > R.cull2)) {
+            const int slot = atomicAdd(acc.tile_count + ir, 1);
+            acc.tiles[(size_t)ir * acc.ntile + slot] = blockIdx.x;
+        }
+    }
+}
+
+template <int METHOD, bool UNI>
+__global__ void __launch_bounds__(kNetThreads, NET_MINB) net_radar_kernel(const __grid_constant__ NetArgs p,
+                                                                           const NetAcc acc, int ir) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const NetRadar& R = p.radars[ir];
+    const int ne = R.ne;
+    const unsigned T = blockDim.x;
+    SweepDesc* s_sw = reinterpret_cast<SweepDesc*>(smem_raw);
+    PairDesc* s_pr = reinterpret_cast<PairDesc*>(s_sw + ne);
+    FastSweep* s_fs = reinterpret_cast<FastSweep*>(s_pr + (ne - 1));
+    NetPair* s_np = reinterpret_cast<NetPair*>(s_fs + ne);
+    AzEntry* my_az = reinterpret_cast<AzEntry*>(s_np + (ne - 1)) + (size_t)threadIdx.x * ne;    // [thread][sweep]
+    stage_sweeps(s_sw, R.vol.sweeps, ne);
+    {
+        const int w1 = (ne - 1) * (int)(sizeof(PairDesc) / sizeof(int)), w2 = ne * (int)(sizeof(FastSweep) / sizeof(int)),
+                  w3 = (ne - 1) * (int)(sizeof(NetPair) / sizeof(int));
+        const int* a = reinterpret_cast<const int*>(R.pairs);       // already scaled by 2a on the host
+        const int* b = reinterpret_cast<const int*>(R.r2.fs);
+        const int* c = reinterpret_cast<const int*>(R.npairs);
+        for (int i = threadIdx.x; i < w1; i += T) reinterpret_cast<int*>(s_pr)[i] = a[i];
+        for (int i = threadIdx.x; i < w2; i += T) reinterpret_cast<int*>(s_fs)[i] = b[i];
+        for (int i = threadIdx.x; i < w3; i += T) reinterpret_cast<int*>(s_np)[i] = c[i];
+    }
+    __syncthreads();
+
+    bool active;
+    long long col;
+    net_tile_column(p, acc.tiles[(size_t)ir * acc.ntile + blockIdx.x], active, col);
+    if (!active) return;
+    // radar-local coordinates (RadarInterp.py:990-991) and the 2-D distance of the weight cache
+    const double x = sub(p.gx[col], R.x), y = sub(p.gy[col], R.y);
+    const double d2 = add(mul(x, x), mul(y, y));
+    if (!(d2 <= R.cull2)) return;                     // beyond every gate: nothing to add (NaN: reference chain below)
     const float fill32 = p.fill32;
-
-    // bounding box of the block's columns: one reduction, then every radar is culled block-uniformly
-    const double gx = p.gx[col], gy = p.gy[col];
-    {
-        double x0 = gx, x1 = gx, y0 = gy, y1 = gy;
-        for (int o = 16; o > 0; o >>= 1) {
-            x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o));
-            x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-            y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
-            y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-        }
-        double* s_red = reinterpret_cast<double*>(smem_raw);      // reused before any per-thread state is written
-        if ((threadIdx.x & 31) == 0) {
-            const int w = threadIdx.x >> 5;
-            s_red[4 * w] = x0; s_red[4 * w + 1] = x1; s_red[4 * w + 2] = y0; s_red[4 * w + 3] = y1;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < (int)(T >> 5); ++w) {
-                x0 = fmin(x0, s_red[4 * w]); x1 = fmax(x1, s_red[4 * w + 1]);
-                y0 = fmin(y0, s_red[4 * w + 2]); y1 = fmax(y1, s_red[4 * w + 3]);
-            }
-            s_box[0] = x0; s_box[1] = x1; s_box[2] = y0; s_box[3] = y1;
-        }
-        __syncthreads();
-    }
-    const double bx0 = s_box[0], bx1 = s_box[1], by0 = s_box[2], by1 = s_box[3];
-    __syncthreads();          // s_red aliases the azimuth table
-
-    for (int i = 0; i < kNetZC; ++i) {
-        acc_wv[i * T] = 0.f;
-        acc_w[i * T] = 0.f;
-        cnt8[i * T] = 0;
-        cov8[i * T] = 0;
-        if (METHOD == kNetNearest) best_d2[i * T] = __longlong_as_double(0x7ff0000000000000LL);
-        if (p.quality_out && active && i < nzc) p.quality_out[(size_t)(z0 + i) * (size_t)p.ncol + (size_t)col] = 0.0;
-    }
-    float cr_best = 0.f;
-    bool cr_any = false;
+    // column invariants of this radar (RadarGridC.pyx:142-146,158)
+    const double s = sqrt_rn(d2);
+    const double phi = div(s, R.Re);
+    const double cphi = cos_small(phi);
+    const double az = azimuth_from_xy(x, y);
+    column_azimuth_table_r2<false>(s_sw, ne, R.r2.az_t, az, my_az, nullptr, 1);
+    ColumnCtx c;
+    c.s_sw = s_sw; c.s_pr = s_pr;
+    c.my_az = my_az; c.my_iaz = nullptr; c.az_stride = 1;
+    c.ne = ne;
+    c.rg_t = reinterpret_cast<const double2*>(R.vol.rng);
+    c.a2 = R.a2; c.twoa = R.twoa; c.guard = R.guard; c.inv_twoa = R.inv_twoa;
+    c.fill32 = fill32;
+    c.nearest_gate = p.nearest_gate != 0; c.lowest_sweep = p.lowest_sweep != 0;
+    c.highest_sweep = p.highest_sweep != 0;
+    c.my_tag = nullptr; c.azt = nullptr; c.az = 0.0;
+    R2Ctx q = R.r2;
+    q.fs = s_fs;
+    // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
+    const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? expf(-(float)d2 * R.inv_r2inf4) : 1.f;
     unsigned long long ties = 0;
 
-    for (int ir = 0; ir < p.nradar; ++ir) {
-        const NetRadar& R = p.radars[ir];
-        {   // block-uniform cull: distance from the site to the block's bounding box
-            const double ddx = fmax(fmax(bx0 - R.x, R.x - bx1), 0.0);
-            const double ddy = fmax(fmax(by0 - R.y, R.y - by1), 0.0);
-            if (ddx * ddx + ddy * ddy > R.cull2) continue;
-        }
-        // radar-local coordinates (RadarInterp.py:990-991) and the 2-D distance of the weight cache
-        const double x = sub(gx, R.x), y = sub(gy, R.y);
-        const double d2 = add(mul(x, x), mul(y, y));
-        if (!active || !(d2 <= R.cull2)) continue;
-
-        const int ne = R.ne;
-        const SweepDesc* s_sw = R.vol.sweeps;         // descriptor tables stay in global memory (L1-resident)
-        const NetPair* s_np = R.npairs;
-        const NetLevel* s_lv = R.levels + z0;
-        // column invariants of this radar (RadarGridC.pyx:142-146,158)
-        const double s = sqrt_rn(d2);
-        const double phi = div(s, R.Re);
-        const double cphi = cos_small(phi);
-        const double az = azimuth_from_xy(x, y);
-        column_azimuth_table_r2<false>(s_sw, ne, R.r2.az_t, az, my_az, nullptr, T);
-        ColumnCtx c;
-        c.s_sw = s_sw; c.s_pr = R.pairs;              // pair thresholds pre-scaled by 2a on the host
-        c.my_az = my_az; c.my_iaz = nullptr; c.az_stride = T;
-        c.ne = ne;
-        c.rg_t = reinterpret_cast<const double2*>(R.vol.rng);
-        c.a2 = R.a2; c.twoa = R.twoa; c.guard = R.guard; c.inv_twoa = R.inv_twoa;
-        c.fill32 = fill32;
-        c.nearest_gate = p.nearest_gate != 0; c.lowest_sweep = p.lowest_sweep != 0;
-        c.highest_sweep = p.highest_sweep != 0;
-        c.my_tag = nullptr; c.azt = nullptr; c.az = 0.0;
-        // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
-        const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? expf(-(float)d2 * R.inv_r2inf4) : 1.f;
-
-        int k = -1, k6 = 0;
-        const LevelPair* lp = R.r2.lp + (size_t)z0 * (2 * ne + 3);
+    int k = -1, k6 = 0;
+    const LevelPair* lp = R.r2.lp;
+    const NetLevel* lv = R.levels;
+    size_t o = (size_t)col;
+    const double src_lo = R.src_lo, src_hi = R.src_hi;
+    const float inv_decay = R.inv_decay;
 #pragma unroll 1
-        for (int i = 0; i < nzc; ++i) {
-            float res[1];
-            VoxelInfo vi;
-            r2_voxel<1, false, UNI>(c, R.r2, R.vol.val, s_lv[i].cy, lp, cphi, k, k6, res, vi);
-            lp += 2 * ne + 3;
-            float v = res[0];
-            // range-sanity filter (RadarInterp.py:1003-1014), compared in double like the reference
-            if (p.sanity && v != fill32) {
-                const double vd = (double)v;
-                if (!(R.src_lo <= R.src_hi) || vd < R.src_lo || vd > R.src_hi) v = fill32;
-            }
-            const bool valid = (v != fill32) && (v == v) && (fabsf(v) != __int_as_float(0x7f800000));
-            // observability (RadarInterp.py:566-599 / 636-684)
-            const int kk = vi.lower < ne - 1 ? vi.lower : ne - 2;
-            const NetPair np = s_np[vi.bracket == kPair ? kk : 0];
-            const double r2 = vi.r2;
-            const bool is_pair = vi.bracket == kPair;
-            bool obs = is_pair & (r2 > np.of2_hi) & (r2 < np.ol2_lo);
-            const bool sure_out = (r2 < np.of2_lo) | (r2 > np.ol2_hi);
-            if (vi.tie || (is_pair & !obs & !sure_out) || !(r2 > 0.0)) {
-                obs = twin_observable(x, y, R, s_lv[i], s_sw, s_np, ne);
-                ++ties;
-            }
-            float q = 0.f;
-            if (obs) {
-                // RadarInterp.py:687-695
-                const float rf = (float)vi.r;
-                const float t = rf * R.inv_decay;
-                const float b = rf * np.beam_k;
-                q = expf(-t * t) * __frcp_rn(fmaf(b, b, 1.f)) * np.vert_w;
-                cov8[i * T] += 1;
-            }
-            if (p.quality_out) p.quality_out[(size_t)(z0 + i) * (size_t)p.ncol + (size_t)col] = (double)q;
-            if (valid) {
-                cnt8[i * T] += 1;
-                float& awv = acc_wv[i * T];
-                float& aw = acc_w[i * T];
-                if (METHOD == kNetMax) {
-                    if (aw == 0.f || v > awv) awv = v;
-                    aw = 1.f;
-                } else if (METHOD == kNetNearest) {
-                    double& bd = best_d2[i * T];
-                    if (d2 < bd) { bd = d2; awv = v; aw = 1.f; }
-                } else {
-                    const float w = (METHOD == kNetQuality && p.quality) ? w2d * q : w2d;
-                    awv = fmaf(w, v, awv);
-                    aw += w;
-                }
-            }
+    for (int i = 0; i < p.nz; ++i, o += (size_t)p.ncol, lp += 2 * ne + 3) {
+        // the voxel's accumulators are requested before the (long) voxel body so that their latency hides
+        // behind it (22 ms -> 15 ms on C4)
+        const float awv = acc.wv[o], aw = acc.w[o];
+        const unsigned char acnt = acc.cnt[o], acov = acc.cov[o];
+        float res[1];
+        VoxelInfo vi;
+        r2_voxel<1, false, UNI>(c, q, R.vol.val, lv[i].cy, lp, cphi, k, k6, res, vi);
+        float v = res[0];
+        // range-sanity filter (RadarInterp.py:1003-1014), compared in double like the reference
+        if (p.sanity && v != fill32) {
+            const double vd = (double)v;
+            if (!(src_lo <= src_hi) || vd < src_lo || vd > src_hi) v = fill32;
         }
-
-        if (do_cr) {
-            // get_CR_xy on the local grid: every sweep at its fixed elevation, blind "mask"
-            // (RadarGridC.pyx:596-624), then the NaN-aware max over radars (RadarInterp.py:2047-2063)
-            const double sphi = sin_small(phi);
-            const double2* rg_t = reinterpret_cast<const double2*>(R.vol.rng);
-            const float4* val = static_cast<const float4*>(R.vol.val[0]);
-            for (int ie = 0; ie < ne; ++ie) {
-                const SweepDesc d = s_sw[ie];
-                if (d.naz < 2 || d.ng < 2) continue;
-                const double denom = sub(cphi, mul(sphi, d.tan_e));
-                if (denom == 0.0) continue;
-                const double g = div(R.a, denom);
-                double r2 = sub(add(R.a2, mul(g, g)), mul(mul(R.twoa, g), cphi));
-                if (r2 < 0.0) r2 = 0.0;
-                const double r = sqrt_rn(r2);
-                if (r != r) continue;
-                const RangeBracket rb = range_bracket(d, rg_t, r, false);
-                const float v = sample_pairs(val, my_az[(size_t)ie * T], rb, fill32);
-                if (v == fill32 || v != v) continue;
-                if (!cr_any || v > cr_best) cr_best = v;
-                cr_any = true;
+        const bool valid = (v != fill32) && (v == v) && (fabsf(v) != __int_as_float(0x7f800000));
+        // observability (RadarInterp.py:566-599 / 636-684)
+        const int kk = vi.lower < ne - 1 ? vi.lower : ne - 2;
+        const bool is_pair = vi.bracket == kPair;
+        const NetPair& np = s_np[is_pair ? kk : 0];
+        const double r2 = vi.r2;
+        bool obs = is_pair & (r2 > np.of2_hi) & (r2 < np.ol2_lo);
+        const bool sure_out = (r2 < np.of2_lo) | (r2 > np.ol2_hi);
+        if (vi.tie || (is_pair & !obs & !sure_out) || !(r2 > 0.0)) {
+            obs = twin_observable(sub(p.gx[col], R.x), sub(p.gy[col], R.y), R, lv[i], s_sw, s_np, ne);
+            ++ties;
+        }
+        float qw = 0.f;
+        if (obs) {
+            // RadarInterp.py:687-695
+            const float rf = (float)vi.r;
+            const float t = rf * inv_decay;
+            const float b = rf * np.beam_k;
+            qw = expf(-t * t) * __frcp_rn(fmaf(b, b, 1.f)) * np.vert_w;
+            acc.cov[o] = acov + 1;
+        }
+        if (p.quality_out) p.quality_out[o] = (double)qw;
+        if (valid) {
+            acc.cnt[o] = acnt + 1;
+            if (METHOD == kNetMax) {
+                if (aw == 0.f || v > awv) acc.wv[o] = v;
+                acc.w[o] = 1.f;
+            } else if (METHOD == kNetNearest) {
+                if (d2 < acc.best_d2[o]) { acc.best_d2[o] = d2; acc.wv[o] = v; acc.w[o] = 1.f; }
+            } else {
+                const float w = (METHOD == kNetQuality && p.quality) ? w2d * qw : w2d;
+                acc.wv[o] = fmaf(w, v, awv);
+                acc.w[o] = aw + w;
             }
         }
     }
 
-    if (!active) return;
-    for (int i = 0; i < nzc; ++i) {
-        const size_t o = (size_t)(z0 + i) * (size_t)p.ncol + (size_t)col;
-        const float awv = acc_wv[i * T], aw = acc_w[i * T];
+    if (p.cr != nullptr) {
+        // get_CR_xy on the local grid: every sweep at its fixed elevation, blind "mask"
+        // (RadarGridC.pyx:596-624), then the NaN-aware max over radars (RadarInterp.py:2047-2063)
+        const double sphi = sin_small(phi);
+        const double2* rg_t = reinterpret_cast<const double2*>(R.vol.rng);
+        const float4* val = static_cast<const float4*>(R.vol.val[0]);
+        float best = acc.cr[col];
+        for (int ie = 0; ie < ne; ++ie) {
+            const SweepDesc& d = s_sw[ie];
+            if (d.naz < 2 || d.ng < 2) continue;
+            const double denom = sub(cphi, mul(sphi, d.tan_e));
+            if (denom == 0.0) continue;
+            const double g = div(R.a, denom);
+            double r2 = sub(add(R.a2, mul(g, g)), mul(mul(R.twoa, g), cphi));
+            if (r2 < 0.0) r2 = 0.0;
+            const double r = sqrt_rn(r2);
+            if (r != r) continue;
+            const RangeBracket rb = range_bracket(d, rg_t, r, false);
+            const float v = sample_pairs(val, my_az[ie], rb, fill32);
+            if (v == fill32 || v != v) continue;
+            if (!(best >= v)) best = v;               // NaN (nothing yet) or smaller
+        }
+        acc.cr[col] = best;
+    }
+    if (ties && p.tie_count) atomicAdd(p.tie_count, ties);
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(256) net_finalize_kernel(const __grid_constant__ NetArgs p, const NetAcc acc) {
+    const size_t nvox = (size_t)p.nz * (size_t)p.ncol;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += (size_t)gridDim.x * blockDim.x) {
+        const float awv = acc.wv[i], aw = acc.w[i];
         double out = p.fill;
         if (METHOD == kNetMax || METHOD == kNetNearest) {
             if (aw != 0.f) out = (double)awv;
         } else {
             if (aw > 0.f) out = (double)awv / (double)aw;            // has_data = total_weight > 0
         }
-        const unsigned c8 = cov8[i * T];
-        p.composite[o] = out;
-        if (p.valid_count) p.valid_count[o] = (int16_t)cnt8[i * T];
-        if (p.coverage) p.coverage[o] = (int16_t)c8;
-        if (p.blind) p.blind[o] = (int8_t)(c8 == 0u);
+        const unsigned c8 = acc.cov[i];
+        p.composite[i] = out;
+        if (p.valid_count) p.valid_count[i] = (int16_t)acc.cnt[i];
+        if (p.coverage) p.coverage[i] = (int16_t)c8;
+        if (p.blind) p.blind[i] = (int8_t)(c8 == 0u);
+        if (p.cr && i < (size_t)p.ncol) p.cr[i] = (double)acc.cr[i];   // NaN where no radar has an echo
     }
-    if (do_cr) p.cr[col] = cr_any ? (double)cr_best : __longlong_as_double(0x7ff8000000000000LL);
-    if (ties && p.tie_count) atomicAdd(p.tie_count, ties);
 }
 
 // ---------------------------------------------------------------------------------------------
