@@ -329,7 +329,7 @@ def bench_network(args, torch, dist, dev, rank, world):
         "valid_fraction_rank0": valid_frac,
         "roofline": {"bound": "hbm", "achieved": balg / kern_s / 1e9, "peak": peak * world, "unit": "GB/s",
                      "frac": balg / kern_s / 1e9 / (peak * world), "algorithmic_bytes": int(balg),
-                     "kernel": "pcg::network_kernel<3>"},
+                     "kernel": "pcg::net_radar_kernel<3,1> x radars + net_cull_kernel + net_finalize_kernel<3>"},
     }
 
 # --------------------------------------------------------------------------------------------
