@@ -87,7 +87,6 @@ int lib_stream(cudaStream_t* out) {
     return PCG_OK;
 }
 
-double resolve_re(double re) { return re; }
 
 }  // namespace
 
@@ -686,7 +685,6 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         d.tan_e = tan(fix_elev[s] * kDeg2Rad);     // RadarGridC.pyx:110,113 (host glibc)
         d.cthr = -sin(fix_elev[s] * kDeg2Rad);     // cos(pi/2 + el): elevation threshold in cosine space
         d.sorted = 1;
-        d.sec_e = (float)(1.0 / cos(fix_elev[s] * kDeg2Rad));
         if (s > 0 && !(fix_elev[s - 1] <= fix_elev[s])) strict = false;   // packer sorts by fixed angle
         if (naz[s] > 0) {
             d.az_first = az[s][0];
@@ -967,7 +965,7 @@ int pcg_get_cappi3d_dev(const pcg_volume* vol, double radar_height, double effec
     rc = check_common(effective_earth_radius, nx, ny);
     if (rc) return rc;
     const int shift = (radar_x != 0.0 || radar_y != 0.0 || merge_max) ? 1 : 0;
-    return enqueue_cappi(vol, radar_height, resolve_re(effective_earth_radius), d_grid_x, d_grid_y,
+    return enqueue_cappi(vol, radar_height, effective_earth_radius, d_grid_x, d_grid_y,
                          (long long)nx * ny, ny, level_heights, nz, fill, blind_code, beam_width_deg,
                          radar_x, radar_y, shift, merge_max, d_out, d_index_out, (cudaStream_t)stream);
 }
@@ -1217,12 +1215,6 @@ int pcg_debug_xye_to_antenna(const double* x, const double* y, size_t n, double 
 
 namespace {
 
-struct NetHostTables {
-    std::vector<NetRadar> radars;
-    std::vector<NetPair> npairs;
-    std::vector<NetLevel> levels;
-    std::vector<PairDesc> pairs;     // per radar, thresholds scaled by 2a
-};
 
 __global__ void fill_f64_kernel(double* p, size_t n, double v) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -1292,7 +1284,6 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     if (nz < 0) return fail(PCG_ERR_ARG, "nz must be non-negative");
     if (ncol == 0 || nz == 0) return PCG_OK;
     int rc;
-    int max_ne = 2;
     bool uni = true;
     size_t npair_total = 0, n_ls = 0;
     for (int i = 0; i < nradar; ++i) {
@@ -1305,7 +1296,6 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
         if (!(fill == vols[i]->fill))
             return fail(PCG_ERR_ARG, "fillvalue %.17g differs from the value volume %d was packed with (%.17g)", fill, i,
                         vols[i]->fill);
-        if (vols[i]->ne > max_ne) max_ne = vols[i]->ne;
         uni = uni && vols[i]->uniform;
         npair_total += (size_t)(vols[i]->ne - 1);
         n_ls += (size_t)nz * (2 * vols[i]->ne + 3);
@@ -1455,7 +1445,6 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     A.nearest_gate = (prm->blind_code == 1 || prm->blind_code == 3 || prm->blind_code == 4);
     A.lowest_sweep = (prm->blind_code == 2 || prm->blind_code == 3 || prm->blind_code == 4);
     A.highest_sweep = (prm->blind_code == 4);
-    A.max_ne = max_ne;
     A.composite = d_comp; A.valid_count = d_valid; A.coverage = d_cov; A.blind = d_blind; A.cr = d_cr;
     A.quality_out = d_quality; A.tie_count = d_ties;
 

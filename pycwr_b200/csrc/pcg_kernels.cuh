@@ -33,7 +33,7 @@ struct SweepDesc {
     double az_first, az_inv_step;    // index guess: floor((az - az_first) * az_inv_step) + 1
     double rng_inv_step;             // index guess: floor((r - r_first) * rng_inv_step) + 1
     int sorted;                      // tables verified ascending on the host at pack time
-    float sec_e;                     // 1 / cos(elev): slant range of the beam over a ground distance (prefetch hint)
+    int pad;
     double cthr;                     // -sin(elev): the sweep's elevation as a threshold in cosine space
 };
 

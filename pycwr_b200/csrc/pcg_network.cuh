@@ -23,13 +23,9 @@
 
 namespace pcg {
 
-#ifndef NET_ZC
-#define NET_ZC 16
-#endif
 #ifndef NET_MINB
 #define NET_MINB 6
 #endif
-constexpr int kNetZC = NET_ZC;       // levels per block (per-thread accumulators in shared memory)
 constexpr int kNetThreads = 128;
 constexpr int kNetMaxSweeps = 32;    // per radar, bounded by the shared-memory azimuth table
 
@@ -82,8 +78,6 @@ struct NetArgs {
     int quality;                     // multiply the 2-D weight by the geometric quality weight
     int sanity;                      // apply the range-sanity filter
     int nearest_gate, lowest_sweep, highest_sweep;
-    int smem_desc_bytes;             // descriptor area per block (max over radars)
-    int max_ne;                      // azimuth-table rows per block (max sweeps over radars)
     double* composite;               // [nz][ncol]
     int16_t* valid_count;            // [nz][ncol] or NULL
     int16_t* coverage;               // [nz][ncol] or NULL
