@@ -332,6 +332,65 @@ def bench_network(args, torch, dist, dev, rank, world):
                      "kernel": "pcg::net_radar_kernel<3,1> x radars + net_cull_kernel + net_finalize_kernel<3>"},
     }
 
+
+def bench_extra_config(cid, args, torch, dev, steps=10):
+    """Kernel-only timing of another BASELINE config on this GPU (inputs resident, L2 flushed between steps):
+    the same measurement as the headline `value`, reported under `other_configs` (rank 0 only)."""
+    import ctypes
+
+    from pycwr_b200 import RadarGridC as G
+    from pycwr_b200 import _lib, synth
+    from pycwr_b200.runtime import DeviceVolume
+    cfg = synth.config(cid, style=args.style)
+    vol, fields = cfg["volume"], cfg["fields"]
+    nfield = len(fields)
+    dv = DeviceVolume(vol["vol_azimuth"], vol["vol_range"], vol["fix_elevation"],
+                      [vol["vol_value"][f] for f in fields] if nfield > 1 else vol["vol_value"][fields[0]],
+                      fillvalue=FILL, value_dtype=args.value_dtype)
+    gx = torch.from_numpy(cfg["GridX"]).to(dev)
+    gy = torch.from_numpy(cfg["GridY"]).to(dev)
+    nx, ny = cfg["GridX"].shape
+    is_cr = cfg["kind"] == "cr"
+    levels = cfg["levels"]
+    nz = 1 if is_cr else int(levels.size)
+    out = torch.empty((nfield, nz, nx, ny) if not is_cr else (nx, ny), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+    blind = {"mask": 0, "hybrid": 3}[cfg["blind_method"]]
+
+    def launch():
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if is_cr:
+            _lib.check(lib.pcg_get_cr_dev(dv.handle, vol["radar_height"], G.DEFAULT_EFFECTIVE_EARTH_RADIUS, gx.data_ptr(),
+                                          gy.data_ptr(), nx, ny, FILL, 0.0, 0.0, out.data_ptr(), st))
+        else:
+            _lib.check(lib.pcg_get_cappi3d_dev(dv.handle, vol["radar_height"], G.DEFAULT_EFFECTIVE_EARTH_RADIUS,
+                                               gx.data_ptr(), gy.data_ptr(), nx, ny, levels.ctypes.data_as(_lib.c_double_p),
+                                               nz, FILL, blind, 1.0, 0.0, 0.0, 0, out.data_ptr(), None, st))
+
+    for _ in range(3):
+        launch()
+        flush.zero_()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        launch()
+        b.record()
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    peak, _ = read_peaks()
+    balg = algorithmic_bytes(cfg, nfield)
+    voxels = nfield * nz * nx * ny
+    dv.close()
+    del out, flush, gx, gy
+    torch.cuda.empty_cache()
+    return {"workload": cfg["name"], "fields": fields, "grid": [nz, nx, ny], "ms_per_step": ms,
+            "value": voxels / (ms * 1e-3), "unit": UNIT + (" (voxel-fields)" if nfield > 1 else ""),
+            "roofline": {"achieved": balg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": balg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": int(balg)}}
+
 # --------------------------------------------------------------------------------------------
 # product arm
 # --------------------------------------------------------------------------------------------
@@ -486,6 +545,9 @@ def run_product(args):
     net = None
     if args.network:
         net = bench_network(args, torch, dist, dev, rank, world)
+    others = None
+    if args.other_configs and rank == 0 and world == 1:
+        others = [bench_extra_config(c, args, torch, dev) for c in (1, 2) if WORKLOADS[args.workload] != c]
 
     if rank != 0:
         if dist is not None:
@@ -525,12 +587,15 @@ def run_product(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": int(balg),
-                     "kernel": ("pcg::cr" if is_cr else "pcg::cappi3d") + ("_fast_kernel" if dv.value_dtype == "f32" else "_kernel"),
+                     "kernel": ("pcg::cr_fast_kernel" if is_cr else "pcg::cappi3d_r2_kernel") if dv.value_dtype == "f32"
+                     else ("pcg::cr_kernel<double>" if is_cr else "pcg::cappi3d_kernel<double>"),
                      "kernel_ms": kern_ms},
         "cpu_baseline": cpu,
     }
     if net is not None:
         line["network"] = net
+    if others:
+        line["other_configs"] = others
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -554,6 +619,8 @@ def main():
     ap.add_argument("--network", dest="network", action="store_true", default=True,
                     help="also run the C4 network composite sharded over the ranks (default)")
     ap.add_argument("--no-network", dest="network", action="store_false")
+    ap.add_argument("--no-other-configs", dest="other_configs", action="store_false", default=True,
+                    help="skip the kernel-only timing of C1 / C2 (N = 1 only)")
     ap.add_argument("--network-radars", type=int, default=32)
     ap.add_argument("--network-scale", type=float, default=1.0, help="1.0 = 3000 x 3000 x 30")
     args = ap.parse_args()
