@@ -223,9 +223,10 @@ def bench_network(args, torch, dist, dev, rank, world):
     sites_cfg = {"alt": meta["radar_alt"]}
     nlat, nlon = gx_h.shape
     nz = int(levels.size)
-    bounds = sharding.slab_bounds(nlat, world)
-    r0, r1 = bounds[rank]
     reach = [460e3 * 1.002 / 0.999 + 1000.0] * len(sites)
+    # row slabs balanced by the (column, radar) pairs each row holds: the middle of the network is denser
+    bounds = sharding.slab_bounds_weighted(sharding.row_costs(gx_h, gy_h, sites, reach), world)
+    r0, r1 = bounds[rank]
     mine = sharding.radars_reaching(gx_h[r0:r1], gy_h[r0:r1], sites, reach)
     vols, heights, bws = [], [], []
     for k in mine:
@@ -322,7 +323,8 @@ def bench_network(args, torch, dist, dev, rank, world):
         "workload": "C4_network_%dr_%dx%dx%d" % (args.network_radars, nlat, nlon, nz),
         "value": voxels * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
         "value_with_gather": voxels * steps / ((ms + gather_ms) * 1e-3), "gather_ms_per_step": gather_ms / steps,
-        "n_gpus": world, "scaling": "strong", "partition": "row slabs of the output grid, radars culled per slab",
+        "n_gpus": world, "scaling": "strong", "partition": "row slabs of the output grid balanced by (column, radar) pairs, radars culled per slab",
+        "slab_rows": [b[1] - b[0] for b in bounds],
         "collective": "all_gather of finished composite slabs (NCCL)" if world > 1 else "none",
         "radars_per_rank_mean": float(nrad.item()) / world, "composite_method": "quality_weighted",
         "blind_method": "hybrid", "style": "stress", "gpu_launches": int(launches),

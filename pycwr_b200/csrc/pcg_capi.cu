@@ -74,7 +74,7 @@ struct Scratch {
     }
 };
 
-enum { S_GX = 0, S_GY, S_OUT, S_IDX, S_TMP0, S_TMP1, S_TMP2, S_NET, S_AUX0, S_AUX1, S_AUX2, S_AUX3, S_AUX4, S_ACC0, S_ACC1, S_ACC2, S_ACC3, S_ACC4, S_ACC5, S_ACC6, S_COUNT };
+enum { S_GX = 0, S_GY, S_OUT, S_IDX, S_TMP0, S_TMP1, S_TMP2, S_NET, S_AUX0, S_AUX1, S_AUX2, S_AUX3, S_AUX4, S_ACC0, S_ACC4, S_ACC5, S_ACC6, S_COUNT };
 Scratch g_scratch[S_COUNT];
 cudaStream_t g_stream[16] = {};
 
@@ -1448,17 +1448,15 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     A.composite = d_comp; A.valid_count = d_valid; A.coverage = d_cov; A.blind = d_blind; A.cr = d_cr;
     A.quality_out = d_quality; A.tie_count = d_ties;
 
-    // accumulators (10 bytes per voxel) and per-radar tile lists
+    // accumulators (one 16-byte cell per voxel) and per-radar tile lists
     const size_t nvox = (size_t)nz * (size_t)ncol;
     NetAcc acc;
     memset(&acc, 0, sizeof(acc));
-    if ((rc = g_scratch[S_ACC0].ensure(nvox * sizeof(float))) || (rc = g_scratch[S_ACC1].ensure(nvox * sizeof(float))) ||
-        (rc = g_scratch[S_ACC2].ensure(nvox)) || (rc = g_scratch[S_ACC3].ensure(nvox)) ||
+    if ((rc = g_scratch[S_ACC0].ensure(nvox * sizeof(NetCell))) ||
         (rc = g_scratch[S_ACC5].ensure((size_t)ncol * sizeof(float))) ||
         (rc = g_scratch[S_ACC6].ensure(((size_t)nradar * (size_t)ntile + (size_t)nradar) * sizeof(int))))
         return rc;
-    acc.wv = (float*)g_scratch[S_ACC0].ptr; acc.w = (float*)g_scratch[S_ACC1].ptr;
-    acc.cnt = (unsigned char*)g_scratch[S_ACC2].ptr; acc.cov = (unsigned char*)g_scratch[S_ACC3].ptr;
+    acc.cell = (NetCell*)g_scratch[S_ACC0].ptr;
     acc.cr = (float*)g_scratch[S_ACC5].ptr;
     acc.tile_count = (int*)g_scratch[S_ACC6].ptr;
     acc.tiles = acc.tile_count + nradar;
@@ -1469,10 +1467,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
         fill_f64_kernel<<<148 * 8, 256, 0, st>>>(acc.best_d2, nvox, HUGE_VAL);
         g_launches.fetch_add(1);
     }
-    CUDA_TRY(cudaMemsetAsync(acc.wv, 0, nvox * sizeof(float), st));
-    CUDA_TRY(cudaMemsetAsync(acc.w, 0, nvox * sizeof(float), st));
-    CUDA_TRY(cudaMemsetAsync(acc.cnt, 0, nvox, st));
-    CUDA_TRY(cudaMemsetAsync(acc.cov, 0, nvox, st));
+    CUDA_TRY(cudaMemsetAsync(acc.cell, 0, nvox * sizeof(NetCell), st));
     CUDA_TRY(cudaMemsetAsync(acc.cr, 0xff, (size_t)ncol * sizeof(float), st));      // 0xffffffff is a NaN: no echo yet
     CUDA_TRY(cudaMemsetAsync(acc.tile_count, 0, (size_t)nradar * sizeof(int), st));
     if (d_quality) CUDA_TRY(cudaMemsetAsync(d_quality, 0, nvox * sizeof(double), st));

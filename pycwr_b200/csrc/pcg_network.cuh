@@ -135,13 +135,18 @@ __device__ __noinline__ bool twin_observable(double x, double y, const NetRadar&
 // Within a pass every block gathers from the SAME 97 MB volume, which stays L2-resident (126 MB), the
 // descriptor tables of the radar sit in shared memory, the column prologue runs once per (column, radar)
 // and warps never idle on radars that miss them.  Passes run in radar order on one stream, so the sums
-// accumulate in the reference's order (np.sum over axis 0) without atomics.
+// accumulate in the reference's order (np.sum over axis 0) without atomics.  Weights use the hardware
+// exp2 / reciprocal (relative error < 1e-6 for these arguments, against a 1e-5 bar on the weights).
 // ---------------------------------------------------------------------------------------------
+struct NetCell {               // one voxel's accumulators: a single 128-bit load / store per (voxel, radar)
+    float wv;                  // weighted: sum w*v;  max / nearest: the chosen value
+    float w;                   // weighted: sum w;    max / nearest: 1 when a value was chosen
+    unsigned cnt;              // valid_count
+    unsigned cov;              // coverage_count
+};
+
 struct NetAcc {
-    float* wv;                 // [nz][ncol]  weighted: sum w*v;  max / nearest: the chosen value
-    float* w;                  //             weighted: sum w;    max / nearest: 1 when a value was chosen
-    unsigned char* cnt;        // valid_count
-    unsigned char* cov;        // coverage_count
+    NetCell* cell;             // [nz][ncol]
     double* best_d2;           // nearest only
     float* cr;                 // [ncol], NaN = no echo yet
     int* tiles;                // [nradar][ntile] tile lists
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) net_radar_kernel(const 
     R2Ctx q = R.r2;
     q.fs = s_fs;
     // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
-    const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? expf(-(float)d2 * R.inv_r2inf4) : 1.f;
+    const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? __expf(-(float)d2 * R.inv_r2inf4) : 1.f;
     unsigned long long ties = 0;
 
     int k = -1, k6 = 0;
@@ -262,8 +267,8 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) net_radar_kernel(const 
     for (int i = 0; i < p.nz; ++i, o += (size_t)p.ncol, lp += 2 * ne + 3) {
         // the voxel's accumulators are requested before the (long) voxel body so that their latency hides
         // behind it (22 ms -> 15 ms on C4)
-        const float awv = acc.wv[o], aw = acc.w[o];
-        const unsigned char acnt = acc.cnt[o], acov = acc.cov[o];
+        NetCell cell = acc.cell[o];
+        bool dirty = false;
         float res[1];
         VoxelInfo vi;
         r2_voxel<1, false, UNI>(c, q, R.vol.val, lv[i].cy, lp, cphi, k, k6, res, vi);
@@ -291,23 +296,26 @@ __global__ void __launch_bounds__(kNetThreads, NET_MINB) net_radar_kernel(const 
             const float rf = (float)vi.r;
             const float t = rf * inv_decay;
             const float b = rf * np.beam_k;
-            qw = expf(-t * t) * __frcp_rn(fmaf(b, b, 1.f)) * np.vert_w;
-            acc.cov[o] = acov + 1;
+            qw = __expf(-t * t) * rcp_approx(fmaf(b, b, 1.f)) * np.vert_w;
+            cell.cov += 1;
+            dirty = true;
         }
         if (p.quality_out) p.quality_out[o] = (double)qw;
         if (valid) {
-            acc.cnt[o] = acnt + 1;
+            cell.cnt += 1;
+            dirty = true;
             if (METHOD == kNetMax) {
-                if (aw == 0.f || v > awv) acc.wv[o] = v;
-                acc.w[o] = 1.f;
+                if (cell.w == 0.f || v > cell.wv) cell.wv = v;
+                cell.w = 1.f;
             } else if (METHOD == kNetNearest) {
-                if (d2 < acc.best_d2[o]) { acc.best_d2[o] = d2; acc.wv[o] = v; acc.w[o] = 1.f; }
+                if (d2 < acc.best_d2[o]) { acc.best_d2[o] = d2; cell.wv = v; cell.w = 1.f; }
             } else {
                 const float w = (METHOD == kNetQuality && p.quality) ? w2d * qw : w2d;
-                acc.wv[o] = fmaf(w, v, awv);
-                acc.w[o] = aw + w;
+                cell.wv = fmaf(w, v, cell.wv);
+                cell.w += w;
             }
         }
+        if (dirty) acc.cell[o] = cell;
     }
 
     if (p.cr != nullptr) {
@@ -341,16 +349,17 @@ template <int METHOD>
 __global__ void __launch_bounds__(256) net_finalize_kernel(const __grid_constant__ NetArgs p, const NetAcc acc) {
     const size_t nvox = (size_t)p.nz * (size_t)p.ncol;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += (size_t)gridDim.x * blockDim.x) {
-        const float awv = acc.wv[i], aw = acc.w[i];
+        const NetCell cell = acc.cell[i];
+        const float awv = cell.wv, aw = cell.w;
         double out = p.fill;
         if (METHOD == kNetMax || METHOD == kNetNearest) {
             if (aw != 0.f) out = (double)awv;
         } else {
             if (aw > 0.f) out = (double)awv / (double)aw;            // has_data = total_weight > 0
         }
-        const unsigned c8 = acc.cov[i];
+        const unsigned c8 = cell.cov;
         p.composite[i] = out;
-        if (p.valid_count) p.valid_count[i] = (int16_t)acc.cnt[i];
+        if (p.valid_count) p.valid_count[i] = (int16_t)cell.cnt;
         if (p.coverage) p.coverage[i] = (int16_t)c8;
         if (p.blind) p.blind[i] = (int8_t)(c8 == 0u);
         if (p.cr && i < (size_t)p.ncol) p.cr[i] = (double)acc.cr[i];   // NaN where no radar has an echo

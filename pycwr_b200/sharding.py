@@ -25,6 +25,45 @@ def slab_bounds(nrows, world):
     return bounds
 
 
+def row_costs(grid_x, grid_y, sites_xy, reach_m):
+    """Work estimate per grid row: the total chord length of the radars' reach discs along the row
+    (the number of (column, radar) pairs the composite has to grid there), from the row's mean
+    ordinate and abscissa extent, plus a base cost per row for the passes that touch every voxel
+    (accumulator reset, finalize: about a third of one radar's share on the C4 bench)."""
+    gx = np.asarray(grid_x, dtype=np.float64)
+    gy = np.asarray(grid_y, dtype=np.float64)
+    if gx.size == 0:
+        return np.zeros(gx.shape[0])
+    y = gy.mean(axis=1)
+    x0, x1 = gx.min(axis=1), gx.max(axis=1)
+    width = np.maximum(x1 - x0, 1.0)
+    cost = np.full(gx.shape[0], 0.3)
+    for (sx, sy), r in zip(np.asarray(sites_xy, dtype=np.float64), reach_m):
+        half = np.sqrt(np.maximum(float(r) ** 2 - (y - sy) ** 2, 0.0))
+        lo, hi = np.maximum(sx - half, x0), np.minimum(sx + half, x1)
+        cost += np.maximum(hi - lo, 0.0) / width
+    return cost
+
+
+def slab_bounds_weighted(costs, world):
+    """Contiguous row slabs of (nearly) equal total cost: rank r owns rows [b[r][0], b[r][1])."""
+    costs = np.asarray(costs, dtype=np.float64)
+    world = int(world)
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    n = costs.size
+    total = float(costs.sum())
+    if n == 0 or not total > 0.0:
+        return slab_bounds(n, world)
+    cum = np.concatenate([[0.0], np.cumsum(costs)])
+    cuts = [0]
+    for r in range(1, world):
+        cut = int(np.searchsorted(cum, total * r / world, side="left"))
+        cuts.append(min(max(cut, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def radar_reach_m(vol_range, margin=1.002, extra_m=1000.0):
     """Ground distance beyond which no gate of the radar can be reached (slant range >= 0.999 x
     ground distance for |z|, |h| << Re; the kernel applies the same cull per block)."""
@@ -84,9 +123,11 @@ def gather_slabs(local, bounds, dist=None, group=None, device=None):
 
 
 def network_compose_sharded(compute, grid_x, grid_y, sites_xy, reach_m, dist=None, group=None, device=None,
-                            keys=("composite", "valid_count", "coverage_count", "blind_mask", "CR"), gather=True):
+                            keys=("composite", "valid_count", "coverage_count", "blind_mask", "CR"), gather=True,
+                            balance=True):
     """Run ``compute(rows, radar_indices) -> dict`` on this rank's slab and gather the results.
 
+    Slabs are balanced by ``row_costs`` (``balance=False``: equal row counts).
     ``compute`` is the per-slab worker (``pycwr_b200.interp.network_compose`` bound to its
     volumes on the GPU box).  Returns ``(result, (r0, r1), radar_indices)``; with ``gather`` the
     result holds full-grid arrays on every rank, otherwise this rank's slab only."""
@@ -94,7 +135,9 @@ def network_compose_sharded(compute, grid_x, grid_y, sites_xy, reach_m, dist=Non
         import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    bounds = slab_bounds(np.asarray(grid_x).shape[0], world)
+    # every rank derives the same bounds from the same inputs: no exchange needed
+    bounds = (slab_bounds_weighted(row_costs(grid_x, grid_y, sites_xy, reach_m), world) if balance
+              else slab_bounds(np.asarray(grid_x).shape[0], world))
     r0, r1 = bounds[rank]
     radars = radars_reaching(np.asarray(grid_x)[r0:r1], np.asarray(grid_y)[r0:r1], sites_xy, reach_m)
     local = compute((r0, r1), radars)
