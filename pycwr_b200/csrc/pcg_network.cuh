@@ -24,7 +24,7 @@
 namespace pcg {
 
 #ifndef NET_MINB
-#define NET_MINB 6
+#define NET_MINB 8
 #endif
 constexpr int kNetThreads = 128;
 constexpr int kNetMaxSweeps = 32;    // per radar, bounded by the shared-memory azimuth table
