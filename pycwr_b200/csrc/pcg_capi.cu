@@ -1255,6 +1255,32 @@ int launch_finalize(const NetArgs& a, const NetAcc& acc, int method, cudaStream_
     return PCG_OK;
 }
 
+constexpr int kNetStreams = 6;
+struct NetStreams {
+    cudaStream_t side[kNetStreams] = {};
+    cudaEvent_t ev_side[kNetStreams] = {};
+    cudaEvent_t ev_class = nullptr;
+    bool ready = false;
+};
+NetStreams g_net_streams[16];
+
+int net_streams(NetStreams** out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return fail(PCG_ERR_ARG, "device index %d out of range", dev);
+    NetStreams& n = g_net_streams[dev];
+    if (!n.ready) {
+        for (int k = 0; k < kNetStreams; ++k) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&n.side[k], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&n.ev_side[k], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&n.ev_class, cudaEventDisableTiming));
+        n.ready = true;
+    }
+    *out = &n;
+    return PCG_OK;
+}
+
 // d_* pointers are DEVICE pointers; tables are built on the host and uploaded through S_NET.  The blob of
 // the last call is kept: repeated calls with the same radars / geometry / options only launch.
 std::vector<char> g_net_key;
@@ -1311,6 +1337,20 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     if ((rc = g_scratch[S_NET].ensure(total + 64))) return rc;
     char* d_base = (char*)g_scratch[S_NET].ptr;
 
+    // reach of each radar on the ground: slant range r >= 0.999 * s * min(a, g) / Re for phi < 0.15, so no
+    // gate is reachable beyond reach[i] (HUGE_VAL: no culling for absurd heights or ranges)
+    std::vector<double> reach(nradar);
+    {
+        double zmin = levels[0];
+        for (int k = 1; k < nz; ++k) zmin = levels[k] < zmin ? levels[k] : zmin;
+        for (int i = 0; i < nradar; ++i) {
+            double rlast = 0.0;
+            for (int k = 0; k < vols[i]->ne; ++k) rlast = vols[i]->sweeps[k].r_last > rlast ? vols[i]->sweeps[k].r_last : rlast;
+            const double min_ag = re[i] + (radar_height[i] < zmin ? radar_height[i] : zmin);
+            const double factor = 0.999 * min_ag / re[i];
+            reach[i] = (factor < 0.9 || !(rlast < 1.0e6)) ? HUGE_VAL : rlast / factor * 1.001 + 1.0;
+        }
+    }
     // everything the tables depend on
     std::vector<char> key;
     key_put(&key, &nradar, 1); key_put(&key, &nz, 1); key_put(&key, prm, 1); key_put(&key, &fill, 1);
@@ -1332,8 +1372,6 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
         NetLevel* nlevels = reinterpret_cast<NetLevel*>(blob.data() + off_levels);
         PairDesc* spairs = reinterpret_cast<PairDesc*>(blob.data() + off_spairs);
         LevelSweep* ls_all = reinterpret_cast<LevelSweep*>(blob.data() + off_ls);
-        double zmin = levels[0];
-        for (int k = 1; k < nz; ++k) zmin = levels[k] < zmin ? levels[k] : zmin;
         size_t poff = 0, lsoff = 0;
         std::vector<unsigned char> slow;
         for (int i = 0; i < nradar; ++i) {
@@ -1378,13 +1416,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
             }
             R.inv_decay = (prm->quality_terms & kTermRange) ? (float)(1.0 / prm->range_decay_m) : 0.f;
             R.inv_r2inf4 = (float)(4.0 / (prm->influence_radius_m * prm->influence_radius_m));
-            // reach of the radar: slant range r >= 0.999 * s * min(a, g) / Re for phi < 0.15
-            double rlast = 0.0;
-            for (int k = 0; k < ne; ++k) rlast = v->sweeps[k].r_last > rlast ? v->sweeps[k].r_last : rlast;
-            const double min_ag = re[i] + (radar_height[i] < zmin ? radar_height[i] : zmin);
-            const double factor = 0.999 * min_ag / re[i];
-            if (factor < 0.9 || !(rlast < 1.0e6)) R.cull2 = HUGE_VAL;
-            else { const double cr = rlast / factor * 1.001 + 1.0; R.cull2 = cr * cr; }
+            R.cull2 = reach[i] < HUGE_VAL ? reach[i] * reach[i] : HUGE_VAL;
             const double* bw = beam_widths ? beam_widths[i] : nullptr;
             for (int k = 0; k + 1 < ne; ++k) {
                 NetPair& np = npairs[poff + k];
@@ -1477,15 +1509,48 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     std::vector<int> counts(nradar);
     CUDA_TRY(cudaMemcpyAsync(counts.data(), acc.tile_count, (size_t)nradar * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    // Radars whose reach discs are disjoint touch disjoint voxels, so their passes may overlap in time:
+    // greedy classes in radar order (class c holds radars that conflict with none already in it), the
+    // classes run one after the other, the radars of a class on up to kNetStreams side streams.  The
+    // schedule is a function of the geometry alone, so results are reproducible run to run.
+    std::vector<int> cls(nradar, -1);
+    int nclass = 0;
     for (int i = 0; i < nradar; ++i) {
         if (counts[i] <= 0) continue;
-        const int ne = vols[i]->ne;
-        const size_t smem = (size_t)ne * (sizeof(SweepDesc) + sizeof(FastSweep)) +
-                            (size_t)(ne - 1) * (sizeof(PairDesc) + sizeof(NetPair)) +
-                            (size_t)ne * kNetThreads * sizeof(AzEntry);
-        if ((rc = launch_radar_pass_any(A, acc, prm->method, uni, i, counts[i], smem, st))) return rc;
-        g_launches.fetch_add(1);
-        CUDA_TRY(cudaGetLastError());
+        for (int c = 0; c <= nclass && cls[i] < 0; ++c) {
+            bool ok = true;
+            for (int j = 0; j < i && ok; ++j) {
+                if (cls[j] != c) continue;
+                const double dx = radar_x[i] - radar_x[j], dy = radar_y[i] - radar_y[j], rr = reach[i] + reach[j];
+                if (!(dx * dx + dy * dy > rr * rr)) ok = false;
+            }
+            if (ok) cls[i] = c;
+        }
+        if (cls[i] == nclass) ++nclass;
+    }
+    NetStreams* ns = nullptr;
+    if ((rc = net_streams(&ns))) return rc;
+    CUDA_TRY(cudaEventRecord(ns->ev_class, st));
+    for (int c = 0; c < nclass; ++c) {
+        int slot = 0, used = 0;
+        for (int i = 0; i < nradar; ++i) {
+            if (cls[i] != c) continue;
+            const int ne = vols[i]->ne;
+            const size_t smem = (size_t)ne * (sizeof(SweepDesc) + sizeof(FastSweep)) +
+                                (size_t)(ne - 1) * (sizeof(PairDesc) + sizeof(NetPair)) +
+                                (size_t)ne * kNetThreads * sizeof(AzEntry);
+            cudaStream_t s2 = ns->side[slot];
+            if (slot >= used) { CUDA_TRY(cudaStreamWaitEvent(s2, ns->ev_class, 0)); used = slot + 1; }
+            if ((rc = launch_radar_pass_any(A, acc, prm->method, uni, i, counts[i], smem, s2))) return rc;
+            g_launches.fetch_add(1);
+            CUDA_TRY(cudaGetLastError());
+            slot = (slot + 1) % kNetStreams;
+        }
+        for (int k = 0; k < used; ++k) {
+            CUDA_TRY(cudaEventRecord(ns->ev_side[k], ns->side[k]));
+            CUDA_TRY(cudaStreamWaitEvent(st, ns->ev_side[k], 0));
+        }
+        CUDA_TRY(cudaEventRecord(ns->ev_class, st));
     }
     if ((rc = launch_finalize(A, acc, prm->method, st))) return rc;
     g_launches.fetch_add(1);
