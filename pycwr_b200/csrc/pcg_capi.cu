@@ -328,8 +328,11 @@ void build_level_sweeps(const pcg_volume* v, double Re, double av, const double*
                 LevelSweep& L = row[k + 1];
                 if (!(rho > 0.0L) || !(fabsl(e) < 1.55L)) { (*slow)[iz] = 1; continue; }
                 const long double rho2 = rho * rho;
-                // bound on |r2_ref-equivalent - r2_exact| at the decision point: see pcg_r2.cuh
-                const long double margin = 0.25L + 1e-7L * rho + 1e-14L * rho2;
+                // bound on |r2_ref-equivalent - r2_exact| at the decision point (pcg_r2.cuh), with 4x safety:
+                // the reference's numerator a2 + r2 - g2 carries ~2 ulp(max(a^2, g^2)) of rounding, worth twice
+                // that in r2; its division / acos / scaling ~8e-16 in the cosine, worth 4 a rho times that
+                const long double big = (g > a ? g * g : a * a);
+                const long double margin = 16.0L * 2.220446049250313e-16L * big + 1.3e-14L * a * rho + 1e-14L * rho2;
                 L.t_lo = nextafter((double)(rho2 - margin), -HUGE_VAL);
                 L.t_hi = nextafter((double)(rho2 + margin), HUGE_VAL);
                 L.rho2 = (double)rho2;

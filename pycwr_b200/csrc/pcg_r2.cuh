@@ -10,8 +10,8 @@
 //  * sweep bracket:  el >= e_k  <=>  r <= rho_k(z) = -a sin e_k + sqrt(g^2 - a^2 cos^2 e_k), the slant
 //    range at which beam k crosses the level.  The reference decides on its ROUNDED el, so the
 //    threshold carries a guard band [t_lo, t_hi] = rho_k^2 -+ margin that bounds every rounding of the
-//    reference chain (a^2, g^2 and the two additions of `num` at magnitude 7e13: <= 0.06 in r2; the
-//    division / acos / scaling: <= 3e-8 * rho); voxels inside a band (~1e-5 of a COLUMN per
+//    reference chain (a^2, g^2 and the two additions of `num`: 2 ulp(max(a^2, g^2)), i.e. <= 0.06 in r2
+//    for Re + h ~ 8.5e6; the division / acos / scaling: <= 3e-8 * rho); voxels inside a band (~1e-5 of a COLUMN per
 //    threshold) take the reference's own chain.  Levels at or below the antenna with sweeps that are
 //    not clearly above the horizon are flagged and take that chain entirely.
 //

@@ -276,6 +276,48 @@ def test_non_finite_grid_coordinates():
     assert_parity(got, want, what="non-finite grid")
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_geometry_parity(seed):
+    """Random radar heights, earth radii, elevation sets (dense and sparse, up to 60 degrees), gate
+    spacings (regular and irregular, per-sweep lengths), level sets and blind modes: interpolation
+    indices and masks must stay bit-exact over the whole parameter space of the r2 thresholds."""
+    rng = np.random.default_rng(1000 + seed)
+    ne = int(rng.integers(2, 14))
+    top = rng.choice([6.0, 20.0, 60.0])
+    fe = np.sort(rng.uniform(rng.choice([-0.5, 0.2, 0.5]), top, ne))
+    fe = fe + np.arange(ne) * 1e-3                       # strictly increasing
+    h = float(rng.choice([0.0, 35.0, 1800.0, 4500.0]))
+    Re = float(rng.choice([8494666.6666666661, 6371000.0, 1.2e7, 5.0e7]))
+    step = float(rng.choice([30.0, 250.0, 1000.0]))
+    ng0 = int(rng.integers(40, 400))
+    regular = bool(rng.integers(0, 2))
+    shared = bool(rng.integers(0, 2))
+    az, rg, vv = [], [], []
+    base = (np.arange(ng0) + 1.0) * step
+    if not regular:
+        base = np.sort(base + rng.uniform(-0.3, 0.3, ng0) * step)
+    for k in range(ne):
+        naz = int(rng.integers(8, 200))
+        az.append(synth.azimuth_table(rng, naz))
+        r = base if shared else base[: max(4, ng0 - 7 * k)]
+        rg.append(np.ascontiguousarray(r))
+        vv.append(synth.stress_moment(rng, naz, r.size, -5.0, 70.0))
+    ext = float(base[-1]) * 1.05
+    gx = rng.uniform(-ext, ext, (33, 29))
+    gy = rng.uniform(-ext, ext, (33, 29))
+    gx[0, :4] = [0.0, step, -step, 0.0]                  # over the radar and on the first gate
+    gy[0, :4] = [0.0, 0.0, 0.0, step]
+    zmax = h + max(500.0, ext * np.tan(np.deg2rad(min(top, 45.0))))
+    lv = np.unique(np.concatenate([np.sort(rng.uniform(h - 300.0, zmax, 11)), [h, h + 1e-3, h + step]]))
+    for blind in ("mask", "hybrid", "nearest_valid"):
+        got, gi = G.get_CAPPI_3d(az, rg, fe, vv, h, gx, gy, lv, FILL, Re, blind, return_index=True)
+        want, wi = O.get_CAPPI_3d(az, rg, fe, vv, h, gx, gy, lv, FILL, Re, blind, return_index=True)
+        assert_parity(got, want, gi, wi, "fuzz %d %s (ne=%d h=%g Re=%g step=%g regular=%s shared=%s)" % (
+            seed, blind, ne, h, Re, step, regular, shared))
+    assert_parity(G.get_CR_xy(az, rg, fe, vv, h, gx, gy, FILL, Re), O.get_CR_xy(az, rg, fe, vv, h, gx, gy, FILL, Re),
+                  what="fuzz CR %d" % seed)
+
+
 def test_inputs_not_mutated_and_output_owned():
     cfg = synth.config(1, scale=0.1)
     va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
