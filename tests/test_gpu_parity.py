@@ -318,6 +318,42 @@ def test_randomised_geometry_parity(seed):
                   what="fuzz CR %d" % seed)
 
 
+def test_full_size_c3_properties():
+    """BASELINE config C3 at full size (1201 x 1201 x 40 from 9 x 360 x 1840): size-independent
+    properties plus a scattered sample against the oracle."""
+    if G.VALUE_DTYPE != "f32":
+        pytest.skip("full-size run on the production layout only")
+    cfg = synth.config(3, style="stress")
+    va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
+    gx, gy, lv = cfg["GridX"], cfg["GridY"], cfg["levels"]
+    dv = DeviceVolume(va, vr, fe, vv, fillvalue=FILL, value_dtype="f32")
+    a = np.array(G.get_CAPPI_3d(None, None, None, dv, h, gx, gy, lv, FILL, None, "hybrid"))
+    b = np.array(G.get_CAPPI_3d(None, None, None, dv, h, gx, gy, lv, FILL, None, "hybrid"))
+    dv.close()
+    assert a.shape == (40, 1201, 1201) and np.array_equal(a, b)                  # deterministic
+    valid = a != FILL
+    assert 0.3 < valid.mean() < 0.99
+    assert a[valid].min() >= -5.0 - 1e-3 and a[valid].max() <= 70.0 + 1e-3       # convex combinations of the moments
+    # a scattered sample of columns, every level, against the oracle (indices bit-exact)
+    rng = np.random.default_rng(12)
+    ix, iy = rng.integers(0, 1201, 1500), rng.integers(0, 1201, 1500)
+    sx, sy = np.ascontiguousarray(gx[ix, iy][:, None]), np.ascontiguousarray(gy[ix, iy][:, None])
+    want, wi = O.get_CAPPI_3d(va, vr, fe, vv, h, sx, sy, lv, FILL, None, "hybrid", return_index=True)
+    assert_parity(a[:, ix, iy][:, :, None], want, what="C3 full-size sample")
+    got_s, gi = G.get_CAPPI_3d(va, vr, fe, vv, h, sx, sy, lv, FILL, None, "hybrid", return_index=True)
+    assert np.array_equal(gi, wi) and np.array_equal(np.array(got_s), a[:, ix, iy][:, :, None])   # grid-shape independent
+    # a constant field without gaps comes back exactly, wherever the geometry allows a value
+    const = [np.full_like(v, 23.5) for v in vv]
+    c = np.array(G.get_CAPPI_3d(va, vr, fe, const, h, gx, gy, lv, FILL, None, "hybrid"))
+    geo = c != FILL
+    assert np.all(c[geo] == 23.5) and np.array_equal(geo | valid, geo)           # data gaps only remove voxels
+    # linearity in the moments: grid(2 v + 3) == 2 grid(v) + 3 where v has a value (same fill pattern)
+    lin = [np.where(v == FILL, FILL, 2.0 * v + 3.0) for v in vv]
+    d = np.array(G.get_CAPPI_3d(va, vr, fe, lin, h, gx, gy, lv, FILL, None, "hybrid"))
+    assert np.array_equal(d != FILL, valid)
+    assert np.max(np.abs(d[valid] - (2.0 * a[valid] + 3.0))) <= 1e-3
+
+
 def test_inputs_not_mutated_and_output_owned():
     cfg = synth.config(1, scale=0.1)
     va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
