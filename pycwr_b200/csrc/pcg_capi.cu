@@ -1519,7 +1519,8 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     std::vector<int> cls(nradar, -1);
     int nclass = 0;
     for (int i = 0; i < nradar; ++i) {
-        if (counts[i] <= 0) continue;
+        // (every radar is classed, reached or not: the order of accumulation at a voxel is then the same
+        //  whether the call covers the whole grid or a slab of it)
         for (int c = 0; c <= nclass && cls[i] < 0; ++c) {
             bool ok = true;
             for (int j = 0; j < i && ok; ++j) {
@@ -1537,7 +1538,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     for (int c = 0; c < nclass; ++c) {
         int slot = 0, used = 0;
         for (int i = 0; i < nradar; ++i) {
-            if (cls[i] != c) continue;
+            if (cls[i] != c || counts[i] <= 0) continue;
             const int ne = vols[i]->ne;
             const size_t smem = (size_t)ne * (sizeof(SweepDesc) + sizeof(FastSweep)) +
                                 (size_t)(ne - 1) * (sizeof(PairDesc) + sizeof(NetPair)) +
