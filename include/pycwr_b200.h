@@ -31,6 +31,9 @@ extern "C" {
 #endif
 
 typedef enum {
+    PCG_WARN_NONFINITE = 1, /* pcg_get_cappi3d / pcg_get_cr on a packed (PCG_VALUE_F32) volume: the result
+                               is complete, but a target coordinate was NaN / inf; the reference's
+                               NaN-by-NaN behaviour is only restated by the PCG_VALUE_F64 layout    */
     PCG_OK = 0,
     PCG_ERR_ARG = -1,      /* bad argument (maps to the reference's ValueError)      */
     PCG_ERR_CUDA = -2,     /* CUDA runtime failure / no device                       */

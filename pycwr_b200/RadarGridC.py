@@ -182,16 +182,21 @@ def interp_ppi(az, r, az_0, az_1, r_0, r_1, mat_00, mat_01, mat_10, mat_11, fill
 VALUE_DTYPE = "f32"
 
 
-def _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue, *grids):
+def _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue, dtype=None):
     if isinstance(vol_value, DeviceVolume):
         return vol_value, False
-    dtype = VALUE_DTYPE
-    # NaN / inf target coordinates: the reference's result then hinges on how every comparison and
-    # lerp treats NaN operand by operand; only the float64 layout restates it operation by operation
-    if dtype == "f32" and any(not np.isfinite(g.sum()) for g in grids):     # one pass, no temporaries
-        dtype = "f64"
     return DeviceVolume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue=float(fillvalue),
-                        value_dtype=dtype), True
+                        value_dtype=dtype or VALUE_DTYPE), True
+
+
+def _redo_in_f64(rc, vol, owned, args):
+    """NaN / inf target coordinates (flagged by the packed kernels): the reference's result then hinges
+    on how every comparison and lerp treats NaN operand by operand; only the float64 layout restates it
+    operation by operation, so a volume this call packed itself is packed again that way."""
+    if rc != _lib.PCG_WARN_NONFINITE or not owned or vol.value_dtype != "f32":
+        return None
+    vol.close()
+    return _as_volume(*args, dtype="f64")[0]
 
 
 def _new_output(shape):
@@ -239,16 +244,22 @@ def get_CR_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height, Gr
     gx = _f64_2d(GridX, "GridX")
     gy = _f64_2d(GridY, "GridY")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
-    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue, gx, gy)
+    pack_args = (vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue)
+    vol, owned = _as_volume(*pack_args)
     nx, ny = gx.shape[0], gy.shape[1]
     out = _new_output((nx, ny))
     try:
         if vol.ne == 0:
             out.fill(fillvalue)
         else:
-            _lib.check(_lib.load().pcg_get_cr(
-                vol.handle, float(radar_height), radius, _lib.as_ptr(gx), _lib.as_ptr(gy), nx, ny,
-                float(fillvalue), _lib.as_ptr(out)))
+            for _ in range(2):
+                rc = _lib.check(_lib.load().pcg_get_cr(
+                    vol.handle, float(radar_height), radius, _lib.as_ptr(gx), _lib.as_ptr(gy), nx, ny,
+                    float(fillvalue), _lib.as_ptr(out)))
+                redo = _redo_in_f64(rc, vol, owned, pack_args)
+                if redo is None:
+                    break
+                vol = redo
     finally:
         if owned:
             vol.close()
@@ -262,12 +273,13 @@ def _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code, bea
     shape = (nz, nx, ny) if vol.nfield == 1 else (vol.nfield, nz, nx, ny)
     out = _new_output(shape)
     idx = np.empty((nz, nx, ny, _lib.IDX_STRIDE), dtype=np.int32) if return_index else None
+    rc = _lib.PCG_OK
     if out.size:
-        _lib.check(_lib.load().pcg_get_cappi3d(
+        rc = _lib.check(_lib.load().pcg_get_cappi3d(
             vol.handle, float(radar_height), radius, _lib.as_ptr(gx), _lib.as_ptr(gy), nx, ny,
             levels.ctypes.data_as(_lib.c_double_p), nz, float(fillvalue), blind_code,
             float(beam_width_deg), _lib.as_ptr(out), _lib.as_ptr(idx) if idx is not None else None))
-    return out, idx
+    return out, idx, rc
 
 
 def get_CAPPI_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height, GridX, GridY,
@@ -278,11 +290,17 @@ def get_CAPPI_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height,
     gy = _f64_2d(GridY, "GridY")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
     blind_code = _resolve_blind_code(blind_method)
-    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue, gx, gy)
+    pack_args = (vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue)
+    vol, owned = _as_volume(*pack_args)
     try:
         levels = np.array([float(level_height)], dtype=np.float64)
-        out, idx = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code,
-                          float(beam_width_deg), return_index)
+        for _ in range(2):
+            out, idx, rc = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code,
+                                  float(beam_width_deg), return_index)
+            redo = _redo_in_f64(rc, vol, owned, pack_args)
+            if redo is None:
+                break
+            vol = redo
     finally:
         if owned:
             vol.close()
@@ -300,10 +318,16 @@ def get_CAPPI_3d(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height,
     levels = _f64_1d(level_heights, "level_heights")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
     blind_code = _resolve_blind_code(blind_method)
-    vol, owned = _as_volume(vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue, gx, gy, levels)
+    pack_args = (vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue)
+    vol, owned = _as_volume(*pack_args)
     try:
-        out, idx = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code, 1.0,
-                          return_index)
+        for _ in range(2):
+            out, idx, rc = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code, 1.0,
+                                  return_index)
+            redo = _redo_in_f64(rc, vol, owned, pack_args)
+            if redo is None:
+                break
+            vol = redo
     finally:
         if owned:
             vol.close()

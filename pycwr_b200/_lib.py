@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYCWR_B200_LIB") or os.path.join(_HERE, "libpycwr_b200.so")
 
 PCG_OK, PCG_ERR_ARG, PCG_ERR_CUDA, PCG_ERR_NOMEM = 0, -1, -2, -3
+PCG_WARN_NONFINITE = 1
 IDX_STRIDE = 10
 VALUE_F64, VALUE_F32 = 0, 1
 
@@ -99,8 +100,8 @@ def load():
 
 def check(rc):
     """Map a pcg_status to the exception the reference would have raised."""
-    if rc == PCG_OK:
-        return
+    if rc == PCG_OK or rc == PCG_WARN_NONFINITE:
+        return rc
     msg = load().pcg_last_error().decode("utf-8", "replace")
     if rc == PCG_ERR_ARG:
         raise ValueError(msg)

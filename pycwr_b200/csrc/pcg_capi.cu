@@ -11,6 +11,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <unordered_map>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -28,6 +30,9 @@ using namespace pcg;
 namespace {
 
 thread_local char g_err[512] = "";
+// device flag the packed kernels raise on NaN / inf target coordinates; set by the host-buffer entry points
+// (under g_mutex) around their launches, NULL otherwise
+int* g_nonfinite_flag = nullptr;
 std::atomic<long long> g_launches{0};
 std::mutex g_mutex;   // guards the scratch arena and the library stream
 
@@ -73,6 +78,61 @@ struct Scratch {
         return PCG_OK;
     }
 };
+
+
+// Device-memory pool for the per-call volume arenas and tables: a gridding call that packs its own volume
+// (the reference's calling convention) would otherwise pay a dozen cudaMalloc / cudaFree pairs, and every
+// cudaFree synchronises the device.  Exact-size reuse, bounded; blocks return after a device synchronise.
+struct DevPool {
+    std::mutex m;
+    std::map<std::pair<int, size_t>, std::vector<void*>> free_list;
+    std::unordered_map<void*, std::pair<int, size_t>> live;
+    size_t cached = 0;
+    static constexpr size_t kMaxCached = (size_t)8 << 30;
+
+    cudaError_t alloc(void** out, size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes == 0) bytes = 256;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        std::lock_guard<std::mutex> lk(m);
+        auto it = free_list.find({dev, bytes});
+        if (it != free_list.end() && !it->second.empty()) {
+            *out = it->second.back();
+            it->second.pop_back();
+            cached -= bytes;
+        } else {
+            e = cudaMalloc(out, bytes);
+            if (e == cudaErrorMemoryAllocation && cached) {       // give the cache back and retry once
+                for (auto& kv : free_list) for (void* q : kv.second) cudaFree(q);
+                free_list.clear();
+                cached = 0;
+                cudaGetLastError();
+                e = cudaMalloc(out, bytes);
+            }
+            if (e != cudaSuccess) { *out = nullptr; return e; }
+        }
+        live[*out] = {dev, bytes};
+        return cudaSuccess;
+    }
+
+    void release(void* ptr) {
+        if (!ptr) return;
+        std::lock_guard<std::mutex> lk(m);
+        auto it = live.find(ptr);
+        if (it == live.end()) { cudaFree(ptr); return; }
+        const std::pair<int, size_t> key = it->second;
+        live.erase(it);
+        if (cached + key.second <= kMaxCached) {
+            free_list[key].push_back(ptr);
+            cached += key.second;
+        } else {
+            cudaFree(ptr);
+        }
+    }
+};
+DevPool g_pool;
 
 enum { S_GX = 0, S_GY, S_OUT, S_IDX, S_TMP0, S_TMP1, S_TMP2, S_NET, S_AUX0, S_AUX1, S_AUX2, S_AUX3, S_AUX4, S_ACC0, S_ACC4, S_ACC5, S_ACC6, S_COUNT };
 Scratch g_scratch[S_COUNT];
@@ -456,15 +516,19 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
             build_level_sweeps(vol, Re, av, levels, nz, ls.data() + (ne + 1), stride, &vol->ls_slow);
             build_level_pairs(ls.data(), nz, ne, vol->ls_slow);
             LevelSweep* fresh = nullptr;
-            CUDA_TRY(cudaMalloc((void**)&fresh, ls.size() * sizeof(LevelSweep)));
+            CUDA_TRY(g_pool.alloc((void**)&fresh, ls.size() * sizeof(LevelSweep)));
             cudaError_t e = cudaMemcpy(fresh, ls.data(), ls.size() * sizeof(LevelSweep), cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) { cudaFree(fresh); return fail(PCG_ERR_CUDA, "threshold upload failed: %s", cudaGetErrorString(e)); }
-            cudaFree(vol->d_ls);          // waits for kernels still reading the previous table
+            if (e != cudaSuccess) { g_pool.release(fresh); return fail(PCG_ERR_CUDA, "threshold upload failed: %s", cudaGetErrorString(e)); }
+            if (vol->d_ls) {
+                cudaDeviceSynchronize();  // kernels may still be reading the previous table
+                g_pool.release(vol->d_ls);
+            }
             vol->d_ls = fresh;
             vol->ls_key.swap(key);
         }
         d_ls = vol->d_ls;
     }
+    RA.nonfinite = g_nonfinite_flag;
     RA.r2.fs = vol->d_fs;
     RA.r2.g_t = vol->d_gt;
     RA.r2.h_t = vol->d_ht;
@@ -579,6 +643,7 @@ int enqueue_cr(const pcg_volume* vol, double h, double Re, const double* d_gx, c
         volatile double ftwoa = 2.0 * fav;
         f.a = fav; f.a2 = fa2; f.twoa = ftwoa; f.Re = Re; f.fill = fill; f.fill32 = (float)fill;
         f.out = d_out;
+        f.nonfinite = g_nonfinite_flag;
         cr_fast_kernel<<<(unsigned)((ncol + 255) / 256), 256, (size_t)vol->ne * sizeof(SweepDesc), st>>>(f);
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
@@ -748,12 +813,12 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
                         "%s failed: %s", #expr, cudaGetErrorString(e__));                      \
         }                                                                                      \
     } while (0)
-    VOL_TRY(cudaMalloc((void**)&v->d_az, (n_az ? n_az : 1) * sizeof(double)));
+    VOL_TRY(g_pool.alloc((void**)&v->d_az, (n_az ? n_az : 1) * sizeof(double)));
     // (+2 entries: the straight-line samplers read entries gi-1 and gi before they know the sweep is usable)
-    VOL_TRY(cudaMalloc((void**)&v->d_rng, (n_rng + 2) * rsz));
+    VOL_TRY(g_pool.alloc((void**)&v->d_rng, (n_rng + 2) * rsz));
     VOL_TRY(cudaMemset(v->d_rng, 0, (n_rng + 2) * rsz));
-    VOL_TRY(cudaMalloc((void**)&v->d_sweeps, v->sweeps.size() * sizeof(SweepDesc)));
-    for (int f = 0; f < nfield; ++f) VOL_TRY(cudaMalloc(&v->d_val[f], (n_val ? n_val : 1) * vsz));
+    VOL_TRY(g_pool.alloc((void**)&v->d_sweeps, v->sweeps.size() * sizeof(SweepDesc)));
+    for (int f = 0; f < nfield; ++f) VOL_TRY(g_pool.alloc(&v->d_val[f], (n_val ? n_val : 1) * vsz));
     v->bytes = n_az * sizeof(double) + n_rng * rsz + v->sweeps.size() * sizeof(SweepDesc) +
                (size_t)nfield * n_val * vsz;
 
@@ -879,7 +944,7 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
                     azt[d.az_off + i] = make_double2(az[s][i], gap > 0.0 ? 1.0 / gap : 0.0);
                 }
             }
-            VOL_TRY(cudaMalloc((void**)&v->d_azt, azt.size() * sizeof(double2)));
+            VOL_TRY(g_pool.alloc((void**)&v->d_azt, azt.size() * sizeof(double2)));
             VOL_TRY(cudaMemcpy(v->d_azt, azt.data(), azt.size() * sizeof(double2), cudaMemcpyHostToDevice));
             v->bytes += azt.size() * sizeof(double2);
             bool uni = ne >= 2;
@@ -899,16 +964,16 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
             v->uniform = uni;
             v->uni_rng_off = fs[0].rng_off; v->uni_ngm1 = fs[0].ngm1;
             v->uni_inv_step = fs[0].inv_step; v->uni_c0 = fs[0].c0;
-            VOL_TRY(cudaMalloc((void**)&v->d_fs, fs.size() * sizeof(FastSweep)));
-            VOL_TRY(cudaMalloc((void**)&v->d_gt, gt.size() * sizeof(double2)));
-            VOL_TRY(cudaMalloc((void**)&v->d_ht, ht.size() * sizeof(GateAux)));
+            VOL_TRY(g_pool.alloc((void**)&v->d_fs, fs.size() * sizeof(FastSweep)));
+            VOL_TRY(g_pool.alloc((void**)&v->d_gt, gt.size() * sizeof(double2)));
+            VOL_TRY(g_pool.alloc((void**)&v->d_ht, ht.size() * sizeof(GateAux)));
             VOL_TRY(cudaMemcpyAsync(v->d_fs, fs.data(), fs.size() * sizeof(FastSweep), cudaMemcpyHostToDevice, st));
             VOL_TRY(cudaMemcpyAsync(v->d_gt, gt.data(), gt.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
             VOL_TRY(cudaMemcpyAsync(v->d_ht, ht.data(), ht.size() * sizeof(GateAux), cudaMemcpyHostToDevice, st));
             VOL_TRY(cudaStreamSynchronize(st));      // the host vectors die with this block
             v->bytes += fs.size() * sizeof(FastSweep) + gt.size() * sizeof(double2) + ht.size() * sizeof(GateAux);
         }
-        VOL_TRY(cudaMalloc((void**)&v->d_pairs, pairs.size() * sizeof(PairDesc)));
+        VOL_TRY(g_pool.alloc((void**)&v->d_pairs, pairs.size() * sizeof(PairDesc)));
         VOL_TRY(cudaMemcpyAsync(v->d_pairs, pairs.data(), pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
         v->bytes += pairs.size() * sizeof(PairDesc);
     }
@@ -935,16 +1000,17 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
 
 int pcg_volume_destroy(pcg_volume* v) {
     if (!v) return PCG_OK;
-    cudaFree(v->d_az);
-    cudaFree(v->d_rng);
-    cudaFree(v->d_sweeps);
-    cudaFree(v->d_pairs);
-    cudaFree(v->d_fs);
-    cudaFree(v->d_azt);
-    cudaFree(v->d_ls);
-    cudaFree(v->d_gt);
-    cudaFree(v->d_ht);
-    for (int f = 0; f < kMaxFields; ++f) cudaFree(v->d_val[f]);
+    cudaDeviceSynchronize();          // nothing may still be reading the arenas when they go back to the pool
+    g_pool.release(v->d_az);
+    g_pool.release(v->d_rng);
+    g_pool.release(v->d_sweeps);
+    g_pool.release(v->d_pairs);
+    g_pool.release(v->d_fs);
+    g_pool.release(v->d_azt);
+    g_pool.release(v->d_ls);
+    g_pool.release(v->d_gt);
+    g_pool.release(v->d_ht);
+    for (int f = 0; f < kMaxFields; ++f) g_pool.release(v->d_val[f]);
     delete v;
     return PCG_OK;
 }
@@ -1009,16 +1075,22 @@ int pcg_get_cappi3d(const pcg_volume* vol, double radar_height, double effective
     }
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = g_scratch[S_TMP2].ensure(sizeof(int)))) return rc;
+    CUDA_TRY(cudaMemsetAsync(g_scratch[S_TMP2].ptr, 0, sizeof(int), st));
+    g_nonfinite_flag = (int*)g_scratch[S_TMP2].ptr;
     rc = enqueue_cappi(vol, radar_height, effective_earth_radius, (const double*)g_scratch[S_GX].ptr,
                        (const double*)g_scratch[S_GY].ptr, (long long)ncol, ny, level_heights, nz, fill,
                        blind_code, beam_width_deg, 0.0, 0.0, 0, 0, (double*)g_scratch[S_OUT].ptr, d_idx, st);
+    g_nonfinite_flag = nullptr;
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, g_scratch[S_OUT].ptr, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (index_out)
         CUDA_TRY(cudaMemcpyAsync(index_out, d_idx, (size_t)nz * ncol * kIdxStride * sizeof(int32_t),
                                  cudaMemcpyDeviceToHost, st));
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, g_scratch[S_TMP2].ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    return PCG_OK;
+    return flag ? PCG_WARN_NONFINITE : PCG_OK;
 }
 
 int pcg_get_cr(const pcg_volume* vol, double radar_height, double effective_earth_radius,
@@ -1037,13 +1109,19 @@ int pcg_get_cr(const pcg_volume* vol, double radar_height, double effective_eart
     if ((rc = g_scratch[S_OUT].ensure(ncol * sizeof(double)))) return rc;
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = g_scratch[S_TMP2].ensure(sizeof(int)))) return rc;
+    CUDA_TRY(cudaMemsetAsync(g_scratch[S_TMP2].ptr, 0, sizeof(int), st));
+    g_nonfinite_flag = (int*)g_scratch[S_TMP2].ptr;
     rc = enqueue_cr(vol, radar_height, effective_earth_radius, (const double*)g_scratch[S_GX].ptr,
                     (const double*)g_scratch[S_GY].ptr, (long long)ncol, fill, -1, 0.0, 0, 0.0, 0.0, 0,
                     (double*)g_scratch[S_OUT].ptr, nullptr, st);
+    g_nonfinite_flag = nullptr;
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, g_scratch[S_OUT].ptr, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, g_scratch[S_TMP2].ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    return PCG_OK;
+    return flag ? PCG_WARN_NONFINITE : PCG_OK;
 }
 
 int pcg_ppi_to_grid(const pcg_volume* vol, int sweep, double elevation_deg, double radar_height,

@@ -253,6 +253,7 @@ struct R2Args {
     FastArgs base;
     R2Ctx r2;
     int lazy_az;                        // many-sweep volume: azimuth brackets on demand (2-entry cache per column)
+    int* nonfinite;                     // optional: set to 1 when a target coordinate is NaN / inf (host entry points)
 };
 
 #ifndef R2_MINB
@@ -304,6 +305,9 @@ __global__ void __launch_bounds__(256, R2_MINB) cappi3d_r2_kernel(const __grid_c
     if (p.grid.shift) { x = sub(x, p.grid.radar_x); y = sub(y, p.grid.radar_y); }
     // column invariants (RadarGridC.pyx:142-146,158)
     const double s = sqrt_rn(add(mul(x, x), mul(y, y)));
+    // NaN / inf targets: the reference's result hinges on NaN semantics operation by operation, which only the
+    // float64 layout restates; tell the host so that it can redo the call there
+    if (P.nonfinite && !(s < __longlong_as_double(0x7ff0000000000000LL))) *P.nonfinite = 1;
     const double cphi = cos_small(div(s, p.Re));
     const double az = azimuth_from_xy(x, y);
 
