@@ -207,6 +207,22 @@ int pcg_column_products_dev(const double *d_volume, const double *d_levels, int 
                             double *d_cr, double *d_vil, double *d_et, unsigned char *d_topped,
                             void *stream);
 
+/* ---- vertical sections and pseudo-RHI cuts -------------------------------
+ * pcg_section_sample: for every sweep of a float64 volume (value_dtype = PCG_VALUE_F64; missing moments
+ *   NaN or the volume's fill value) sample `npts` line points.
+ *   Geometry mode (x, y != NULL): the per-sweep loop of PRD.extract_section (`pycwr/core/NRadar.py:1048-1060`):
+ *   cartesian_xy_elevation_to_range_z (`pycwr/core/transforms.py:224-250`) at the sweep's fixed elevation
+ *   gives (azimuth, slant range, beam height), written to out_az / out_range / out_z [ne][npts], and the
+ *   moment is interpolated there.  Explicit mode (x == NULL): targets come from target_az / target_range,
+ *   [ne][npts] when per_sweep_targets != 0 (the RHI cut of PRD._extract_ppi_rhi, `NRadar.py:1144-1155`,
+ *   rows padded with NaN) else one [npts] row used for every sweep; out_az / out_range / out_z may be NULL.
+ *   Interpolation: PRD._interpolate_ppi_strip_arrays (`NRadar.py:833-913`); azimuth tables must already be
+ *   de-duplicated and reduced mod 360 (`:845-850`, host side).  out_value [ne][npts], NaN = no data. */
+int pcg_section_sample(const pcg_volume *vol, int field, int npts, const double *x, const double *y,
+                       double radar_height, double effective_earth_radius, const double *target_az,
+                       const double *target_range, int per_sweep_targets, double *out_value,
+                       double *out_az, double *out_range, double *out_z);
+
 /* ---- the gridding step of retrieve_wind_volume_xy (`pycwr/retrieve/WindField.py`) ----------
  * pcg_wind_gather: _grid_vvp_retrieval_xy (:629-689) with _aggregate_neighbors (:597-626) for one sweep.
  *   samples: [10][ns] float64 structure of arrays in the order x, y, z, u, v, fit_rmse, valid_count,

@@ -24,6 +24,7 @@
 #include "pcg_network.cuh"
 #include "pcg_products.cuh"
 #include "pcg_wind.cuh"
+#include "pcg_section.cuh"
 
 using namespace pcg;
 
@@ -1998,6 +1999,62 @@ extern "C" int pcg_wind_vertical(const double* sweeps, int nsweep, long long nco
     CUDA_TRY(cudaMemcpyAsync(out_f64, o, 5 * nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(out_i32, oi, 4 * nvox * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(quality_flag, A.flag, nvox, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+// ---- vertical sections (f3) --------------------------------------------------------------------
+extern "C" int pcg_section_sample(const pcg_volume* vol, int field, int npts, const double* x, const double* y,
+                                  double radar_height, double effective_earth_radius, const double* target_az,
+                                  const double* target_range, int per_sweep_targets, double* out_value,
+                                  double* out_az, double* out_range, double* out_z) {
+    int rc;
+    if ((rc = check_volume(vol))) return rc;
+    if (vol->dtype != PCG_VALUE_F64)
+        return fail(PCG_ERR_ARG, "section sampling needs a float64 volume (value_dtype = PCG_VALUE_F64)");
+    if (field < 0 || field >= vol->nfield) return fail(PCG_ERR_ARG, "field %d out of range", field);
+    if (npts < 0) return fail(PCG_ERR_ARG, "npts must be non-negative");
+    if (!out_value) return fail(PCG_ERR_ARG, "NULL output pointer");
+    const bool geometry = x != nullptr;
+    if (geometry && (!y || !out_az || !out_range || !out_z))
+        return fail(PCG_ERR_ARG, "geometry mode needs y, out_az, out_range and out_z");
+    if (!geometry && (!target_az || !target_range)) return fail(PCG_ERR_ARG, "explicit mode needs target_az and target_range");
+    if (geometry && !(effective_earth_radius > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
+    const int ne = vol->ne;
+    const size_t n = (size_t)ne * (size_t)npts;
+    if (n == 0) return PCG_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    const size_t n_in = geometry ? (size_t)npts : (per_sweep_targets ? n : (size_t)npts);
+    if ((rc = g_scratch[S_GX].ensure(n_in * sizeof(double))) || (rc = g_scratch[S_GY].ensure(n_in * sizeof(double))) ||
+        (rc = g_scratch[S_OUT].ensure(4 * n * sizeof(double))))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, geometry ? x : target_az, n_in * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, geometry ? y : target_range, n_in * sizeof(double), cudaMemcpyHostToDevice, st));
+    SectionArgs A;
+    A.vol = view_of(vol);
+    A.field = field;
+    A.npts = npts;
+    A.geometry = geometry ? 1 : 0;
+    A.per_sweep = per_sweep_targets ? 1 : 0;
+    A.h = radar_height;
+    A.Re = effective_earth_radius;
+    A.x = A.t_az = (const double*)g_scratch[S_GX].ptr;
+    A.y = A.t_rng = (const double*)g_scratch[S_GY].ptr;
+    A.fill = vol->fill;
+    double* o = (double*)g_scratch[S_OUT].ptr;
+    A.out_val = o; A.out_az = o + n; A.out_rng = o + 2 * n; A.out_z = o + 3 * n;
+    dim3 grid((unsigned)std::min<size_t>(((size_t)npts + 127) / 128, 4096), (unsigned)ne);
+    section_kernel<<<grid, 128, 0, st>>>(A);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_value, o, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (geometry) {
+        CUDA_TRY(cudaMemcpyAsync(out_az, o + n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(out_range, o + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(out_z, o + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     return PCG_OK;
 }

@@ -90,6 +90,23 @@ class ArrayPRD(object):
         self.vol = self._vol_cache[key]
         return self.vol
 
+    # vertical sections: NRadar.py:1008-1121,1123-1200 on the GPU
+    def extract_section(self, start, end, field_name="dBZ", point_units="km", interpolation="linear",
+                        range_mode=None, sample_spacing=None):
+        from . import section
+        return section.extract_section(self, start, end, field_name, point_units, interpolation, range_mode,
+                                       sample_spacing)
+
+    def extract_section_lonlat(self, start_lonlat, end_lonlat, field_name="dBZ", interpolation="linear",
+                               range_mode=None, sample_spacing=None):
+        from . import section
+        return section.extract_section_lonlat(self, start_lonlat, end_lonlat, field_name, interpolation,
+                                              range_mode, sample_spacing)
+
+    def extract_rhi(self, azimuth=None, field_name="dBZ", range_mode=None):
+        from . import section
+        return section.extract_rhi(self, azimuth, field_name, range_mode)
+
 
 class _Values(object):
     def __init__(self, values):
@@ -329,3 +346,10 @@ class B200ProductMixin(object):
     add_product_CR_lonlat = add_product_CR_lonlat
     add_product_CAPPI_lonlat = add_product_CAPPI_lonlat
     _grid_reflectivity_volume_xy = grid_reflectivity_volume_xy
+
+    @staticmethod
+    def _interpolate_ppi_strip_arrays(azimuth, ranges, values, target_azimuth, target_range):
+        """``extract_section`` / ``_extract_ppi_rhi`` of the reference keep their loops and call this per
+        sweep (``NRadar.py:1061-1063,1153-1155``); ``pycwr_b200.section`` has the one-launch versions."""
+        from . import section
+        return section._interpolate_ppi_strip_arrays(azimuth, ranges, values, target_azimuth, target_range)
