@@ -207,6 +207,21 @@ int pcg_column_products_dev(const double *d_volume, const double *d_levels, int 
                             double *d_cr, double *d_vil, double *d_et, unsigned char *d_topped,
                             void *stream);
 
+/* ---- local VVP wind retrieval on one sweep -----------------------------
+ * pcg_vvp_local: _run_local_vvp (`pycwr/retrieve/WindField.py:1843-1941`): for every (ray, gate) a
+ *   moving window of az_num rays (wrapping) x bin_num gates (both odd), its valid-sample statistics
+ *   (`:58-90`), and — where the window passes the thresholds — the weighted least-squares fit of
+ *   (u, v, radial offset) with Gaussian window weights (`:1832-1840`) and up to five Huber re-weightings
+ *   (`_solve_weighted_least_squares`, `:115-200`).  velocity: [naz][nrange] float64, NaN = missing (the
+ *   caller has already mapped its fill value to NaN, `:50-55`); azimuth, elevation: [naz] degrees.
+ *   out_f64: [9][naz][nrange] in the order u, v, wind_speed, wind_direction, radial_offset, fit_rmse,
+ *   condition_number, valid_fraction, azimuth_coverage_deg (NaN where undefined); out_i32:
+ *   [2][naz][nrange] azimuth_sector_count, valid_count. */
+int pcg_vvp_local(const double *azimuth, const double *elevation, const double *velocity, int naz, int nrange,
+                  int az_num, int bin_num, double min_valid_fraction, int min_valid_count,
+                  double min_azimuth_coverage_deg, int min_azimuth_sector_count, double max_condition_number,
+                  double *out_f64, int32_t *out_i32);
+
 /* ---- vertical sections and pseudo-RHI cuts -------------------------------
  * pcg_section_sample: for every sweep of a float64 volume (value_dtype = PCG_VALUE_F64; missing moments
  *   NaN or the volume's fill value) sample `npts` line points.

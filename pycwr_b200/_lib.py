@@ -57,6 +57,7 @@ SIGNATURES = {
     "pcg_wind_gather": (_i, [_vp, ctypes.c_longlong, _vp, _vp, ctypes.c_longlong, _d, _d, _i, _d, _vp, _vp, _vp]),
     "pcg_wind_vertical": (_i, [_vp, _i, ctypes.c_longlong, c_double_p, _i, _d, _d, _vp, _vp, _vp]),
     "pcg_section_sample": (_i, [_vp, _i, _i, _vp, _vp, _d, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "pcg_vvp_local": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _i, _d, _i, _d, _vp, _vp]),
     "pcg_debug_cartesian_to_antenna": (_i, [_vp, _vp, ctypes.c_size_t, _d, _d, _d, _vp, _vp, _vp]),
     "pcg_debug_sqrt_check": (_i, [_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), c_double_p]),
     "pcg_debug_xye_to_antenna": (_i, [_vp, _vp, ctypes.c_size_t, _d, _d, _d, _vp, _vp]),

@@ -25,6 +25,7 @@
 #include "pcg_products.cuh"
 #include "pcg_wind.cuh"
 #include "pcg_section.cuh"
+#include "pcg_vvp.cuh"
 
 using namespace pcg;
 
@@ -2055,6 +2056,81 @@ extern "C" int pcg_section_sample(const pcg_volume* vol, int field, int npts, co
         CUDA_TRY(cudaMemcpyAsync(out_range, o + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(out_z, o + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCG_OK;
+}
+
+// ---- local VVP (f4) ----------------------------------------------------------------------------
+extern "C" int pcg_vvp_local(const double* azimuth, const double* elevation, const double* velocity, int naz,
+                             int nrange, int az_num, int bin_num, double min_valid_fraction, int min_valid_count,
+                             double min_azimuth_coverage_deg, int min_azimuth_sector_count,
+                             double max_condition_number, double* out_f64, int32_t* out_i32) {
+    if (az_num < 1 || az_num % 2 != 1) return fail(PCG_ERR_ARG, "az_num must be odd");
+    if (bin_num < 1 || bin_num % 2 != 1) return fail(PCG_ERR_ARG, "bin_num must be odd");
+    if (naz < 0 || nrange < 0) return fail(PCG_ERR_ARG, "sizes must be non-negative");
+    if (naz > 65535) return fail(PCG_ERR_ARG, "at most 65535 rays per sweep");
+    if (!out_f64 || !out_i32) return fail(PCG_ERR_ARG, "NULL output pointer");
+    const size_t cells = (size_t)naz * (size_t)nrange;
+    if (cells == 0) return PCG_OK;
+    if (!azimuth || !elevation || !velocity) return fail(PCG_ERR_ARG, "NULL input pointer");
+    const size_t nwin = (size_t)az_num * (size_t)bin_num;
+    auto smem_for = [&](int warps) {
+        return (4 * (size_t)az_num + (size_t)bin_num + (size_t)warps * (2 * nwin + (size_t)((az_num + 1) / 2))) * sizeof(double);
+    };
+    int warps = kVvpMaxWarps;
+    while (warps > 1 && smem_for(warps) > 200 * 1024) warps >>= 1;
+    if (smem_for(warps) > 227 * 1024) return fail(PCG_ERR_ARG, "window of %zu samples does not fit in shared memory", nwin);
+
+    // per-ray design terms (_design_matrix :93-106), azimuth mod 360, window weight factors (:1832-1840)
+    std::vector<double> host((size_t)3 * naz + az_num + bin_num);
+    double* h_d0 = host.data();
+    double* h_d1 = h_d0 + naz;
+    double* h_azm = h_d1 + naz;
+    double* h_wa = h_azm + naz;
+    double* h_wb = h_wa + az_num;
+    for (int i = 0; i < naz; ++i) {
+        const double ar = azimuth[i] * kDeg2Rad, er = elevation[i] * kDeg2Rad;
+        const double ce = cos(er);
+        h_d0[i] = sin(ar) * ce;
+        h_d1[i] = cos(ar) * ce;
+        double m = std::isfinite(azimuth[i]) ? fmod(azimuth[i], 360.0) : NAN;
+        if (m != 0.0) { if (m < 0.0) m += 360.0; } else m = 0.0;
+        h_azm[i] = m;
+    }
+    const double sig_a = std::max(1.0, (az_num - 1) / 3.0), sig_b = std::max(1.0, (bin_num - 1) / 3.0);
+    for (int i = 0; i < az_num; ++i) { const double t = ((double)i - (az_num - 1) / 2.0) / sig_a; h_wa[i] = exp(-0.5 * (t * t)); }
+    for (int i = 0; i < bin_num; ++i) { const double t = ((double)i - (bin_num - 1) / 2.0) / sig_b; h_wb[i] = exp(-0.5 * (t * t)); }
+
+    int rc;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    if ((rc = g_scratch[S_AUX4].ensure(cells * sizeof(double))) || (rc = g_scratch[S_TMP0].ensure(host.size() * sizeof(double))) ||
+        (rc = g_scratch[S_OUT].ensure(9 * cells * sizeof(double))) || (rc = g_scratch[S_IDX].ensure(2 * cells * sizeof(int))))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_AUX4].ptr, velocity, cells * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_TMP0].ptr, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    VvpArgs A;
+    A.vel = (const double*)g_scratch[S_AUX4].ptr;
+    const double* t = (const double*)g_scratch[S_TMP0].ptr;
+    A.d0 = t; A.d1 = t + naz; A.azm = t + 2 * (size_t)naz; A.w_az = t + 3 * (size_t)naz; A.w_bin = A.w_az + az_num;
+    A.naz = naz; A.nrange = nrange; A.az_num = az_num; A.bin_num = bin_num;
+    A.min_valid_fraction = min_valid_fraction; A.min_valid_count = min_valid_count;
+    A.min_coverage = min_azimuth_coverage_deg; A.min_sector_count = min_azimuth_sector_count;
+    A.max_cond = max_condition_number;
+    double* o = (double*)g_scratch[S_OUT].ptr;
+    A.u = o; A.v = o + cells; A.speed = o + 2 * cells; A.direction = o + 3 * cells; A.offset = o + 4 * cells;
+    A.rmse = o + 5 * cells; A.cond = o + 6 * cells; A.valid_fraction = o + 7 * cells; A.coverage = o + 8 * cells;
+    int* oi = (int*)g_scratch[S_IDX].ptr;
+    A.sector_count = oi; A.valid_count = oi + cells;
+    const size_t smem = smem_for(warps);
+    CUDA_TRY(cudaFuncSetAttribute(vvp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((nrange + warps - 1) / warps), (unsigned)naz);
+    vvp_kernel<<<grid, warps * 32, smem, st>>>(A);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_f64, o, 9 * cells * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_i32, oi, 2 * cells * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return PCG_OK;
 }

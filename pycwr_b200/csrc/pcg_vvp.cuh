@@ -1,0 +1,380 @@
+// pcg_vvp.cuh — local moving-window VVP retrieval on one sweep:
+//   _run_local_vvp (pycwr/retrieve/WindField.py:1843-1941) with its helpers
+//   _azimuth_coverage_deg (:58-68), _azimuth_sector_count (:71-81), _effective_min_sector_count (:84-90),
+//   _design_matrix (:93-106), _vvp_window_weights (:1832-1840), _solve_weighted_least_squares (:115-200)
+//   and _wind_direction_from_uv (:109-112).
+//
+// The reference runs a Python loop over every (ray, gate) and, per window, NumPy calls for the window
+// statistics, up to six 3x3 weighted least-squares solves (initial + 5 Huber re-weightings) and two
+// medians per re-weighting.  Here one WARP owns one window (az_num x bin_num samples, 819 by default):
+//   * the window's velocities are staged once in shared memory; the rows' design terms, azimuths and
+//     Gaussian weights are staged once per block (the block's warps are consecutive gates of one ray);
+//   * normal equations are accumulated per lane and reduced by butterfly shuffles (every lane ends with
+//     the same sums, so the 3x3 work — Jacobi eigenvalues for the 2-norm condition number, LU with
+//     partial pivoting like LAPACK's gesv — runs redundantly without further communication);
+//   * medians are exact: bitwise selection on order-preserving 64-bit keys, counts via the warp
+//     reduction instruction.
+// FP64 throughout (velocities: 1e-5 relative bar).  Window statistics (counts, valid fraction, azimuth
+// coverage, sector count) are bit-exact; the fits agree to rounding (different summation order).
+#pragma once
+#include "pcg_math.cuh"
+#include "pcg_network.cuh"
+
+namespace pcg {
+
+constexpr int kVvpMaxWarps = 4;       // windows (consecutive gates of one ray) per block
+
+struct VvpArgs {
+    const double* vel;        // [naz][nrange], NaN = missing
+    const double* d0;         // [naz] sin(az) cos(el)
+    const double* d1;         // [naz] cos(az) cos(el)
+    const double* azm;        // [naz] azimuth mod 360 (NaN when the azimuth is not finite)
+    const double* w_az;       // [az_num] window weight factors
+    const double* w_bin;      // [bin_num]
+    int naz, nrange, az_num, bin_num;
+    double min_valid_fraction;
+    int min_valid_count;
+    double min_coverage;
+    int min_sector_count;     // as requested (capped per window by the sectors its rays can occupy)
+    double max_cond;
+    double* u; double* v; double* speed; double* direction; double* offset; double* rmse; double* cond;
+    double* valid_fraction; double* coverage;
+    int* sector_count; int* valid_count;
+};
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+__device__ __forceinline__ double warp_min(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// order_key (pcg_network.cuh): doubles -> unsigned keys with the same order; key_value inverts it
+__device__ __forceinline__ double key_value(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// k-th smallest (0-based) of keys[0..n): the largest P with #{key < P} <= k.  Invalid slots hold ~0.
+__device__ unsigned long long warp_select(const unsigned long long* keys, int n, int k, int lane) {
+    // bits above the highest bit in which the keys differ are common to all of them
+    unsigned long long all_or = 0ull, all_and = ~0ull;
+    for (int s = lane; s < n; s += 32) {
+        const unsigned long long q = keys[s];
+        if (q != ~0ull) { all_or |= q; all_and &= q; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        all_or |= __shfl_xor_sync(0xffffffffu, all_or, o);
+        all_and &= __shfl_xor_sync(0xffffffffu, all_and, o);
+    }
+    const unsigned long long diff = all_or ^ all_and;
+    const int top = diff ? 63 - __clzll((long long)diff) : -1;
+    unsigned long long prefix = (top >= 63) ? 0ull : (all_and & ~((2ull << top) - 1ull));
+    if (top < 0) return all_and;
+    for (int b = top; b >= 0; --b) {
+        const unsigned long long cand = prefix | (1ull << b);
+        unsigned cnt = 0;
+        for (int s = lane; s < n; s += 32) cnt += keys[s] < cand ? 1u : 0u;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if ((int)cnt <= k) prefix = cand;
+    }
+    return prefix;
+}
+
+// np.median of the m valid keys (invalid slots hold ~0): the middle one, or the mean of the middle two
+__device__ double warp_median(const unsigned long long* keys, int n, int m, int lane) {
+    const int k = (m - 1) >> 1;
+    const unsigned long long lo = warp_select(keys, n, k, lane);
+    if (m & 1) return key_value(lo);
+    // next order statistic: lo again when it is repeated beyond position k, else the smallest key above it
+    unsigned le = 0;
+    unsigned long long up = ~0ull;
+    for (int s = lane; s < n; s += 32) {
+        const unsigned long long q = keys[s];
+        le += q <= lo ? 1u : 0u;
+        if (q > lo && q < up) up = q;
+    }
+    le = __reduce_add_sync(0xffffffffu, le);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, up, o);
+        up = t < up ? t : up;
+    }
+    const unsigned long long hi = ((int)le >= k + 2) ? lo : up;
+    return (key_value(lo) + key_value(hi)) / 2.0;
+}
+
+// eigenvalues of a symmetric 3x3 by cyclic Jacobi rotations; returns max|lambda| / min|lambda|
+__device__ double sym3_condition(double a00, double a01, double a02, double a11, double a12, double a22) {
+    double A[3][3] = {{a00, a01, a02}, {a01, a11, a12}, {a02, a12, a22}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off == 0.0) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            const double apq = A[p][q];
+            if (apq == 0.0) continue;
+            const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+            const int r = 3 - p - q;
+            const double arp = A[r][p], arq = A[r][q];
+            A[p][p] -= t * apq;
+            A[q][q] += t * apq;
+            A[p][q] = A[q][p] = 0.0;
+            A[r][p] = A[p][r] = c * arp - s * arq;
+            A[r][q] = A[q][r] = s * arp + c * arq;
+        }
+    }
+    const double e0 = fabs(A[0][0]), e1 = fabs(A[1][1]), e2 = fabs(A[2][2]);
+    const double hi = fmax(e0, fmax(e1, e2)), lo = fmin(e0, fmin(e1, e2));
+    if (!(hi == hi) || !(lo == lo)) return __longlong_as_double(0x7ff8000000000000LL);
+    return lo == 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : hi / lo;
+}
+
+// 3x3 solve, LU with partial pivoting (the algorithm of LAPACK gesv behind np.linalg.solve)
+__device__ bool solve3(double N[3][3], double b[3], double x[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int piv = c;
+        double best = fabs(N[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < 3; ++r)
+            if (fabs(N[r][c]) > best) { best = fabs(N[r][c]); piv = r; }
+        if (best == 0.0 || !(best == best)) return false;
+        if (piv != c) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { const double t = N[c][j]; N[c][j] = N[piv][j]; N[piv][j] = t; }
+            const double t = b[c]; b[c] = b[piv]; b[piv] = t;
+        }
+#pragma unroll
+        for (int r = c + 1; r < 3; ++r) {
+            const double f = N[r][c] / N[c][c];
+#pragma unroll
+            for (int j = c; j < 3; ++j) N[r][j] -= f * N[c][j];
+            b[r] -= f * b[c];
+        }
+    }
+    x[2] = b[2] / N[2][2];
+    x[1] = (b[1] - N[1][2] * x[2]) / N[1][1];
+    x[0] = (b[0] - N[0][1] * x[1] - N[0][2] * x[2]) / N[0][0];
+    return true;
+}
+
+struct VvpWindow {
+    const double* resp;   // [n] velocities of the window (NaN = not part of the fit)
+    const double* d0;     // [az_num] per window row
+    const double* d1;
+    const double* wa;
+    const double* wb;
+    int n, bin_num;
+    float inv_bin;
+};
+
+// one weighted solve (_solve_once): Huber factors from the residuals about `prev` when scale > 0
+__device__ bool vvp_solve(const VvpWindow& w, int lane, const double prev[3], double scale, double max_cond,
+                          double coef[3], double& cond) {
+    double n00 = 0, n01 = 0, n02 = 0, n11 = 0, n12 = 0, n22 = 0, b0 = 0, b1 = 0, b2 = 0;
+    for (int s = lane; s < w.n; s += 32) {
+        const double y = w.resp[s];
+        if (!(y == y)) continue;
+        const int row = __float2int_rd(((float)s + 0.5f) * w.inv_bin);
+        const int col = s - row * w.bin_num;
+        const double a0 = w.d0[row], a1 = w.d1[row];
+        double wt = w.wa[row] * w.wb[col];
+        if (scale > 0.0) {
+            const double res = y - (a0 * prev[0] + a1 * prev[1] + prev[2]);
+            const double nrm = fabs(res) / (1.5 * scale);
+            if (!(nrm <= 1.0)) wt *= 1.0 / nrm;
+        }
+        const double sq = sqrt(wt);
+        const double x0 = a0 * sq, x1 = a1 * sq, yy = y * sq;
+        n00 += x0 * x0; n01 += x0 * x1; n02 += x0 * sq;
+        n11 += x1 * x1; n12 += x1 * sq; n22 += sq * sq;
+        b0 += x0 * yy; b1 += x1 * yy; b2 += sq * yy;
+    }
+    n00 = warp_sum(n00); n01 = warp_sum(n01); n02 = warp_sum(n02);
+    n11 = warp_sum(n11); n12 = warp_sum(n12); n22 = warp_sum(n22);
+    b0 = warp_sum(b0); b1 = warp_sum(b1); b2 = warp_sum(b2);
+    cond = sym3_condition(n00, n01, n02, n11, n12, n22);
+    if (!isfinite(cond) || cond > max_cond) return false;
+    double N[3][3] = {{n00, n01, n02}, {n01, n11, n12}, {n02, n12, n22}};
+    double b[3] = {b0, b1, b2};
+    return solve3(N, b, coef);
+}
+
+__global__ void __launch_bounds__(kVvpMaxWarps * 32) vvp_kernel(const __grid_constant__ VvpArgs a) {
+    extern __shared__ double sm[];
+    const int A = a.az_num, B = a.bin_num, n = A * B;
+    const int half_az = A / 2, half_bin = B / 2;
+    double* s_d0 = sm;
+    double* s_d1 = s_d0 + A;
+    double* s_azm = s_d1 + A;
+    double* s_wa = s_azm + A;
+    double* s_wb = s_wa + A;
+    double* per_warp = s_wb + B;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* s_resp = per_warp + (size_t)warp * (2 * (size_t)n + (size_t)((A + 1) / 2));
+    unsigned long long* s_key = (unsigned long long*)(s_resp + n);
+    int* s_rowv = (int*)(s_key + n);
+
+    const int az_index = blockIdx.y;
+    const int gate = blockIdx.x * (blockDim.x >> 5) + warp;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+
+    // rows of the window: np.pad(..., mode="wrap") about ray az_index (WindField.py:1876-1878)
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
+        int row = (az_index - half_az + i) % a.naz;
+        if (row < 0) row += a.naz;
+        s_d0[i] = a.d0[row];
+        s_d1[i] = a.d1[row];
+        s_azm[i] = a.azm[row];
+        s_wa[i] = a.w_az[i];
+    }
+    for (int i = threadIdx.x; i < B; i += blockDim.x) s_wb[i] = a.w_bin[i];
+    __syncthreads();
+    if (gate >= a.nrange) return;
+
+    const size_t o = (size_t)az_index * a.nrange + gate;
+    double r_u = nan, r_v = nan, r_speed = nan, r_dir = nan, r_off = nan, r_rmse = nan, r_cond = nan;
+    double r_vf = nan, r_cov = nan;
+    int r_sec = 0, r_vc = 0;
+
+    if (gate >= half_bin && gate < a.nrange - half_bin) {
+        // ---- stage the window, count its finite velocities (:1903-1906) ----------------------------
+        for (int i = lane; i < A; i += 32) s_rowv[i] = 0;
+        __syncwarp();
+        const float inv_bin = 1.0f / (float)B;
+        unsigned vc = 0, nfit = 0;
+        for (int s = lane; s < n; s += 32) {
+            const int row = __float2int_rd(((float)s + 0.5f) * inv_bin);
+            const int col = s - row * B;
+            int src = (az_index - half_az + row) % a.naz;
+            if (src < 0) src += a.naz;
+            const double y = a.vel[(size_t)src * a.nrange + (gate - half_bin + col)];
+            const bool fin = isfinite(y);
+            const bool fit = fin && isfinite(s_d0[row]) && isfinite(s_d1[row]);
+            s_resp[s] = fit ? y : nan;
+            if (fin) { s_rowv[row] = 1; ++vc; }
+            if (fit) ++nfit;
+        }
+        vc = __reduce_add_sync(0xffffffffu, vc);
+        nfit = __reduce_add_sync(0xffffffffu, nfit);
+        __syncwarp();
+        r_vc = (int)vc;
+        r_vf = (double)r_vc / (double)n;
+
+        // ---- azimuth coverage (:58-68) and occupied 45-degree sectors (:71-81) ----------------------
+        // coverage = 360 - largest gap between consecutive distinct azimuths of the rays holding a
+        // finite sample; the successor of each ray is found by direct search (no ordering assumed)
+        double gap = -1.0, lo_az = __longlong_as_double(0x7ff0000000000000LL);
+        unsigned sectors = 0, capacity = 0;
+        for (int i = lane; i < A; i += 32) {
+            const double z = s_azm[i];
+            if (!(z == z)) continue;
+            capacity |= 1u << (int)floor(z / 45.0);
+            if (!s_rowv[i]) continue;
+            sectors |= 1u << (int)floor(z / 45.0);
+            lo_az = fmin(lo_az, z);
+        }
+        lo_az = warp_min(lo_az);
+        sectors = __reduce_or_sync(0xffffffffu, sectors);
+        capacity = __reduce_or_sync(0xffffffffu, capacity);
+        int distinct = 0;
+        for (int i = lane; i < A; i += 32) {
+            const double z = s_azm[i];
+            if (!(z == z) || !s_rowv[i]) continue;
+            double succ = __longlong_as_double(0x7ff0000000000000LL);
+            for (int j = 0; j < A; ++j) {
+                const double q = s_azm[j];
+                if (s_rowv[j] && q > z && q < succ) succ = q;
+            }
+            if (succ < __longlong_as_double(0x7ff0000000000000LL)) { gap = fmax(gap, sub(succ, z)); distinct = 1; }
+            else gap = fmax(gap, sub(add(lo_az, 360.0), z));
+        }
+        gap = warp_max(gap);
+        distinct = __reduce_or_sync(0xffffffffu, (unsigned)distinct);
+        r_cov = (distinct && gap >= 0.0) ? fmax(0.0, sub(360.0, gap)) : 0.0;
+        r_sec = __popc(sectors);
+        int required = 0;
+        if (a.min_sector_count > 0) required = min(a.min_sector_count, max(__popc(capacity), 1));
+
+        if (!(r_vc < a.min_valid_count || r_vf < a.min_valid_fraction || r_cov < a.min_coverage || r_sec < required) &&
+            nfit > 0) {
+            // ---- weighted least squares with Huber re-weighting (:115-200) ---------------------------
+            VvpWindow w;
+            w.resp = s_resp; w.d0 = s_d0; w.d1 = s_d1; w.wa = s_wa; w.wb = s_wb;
+            w.n = n; w.bin_num = B; w.inv_bin = inv_bin;
+            double coef[3] = {0.0, 0.0, 0.0}, cond = nan;
+            const double zero3[3] = {0.0, 0.0, 0.0};
+            if (vvp_solve(w, lane, zero3, 0.0, a.max_cond, coef, cond)) {
+                for (int it = 0; it < 5; ++it) {
+                    // scale = 1.4826 * median(|res - median(res)|)
+                    for (int s = lane; s < n; s += 32) {
+                        const double y = s_resp[s];
+                        const int row = __float2int_rd(((float)s + 0.5f) * inv_bin);
+                        s_key[s] = (y == y) ? order_key(y - (s_d0[row] * coef[0] + s_d1[row] * coef[1] + coef[2])) : ~0ull;
+                    }
+                    __syncwarp();
+                    const double med = warp_median(s_key, n, (int)nfit, lane);
+                    __syncwarp();
+                    for (int s = lane; s < n; s += 32) {
+                        const unsigned long long q = s_key[s];
+                        if (q != ~0ull) s_key[s] = order_key(fabs(key_value(q) - med));
+                    }
+                    __syncwarp();
+                    const double scale = 1.4826 * warp_median(s_key, n, (int)nfit, lane);
+                    __syncwarp();
+                    if (!isfinite(scale) || scale < 1.0e-6) break;
+                    double nc[3], ncond;
+                    if (!vvp_solve(w, lane, coef, scale, a.max_cond, nc, ncond)) break;
+                    bool close = true;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        close = close && (fabs(nc[k] - coef[k]) <= 1.0e-5 + 1.0e-5 * fabs(coef[k]));
+                    coef[0] = nc[0]; coef[1] = nc[1]; coef[2] = nc[2];
+                    cond = ncond;
+                    if (close) break;
+                }
+                double ss = 0.0;
+                for (int s = lane; s < n; s += 32) {
+                    const double y = s_resp[s];
+                    if (!(y == y)) continue;
+                    const int row = __float2int_rd(((float)s + 0.5f) * inv_bin);
+                    const double res = y - (s_d0[row] * coef[0] + s_d1[row] * coef[1] + coef[2]);
+                    ss += res * res;
+                }
+                ss = warp_sum(ss);
+                r_u = coef[0];
+                r_v = coef[1];
+                r_off = coef[2];
+                r_speed = hypot(r_u, r_v);
+                double dir = fmod(sub(270.0, mul(atan2(r_v, r_u), kRad2Deg)), 360.0);
+                if (dir != 0.0) { if (dir < 0.0) dir = add(dir, 360.0); } else dir = 0.0;   // np.mod: sign of the divisor
+                r_dir = dir;
+                r_rmse = sqrt(ss / (double)nfit);
+            }
+            r_cond = cond;
+        }
+    }
+    if (lane == 0) {
+        a.u[o] = r_u; a.v[o] = r_v; a.speed[o] = r_speed; a.direction[o] = r_dir; a.offset[o] = r_off;
+        a.rmse[o] = r_rmse; a.cond[o] = r_cond; a.valid_fraction[o] = r_vf; a.coverage[o] = r_cov;
+        a.sector_count[o] = r_sec; a.valid_count[o] = r_vc;
+    }
+}
+
+}  // namespace pcg

@@ -3,8 +3,9 @@
 (``_grid_vvp_retrieval_xy`` :629-689) and the per-column vertical reconstruction
 (``_reconstruct_wind_volume_chunk`` :1183-1229 over ``_vertical_profile_from_sweeps`` :692-810).
 Same names, arguments, defaults, output keys / dtypes and errors; the neighbour search and the sums
-run on the GPU (no cKDTree, no per-target Python loop).  The VAD / VVP solvers upstream of this step
-are out of scope."""
+run on the GPU (no cKDTree, no per-target Python loop).  Upstream of it, ``_run_local_vvp`` (:1843-1941,
+SURVEY.md §8 row f4) — the moving-window least-squares retrieval that produces those samples — runs as one
+kernel launch per sweep (one warp per window) instead of a Python loop over every ray and gate."""
 import numpy as np
 
 from . import _lib
@@ -124,3 +125,46 @@ def grid_wind_volume(retrievals, target_x, target_y, level_heights, horizontal_r
     return reconstruct_wind_volume(stack("z"), stack("u"), stack("v"), stack("fit_rmse"), stack("valid_count"),
                                    stack("neighbor_count"), stack("expanded_radius"), level_heights,
                                    vertical_tolerance_m, max_vertical_gap_m)
+
+
+# ------------------------------------------------------------------------------------------------
+# f4: local moving-window VVP on one sweep
+# ------------------------------------------------------------------------------------------------
+
+_VVP_F64 = ("u", "v", "wind_speed", "wind_direction", "radial_offset", "fit_rmse", "condition_number",
+            "valid_fraction", "azimuth_coverage_deg")
+_VVP_I32 = ("azimuth_sector_count", "valid_count")
+
+
+def _run_local_vvp(azimuth, elevation, radial_velocity, az_num, bin_num, fillvalue=-999.0, min_valid_fraction=0.7,
+                   min_valid_count=20, min_azimuth_coverage_deg=0.0, min_azimuth_sector_count=2,
+                   max_condition_number=1.0e9):
+    """``_run_local_vvp`` (``WindField.py:1843-1941``): dict of ``(naz, nrange)`` arrays with the reference's
+    keys and dtypes."""
+    if az_num % 2 != 1:
+        raise ValueError("az_num must be odd")
+    if bin_num % 2 != 1:
+        raise ValueError("bin_num must be odd")
+    vel = np.asarray(radial_velocity, dtype=np.float64)
+    if fillvalue is not None:                                              # _as_float_array :50-55
+        vel = np.where(vel == float(fillvalue), np.nan, vel)
+    vel = np.ascontiguousarray(vel)
+    azimuth = np.ascontiguousarray(azimuth, dtype=np.float64).reshape(-1)
+    if vel.ndim != 2 or azimuth.size != vel.shape[0]:
+        raise ValueError("azimuth length must match the first radial_velocity dimension")
+    if np.asarray(elevation).ndim == 0:
+        elevation = np.full(azimuth.shape, float(elevation), dtype=np.float64)
+    else:
+        elevation = np.ascontiguousarray(elevation, dtype=np.float64).reshape(-1)
+    if elevation.shape != azimuth.shape:
+        raise ValueError("elevation must be scalar or match the azimuth shape")
+    naz, nrange = vel.shape
+    f64 = np.empty((len(_VVP_F64), naz, nrange), dtype=np.float64)
+    i32 = np.empty((len(_VVP_I32), naz, nrange), dtype=np.int32)
+    _lib.check(_lib.load().pcg_vvp_local(
+        azimuth.ctypes.data, elevation.ctypes.data, vel.ctypes.data, int(naz), int(nrange), int(az_num), int(bin_num),
+        float(min_valid_fraction), int(min_valid_count), float(min_azimuth_coverage_deg),
+        int(min_azimuth_sector_count), float(max_condition_number), f64.ctypes.data, i32.ctypes.data))
+    out = {k: f64[i] for i, k in enumerate(_VVP_F64)}
+    out.update({k: i32[i] for i, k in enumerate(_VVP_I32)})
+    return out
