@@ -12,8 +12,8 @@
 //   * normal equations are accumulated per lane and reduced by butterfly shuffles (every lane ends with
 //     the same sums, so the 3x3 work — Jacobi eigenvalues for the 2-norm condition number, LU with
 //     partial pivoting like LAPACK's gesv — runs redundantly without further communication);
-//   * medians are exact: bitwise selection on order-preserving 64-bit keys, counts via the warp
-//     reduction instruction.
+//   * medians are exact: bitwise selection on order-preserving 64-bit keys (high words first, the low
+//     words only among keys that share the selected high word), counts via the warp reduction instruction.
 // FP64 throughout (velocities: 1e-5 relative bar).  Window statistics (counts, valid fraction, azimuth
 // coverage, sector count) are bit-exact; the fits agree to rounding (different summation order).
 #pragma once
@@ -66,45 +66,90 @@ __device__ __forceinline__ double key_value(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-// k-th smallest (0-based) of keys[0..n): the largest P with #{key < P} <= k.  Invalid slots hold ~0.
-__device__ unsigned long long warp_select(const unsigned long long* keys, int n, int k, int lane) {
-    // bits above the highest bit in which the keys differ are common to all of them
-    unsigned long long all_or = 0ull, all_and = ~0ull;
-    for (int s = lane; s < n; s += 32) {
-        const unsigned long long q = keys[s];
-        if (q != ~0ull) { all_or |= q; all_and &= q; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        all_or |= __shfl_xor_sync(0xffffffffu, all_or, o);
-        all_and &= __shfl_xor_sync(0xffffffffu, all_and, o);
-    }
-    const unsigned long long diff = all_or ^ all_and;
-    const int top = diff ? 63 - __clzll((long long)diff) : -1;
-    unsigned long long prefix = (top >= 63) ? 0ull : (all_and & ~((2ull << top) - 1ull));
-    if (top < 0) return all_and;
-    for (int b = top; b >= 0; --b) {
-        const unsigned long long cand = prefix | (1ull << b);
-        unsigned cnt = 0;
-        for (int s = lane; s < n; s += 32) cnt += keys[s] < cand ? 1u : 0u;
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if ((int)cnt <= k) prefix = cand;
-    }
-    return prefix;
+// c += (w >= cand): the carry-out of w - cand feeds an add-with-carry (two integer instructions, no select)
+__device__ __forceinline__ unsigned add_not_below(unsigned c, unsigned w, unsigned cand) {
+    unsigned t;
+    asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %2, %3;\n\taddc.u32 %0, %1, 0;\n\t}" : "=r"(t) : "r"(c), "r"(w), "r"(cand));
+    return t;
 }
 
-// np.median of the m valid keys (invalid slots hold ~0): the middle one, or the mean of the middle two
-__device__ double warp_median(const unsigned long long* keys, int n, int m, int lane) {
+// #{w[s] < cand : s = lane, lane + 32, ...} summed over the warp = n - #{w[s] >= cand}: four independent
+// partial counts, immediate-offset loads
+__device__ __forceinline__ unsigned count_below(const unsigned* w, int n, unsigned cand, int lane) {
+    unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    int s = lane;
+    for (; s + 96 < n; s += 128) {
+        c0 = add_not_below(c0, w[s], cand);
+        c1 = add_not_below(c1, w[s + 32], cand);
+        c2 = add_not_below(c2, w[s + 64], cand);
+        c3 = add_not_below(c3, w[s + 96], cand);
+    }
+    for (; s < n; s += 32) c0 = add_not_below(c0, w[s], cand);
+    return (unsigned)n - __reduce_add_sync(0xffffffffu, (c0 + c1) + (c2 + c3));
+}
+
+// Keys live in shared memory as separate high / low 32-bit words (conflict-free 32-bit loads); slots that
+// are not part of the fit hold hi = 0xffffffff (the key of a negative NaN: never produced by a residual).
+// k-th smallest (0-based): bitwise selection on the high words first — the largest P with #{hi < P} <= k —
+// then, only if several keys share that high word, the same on their low words.
+__device__ unsigned long long warp_select(const unsigned* hi, const unsigned* lo, int n, int k, int lane) {
+    unsigned all_or = 0u, all_and = ~0u;
+    for (int s = lane; s < n; s += 32) {
+        const unsigned h = hi[s];
+        if (h != ~0u) { all_or |= h; all_and &= h; }
+    }
+    all_or = __reduce_or_sync(0xffffffffu, all_or);
+    all_and = __reduce_and_sync(0xffffffffu, all_and);
+    unsigned diff = all_or ^ all_and;
+    unsigned H = all_and;
+    if (diff) {
+        const int top = 31 - __clz((int)diff);
+        H = all_and & ~((2u << top) - 1u);
+        for (int b = top; b >= 0; --b) {
+            const unsigned cand = H | (1u << b);
+            if ((int)count_below(hi, n, cand, lane) <= k) H = cand;
+        }
+    }
+    // the keys sharing H
+    unsigned less = 0, grp = 0, l_or = 0u, l_and = ~0u;
+    for (int s = lane; s < n; s += 32) {
+        const unsigned h = hi[s];
+        less += h < H ? 1u : 0u;
+        if (h == H) { ++grp; const unsigned l = lo[s]; l_or |= l; l_and &= l; }
+    }
+    less = __reduce_add_sync(0xffffffffu, less);
+    grp = __reduce_add_sync(0xffffffffu, grp);
+    l_or = __reduce_or_sync(0xffffffffu, l_or);
+    l_and = __reduce_and_sync(0xffffffffu, l_and);
+    diff = l_or ^ l_and;
+    unsigned L = l_and;
+    if (grp > 1 && diff) {
+        const int k2 = k - (int)less;
+        const int top = 31 - __clz((int)diff);
+        L = l_and & ~((2u << top) - 1u);
+        for (int b = top; b >= 0; --b) {
+            const unsigned cand = L | (1u << b);
+            unsigned cnt = 0;
+            for (int s = lane; s < n; s += 32) cnt += (hi[s] == H && lo[s] < cand) ? 1u : 0u;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if ((int)cnt <= k2) L = cand;
+        }
+    }
+    return ((unsigned long long)H << 32) | L;
+}
+
+// np.median of the m keys taking part: the middle one, or the mean of the middle two
+__device__ double warp_median(const unsigned* hi, const unsigned* lo, int n, int m, int lane) {
     const int k = (m - 1) >> 1;
-    const unsigned long long lo = warp_select(keys, n, k, lane);
-    if (m & 1) return key_value(lo);
-    // next order statistic: lo again when it is repeated beyond position k, else the smallest key above it
+    const unsigned long long mid = warp_select(hi, lo, n, k, lane);
+    if (m & 1) return key_value(mid);
+    // next order statistic: `mid` again when it is repeated beyond position k, else the smallest key above it
     unsigned le = 0;
     unsigned long long up = ~0ull;
     for (int s = lane; s < n; s += 32) {
-        const unsigned long long q = keys[s];
-        le += q <= lo ? 1u : 0u;
-        if (q > lo && q < up) up = q;
+        const unsigned long long q = ((unsigned long long)hi[s] << 32) | lo[s];
+        le += q <= mid ? 1u : 0u;
+        if (q > mid && q < up) up = q;
     }
     le = __reduce_add_sync(0xffffffffu, le);
 #pragma unroll
@@ -112,8 +157,8 @@ __device__ double warp_median(const unsigned long long* keys, int n, int m, int 
         const unsigned long long t = __shfl_xor_sync(0xffffffffu, up, o);
         up = t < up ? t : up;
     }
-    const unsigned long long hi = ((int)le >= k + 2) ? lo : up;
-    return (key_value(lo) + key_value(hi)) / 2.0;
+    const unsigned long long next = ((int)le >= k + 2) ? mid : up;
+    return (key_value(mid) + key_value(next)) / 2.0;
 }
 
 // eigenvalues of a symmetric 3x3 by cyclic Jacobi rotations; returns max|lambda| / min|lambda|
@@ -197,8 +242,9 @@ __device__ bool vvp_solve(const VvpWindow& w, int lane, const double prev[3], do
         double wt = w.wa[row] * w.wb[col];
         if (scale > 0.0) {
             const double res = y - (a0 * prev[0] + a1 * prev[1] + prev[2]);
-            const double nrm = fabs(res) / (1.5 * scale);
-            if (!(nrm <= 1.0)) wt *= 1.0 / nrm;
+            // np.where(normalized <= 1, 1, 1 / normalized), normalized = |res| / (1.5 scale): one division
+            const double lim = 1.5 * scale, ar = fabs(res);
+            if (!(ar <= lim)) wt *= lim / ar;
         }
         const double sq = sqrt(wt);
         const double x0 = a0 * sq, x1 = a1 * sq, yy = y * sq;
@@ -228,8 +274,9 @@ __global__ void __launch_bounds__(kVvpMaxWarps * 32) vvp_kernel(const __grid_con
     double* per_warp = s_wb + B;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* s_resp = per_warp + (size_t)warp * (2 * (size_t)n + (size_t)((A + 1) / 2));
-    unsigned long long* s_key = (unsigned long long*)(s_resp + n);
-    int* s_rowv = (int*)(s_key + n);
+    unsigned* s_hi = (unsigned*)(s_resp + n);
+    unsigned* s_lo = s_hi + n;
+    int* s_rowv = (int*)(s_lo + n);
 
     const int az_index = blockIdx.y;
     const int gate = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -321,22 +368,29 @@ __global__ void __launch_bounds__(kVvpMaxWarps * 32) vvp_kernel(const __grid_con
             double coef[3] = {0.0, 0.0, 0.0}, cond = nan;
             const double zero3[3] = {0.0, 0.0, 0.0};
             if (vvp_solve(w, lane, zero3, 0.0, a.max_cond, coef, cond)) {
+#pragma unroll 1
                 for (int it = 0; it < 5; ++it) {
                     // scale = 1.4826 * median(|res - median(res)|)
                     for (int s = lane; s < n; s += 32) {
                         const double y = s_resp[s];
                         const int row = __float2int_rd(((float)s + 0.5f) * inv_bin);
-                        s_key[s] = (y == y) ? order_key(y - (s_d0[row] * coef[0] + s_d1[row] * coef[1] + coef[2])) : ~0ull;
+                        const unsigned long long q =
+                            (y == y) ? order_key(y - (s_d0[row] * coef[0] + s_d1[row] * coef[1] + coef[2])) : ~0ull;
+                        s_hi[s] = (unsigned)(q >> 32);
+                        s_lo[s] = (unsigned)q;
                     }
                     __syncwarp();
-                    const double med = warp_median(s_key, n, (int)nfit, lane);
+                    const double med = warp_median(s_hi, s_lo, n, (int)nfit, lane);
                     __syncwarp();
                     for (int s = lane; s < n; s += 32) {
-                        const unsigned long long q = s_key[s];
-                        if (q != ~0ull) s_key[s] = order_key(fabs(key_value(q) - med));
+                        const unsigned h = s_hi[s];
+                        if (h == ~0u) continue;
+                        const unsigned long long q = order_key(fabs(key_value(((unsigned long long)h << 32) | s_lo[s]) - med));
+                        s_hi[s] = (unsigned)(q >> 32);
+                        s_lo[s] = (unsigned)q;
                     }
                     __syncwarp();
-                    const double scale = 1.4826 * warp_median(s_key, n, (int)nfit, lane);
+                    const double scale = 1.4826 * warp_median(s_hi, s_lo, n, (int)nfit, lane);
                     __syncwarp();
                     if (!isfinite(scale) || scale < 1.0e-6) break;
                     double nc[3], ncond;
