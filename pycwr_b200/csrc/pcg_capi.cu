@@ -646,7 +646,11 @@ int enqueue_cr(const pcg_volume* vol, double h, double Re, const double* d_gx, c
         f.a = fav; f.a2 = fa2; f.twoa = ftwoa; f.Re = Re; f.fill = fill; f.fill32 = (float)fill;
         f.out = d_out;
         f.nonfinite = g_nonfinite_flag;
-        cr_fast_kernel<<<(unsigned)((ncol + 255) / 256), 256, (size_t)vol->ne * sizeof(SweepDesc), st>>>(f);
+        // small grids: two warps share the sweeps of every 32 columns (see cr_fast_kernel)
+        const int W = (vol->ne >= 2 && ncol < 148LL * 2048) ? 2 : 1;
+        const long long per_block = 32LL * (kCrWarps / W);
+        cr_fast_kernel<<<(unsigned)((ncol + per_block - 1) / per_block), 32 * kCrWarps,
+                         (size_t)vol->ne * sizeof(SweepDesc), st>>>(f, W);
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
         return PCG_OK;
