@@ -2079,7 +2079,7 @@ extern "C" int pcg_vvp_local(const double* azimuth, const double* elevation, con
     if (!azimuth || !elevation || !velocity) return fail(PCG_ERR_ARG, "NULL input pointer");
     const size_t nwin = (size_t)az_num * (size_t)bin_num;
     auto smem_for = [&](int warps) {
-        return (4 * (size_t)az_num + (size_t)bin_num + (size_t)warps * (2 * nwin + (size_t)((az_num + 1) / 2))) * sizeof(double);
+        return (4 * (size_t)az_num + (size_t)bin_num + (size_t)warps * (2 * nwin + 32 + (size_t)((az_num + 1) / 2))) * sizeof(double);
     };
     int warps = kVvpMaxWarps;
     while (warps > 1 && smem_for(warps) > 200 * 1024) warps >>= 1;

@@ -92,7 +92,17 @@ __device__ __forceinline__ unsigned count_below(const unsigned* w, int n, unsign
 // are not part of the fit hold hi = 0xffffffff (the key of a negative NaN: never produced by a residual).
 // k-th smallest (0-based): bitwise selection on the high words first — the largest P with #{hi < P} <= k —
 // then, only if several keys share that high word, the same on their low words.
-__device__ unsigned long long warp_select(const unsigned* hi, const unsigned* lo, int n, int k, int lane) {
+//
+// The bit-by-bit narrowing on the high words stops as soon as at most 32 keys remain in the surviving
+// interval (a handful of iterations for residual-like data: sign and exponent settle quickly and only a
+// few per cent of a window share the median's binade); those keys are compacted to one per lane and
+// ranked with shuffles.  Only degenerate windows (more than 32 keys sharing a complete high word) run
+// the selection down to the last bit and repeat it on the low words.
+struct Select2 { unsigned long long kth, next; };     // order statistics k and k + 1 (next: when asked for)
+
+__device__ Select2 warp_select(const unsigned* hi, const unsigned* lo, int n, int m, int k, bool want_next,
+                               unsigned long long* cand_buf, int lane) {
+    Select2 out;
     unsigned all_or = 0u, all_and = ~0u;
     for (int s = lane; s < n; s += 32) {
         const unsigned h = hi[s];
@@ -100,65 +110,112 @@ __device__ unsigned long long warp_select(const unsigned* hi, const unsigned* lo
     }
     all_or = __reduce_or_sync(0xffffffffu, all_or);
     all_and = __reduce_and_sync(0xffffffffu, all_and);
-    unsigned diff = all_or ^ all_and;
-    unsigned H = all_and;
-    if (diff) {
-        const int top = 31 - __clz((int)diff);
-        H = all_and & ~((2u << top) - 1u);
-        for (int b = top; b >= 0; --b) {
-            const unsigned cand = H | (1u << b);
-            if ((int)count_below(hi, n, cand, lane) <= k) H = cand;
+    const unsigned diff = all_or ^ all_and;
+    int b = diff ? 31 - __clz((int)diff) : -1;          // bits b..0 of the high word are still undecided
+    unsigned H = (b >= 0) ? (all_and & ~((2u << b) - 1u)) : all_and;
+    int below = 0, upto = m;                             // #keys < [H, last], #keys <= last
+    while (upto - below > 32 && b >= 0) {
+        const unsigned cand = H | (1u << b);
+        const int cnt = (int)count_below(hi, n, cand, lane);
+        if (cnt <= k) { H = cand; below = cnt; } else { upto = cnt; }
+        --b;
+    }
+    if (upto - below <= 32) {
+        const unsigned last = H | ((b >= 0) ? ((2u << b) - 1u) : 0u);
+        // compact the survivors, one per lane
+        int filled = 0;
+        for (int s0 = 0; s0 < n; s0 += 32) {
+            const int s = s0 + lane;
+            const unsigned h = s < n ? hi[s] : ~0u;
+            const bool in = (h >= H) & (h <= last) & (h != ~0u);
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) cand_buf[filled + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)h << 32) | lo[s];
+            filled += __popc(bal);
         }
+        __syncwarp();
+        const unsigned long long key = lane < filled ? cand_buf[lane] : ~0ull;
+        __syncwarp();
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const unsigned long long o = __shfl_sync(0xffffffffu, key, j);
+            rank += (o < key || (o == key && j < lane)) ? 1 : 0;
+        }
+        const int r = k - below;
+        unsigned who = __ballot_sync(0xffffffffu, rank == r);
+        out.kth = __shfl_sync(0xffffffffu, key, __ffs((int)who) - 1);
+        out.next = out.kth;
+        if (want_next) {
+            if (r + 1 < filled) {
+                who = __ballot_sync(0xffffffffu, rank == r + 1);
+                out.next = __shfl_sync(0xffffffffu, key, __ffs((int)who) - 1);
+            } else {                                     // the smallest key above the interval
+                unsigned long long up = ~0ull;
+                for (int s = lane; s < n; s += 32) {
+                    const unsigned h = hi[s];
+                    if (h > last && h != ~0u) {
+                        const unsigned long long q = ((unsigned long long)h << 32) | lo[s];
+                        up = q < up ? q : up;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long t = __shfl_xor_sync(0xffffffffu, up, o);
+                    up = t < up ? t : up;
+                }
+                out.next = up;
+            }
+        }
+        return out;
     }
-    // the keys sharing H
-    unsigned less = 0, grp = 0, l_or = 0u, l_and = ~0u;
-    for (int s = lane; s < n; s += 32) {
-        const unsigned h = hi[s];
-        less += h < H ? 1u : 0u;
-        if (h == H) { ++grp; const unsigned l = lo[s]; l_or |= l; l_and &= l; }
-    }
-    less = __reduce_add_sync(0xffffffffu, less);
-    grp = __reduce_add_sync(0xffffffffu, grp);
+    // ---- more than 32 keys share the high word H: select on their low words ----------------------
+    unsigned l_or = 0u, l_and = ~0u;
+    for (int s = lane; s < n; s += 32)
+        if (hi[s] == H) { const unsigned l = lo[s]; l_or |= l; l_and &= l; }
     l_or = __reduce_or_sync(0xffffffffu, l_or);
     l_and = __reduce_and_sync(0xffffffffu, l_and);
-    diff = l_or ^ l_and;
+    const unsigned ldiff = l_or ^ l_and;
     unsigned L = l_and;
-    if (grp > 1 && diff) {
-        const int k2 = k - (int)less;
-        const int top = 31 - __clz((int)diff);
+    if (ldiff) {
+        const int k2 = k - below;
+        const int top = 31 - __clz((int)ldiff);
         L = l_and & ~((2u << top) - 1u);
-        for (int b = top; b >= 0; --b) {
-            const unsigned cand = L | (1u << b);
+        for (int bb = top; bb >= 0; --bb) {
+            const unsigned cand = L | (1u << bb);
             unsigned cnt = 0;
             for (int s = lane; s < n; s += 32) cnt += (hi[s] == H && lo[s] < cand) ? 1u : 0u;
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             if ((int)cnt <= k2) L = cand;
         }
     }
-    return ((unsigned long long)H << 32) | L;
+    out.kth = ((unsigned long long)H << 32) | L;
+    out.next = out.kth;
+    if (want_next) {
+        // `kth` again when it is repeated beyond position k, else the smallest key above it
+        unsigned le = 0;
+        unsigned long long up = ~0ull;
+        for (int s = lane; s < n; s += 32) {
+            const unsigned long long q = ((unsigned long long)hi[s] << 32) | lo[s];
+            le += q <= out.kth ? 1u : 0u;
+            if (q > out.kth && q < up) up = q;
+        }
+        le = __reduce_add_sync(0xffffffffu, le);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, up, o);
+            up = t < up ? t : up;
+        }
+        out.next = ((int)le >= k + 2) ? out.kth : up;
+    }
+    return out;
 }
 
 // np.median of the m keys taking part: the middle one, or the mean of the middle two
-__device__ double warp_median(const unsigned* hi, const unsigned* lo, int n, int m, int lane) {
-    const int k = (m - 1) >> 1;
-    const unsigned long long mid = warp_select(hi, lo, n, k, lane);
-    if (m & 1) return key_value(mid);
-    // next order statistic: `mid` again when it is repeated beyond position k, else the smallest key above it
-    unsigned le = 0;
-    unsigned long long up = ~0ull;
-    for (int s = lane; s < n; s += 32) {
-        const unsigned long long q = ((unsigned long long)hi[s] << 32) | lo[s];
-        le += q <= mid ? 1u : 0u;
-        if (q > mid && q < up) up = q;
-    }
-    le = __reduce_add_sync(0xffffffffu, le);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(0xffffffffu, up, o);
-        up = t < up ? t : up;
-    }
-    const unsigned long long next = ((int)le >= k + 2) ? mid : up;
-    return (key_value(mid) + key_value(next)) / 2.0;
+__device__ double warp_median(const unsigned* hi, const unsigned* lo, int n, int m, unsigned long long* cand_buf,
+                              int lane) {
+    const Select2 s2 = warp_select(hi, lo, n, m, (m - 1) >> 1, !(m & 1), cand_buf, lane);
+    if (m & 1) return key_value(s2.kth);
+    return (key_value(s2.kth) + key_value(s2.next)) / 2.0;
 }
 
 // eigenvalues of a symmetric 3x3 by cyclic Jacobi rotations; returns max|lambda| / min|lambda|
@@ -273,10 +330,11 @@ __global__ void __launch_bounds__(kVvpMaxWarps * 32) vvp_kernel(const __grid_con
     double* s_wb = s_wa + A;
     double* per_warp = s_wb + B;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* s_resp = per_warp + (size_t)warp * (2 * (size_t)n + (size_t)((A + 1) / 2));
+    double* s_resp = per_warp + (size_t)warp * (2 * (size_t)n + 32 + (size_t)((A + 1) / 2));
     unsigned* s_hi = (unsigned*)(s_resp + n);
     unsigned* s_lo = s_hi + n;
-    int* s_rowv = (int*)(s_lo + n);
+    unsigned long long* s_cand = (unsigned long long*)(s_lo + n);        // 32 compacted keys
+    int* s_rowv = (int*)(s_cand + 32);
 
     const int az_index = blockIdx.y;
     const int gate = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -380,7 +438,7 @@ __global__ void __launch_bounds__(kVvpMaxWarps * 32) vvp_kernel(const __grid_con
                         s_lo[s] = (unsigned)q;
                     }
                     __syncwarp();
-                    const double med = warp_median(s_hi, s_lo, n, (int)nfit, lane);
+                    const double med = warp_median(s_hi, s_lo, n, (int)nfit, s_cand, lane);
                     __syncwarp();
                     for (int s = lane; s < n; s += 32) {
                         const unsigned h = s_hi[s];
@@ -390,7 +448,7 @@ __global__ void __launch_bounds__(kVvpMaxWarps * 32) vvp_kernel(const __grid_con
                         s_lo[s] = (unsigned)q;
                     }
                     __syncwarp();
-                    const double scale = 1.4826 * warp_median(s_hi, s_lo, n, (int)nfit, lane);
+                    const double scale = 1.4826 * warp_median(s_hi, s_lo, n, (int)nfit, s_cand, lane);
                     __syncwarp();
                     if (!isfinite(scale) || scale < 1.0e-6) break;
                     double nc[3], ncond;
