@@ -393,6 +393,65 @@ def bench_extra_config(cid, args, torch, dev, steps=10):
             "roofline": {"achieved": balg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": balg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": int(balg)}}
 
+def bench_next_rows(args):
+    """SURVEY §8(f) rows built beyond the gridding path, timed through their host-facing calls (host buffers,
+    copies included): f3 vertical section through the C1-C3 volume, f4 local VVP on one sweep.  The VVP line
+    carries a CPU figure from the oracle (= the reference's algorithm, NumPy + LAPACK per window) on a bounded
+    sample of windows."""
+    import time
+
+    from pycwr_b200 import section, synth, wind
+    out = {}
+    vol = synth.make_volume(synth.BASE_SEED + 7, style="storm")
+    sweeps = [(a, r, np.where(v == FILL, np.nan, v))
+              for a, r, v in zip(vol["vol_azimuth"], vol["vol_range"], vol["vol_value"]["dBZ"])]
+    sv = section.SectionVolume(sweeps, vol["fix_elevation"])
+    x, y, _ = section._build_section_line((-150e3, -40e3), (150e3, 90e3), 250.0)
+    for _ in range(3):
+        sv.sample_line(x, y, vol["radar_height"])
+    t0 = time.perf_counter()
+    reps = 50
+    for _ in range(reps):
+        vals = sv.sample_line(x, y, vol["radar_height"])[0]
+    dt = (time.perf_counter() - t0) / reps
+    sv.close()
+    out["f3_section"] = {"workload": "section of %d points through %d sweeps (366 x 1840), volume resident" % (x.size, len(sweeps)),
+                         "ms_per_call": dt * 1e3, "samples_per_s": vals.size / dt, "kernel": "pcg::section_kernel"}
+    # f4: a 360 x 920 velocity sweep, the reference's default 91 x 9 window
+    rng = np.random.default_rng(33)
+    naz, nrange = 360, 920
+    az = np.sort(np.mod(np.arange(naz) * 1.0 + rng.uniform(-0.3, 0.3, naz), 360.0))
+    el = np.full(naz, 1.45)
+    a = np.deg2rad(az)[:, None]
+    g = np.arange(nrange)[None, :]
+    vr = ((9.0 + 0.01 * g) * np.sin(a) + (-4.0 + 0.02 * g) * np.cos(a)) * np.cos(np.deg2rad(1.45)) \
+        + rng.normal(0.0, 0.6, (naz, nrange))
+    bad = rng.random(vr.shape) < 0.05
+    vr[bad] += rng.uniform(8.0, 25.0, int(bad.sum()))
+    vr[rng.random(vr.shape) < 0.2] = FILL
+    for _ in range(2):
+        res = wind._run_local_vvp(az, el, vr, 91, 9)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        res = wind._run_local_vvp(az, el, vr, 91, 9)
+    dt = (time.perf_counter() - t0) / reps
+    windows = naz * (nrange - 8)
+    line = {"workload": "local VVP, %d x %d sweep, 91 x 9 window" % (naz, nrange), "ms_per_sweep": dt * 1e3,
+            "windows_per_s": windows / dt, "fits": int(np.isfinite(res["u"]).sum()), "kernel": "pcg::vvp_kernel"}
+    if not args.no_cpu:
+        from oracle import vvp_oracle
+        t0 = time.perf_counter()
+        sub = vvp_oracle.run_local_vvp(az, el, vr[:, :24], 91, 9)          # 16 analysed gates x 360 rays
+        cdt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": naz * 16 / cdt, "unit": "windows/s", "cores": 1, "kind": "port",
+                                "sample": "gates 4..19 of every ray (%d windows)" % (naz * 16)}
+        m = np.isfinite(sub["u"][:, 4:20])
+        line["max_abs_diff_u_vs_oracle"] = float(np.max(np.abs(sub["u"][:, 4:20][m] - res["u"][:, 4:20][m]))) if m.any() else None
+    out["f4_local_vvp"] = line
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # product arm
 # --------------------------------------------------------------------------------------------
@@ -550,6 +609,7 @@ def run_product(args):
     others = None
     if args.other_configs and rank == 0 and world == 1:
         others = [bench_extra_config(c, args, torch, dev) for c in (1, 2) if WORKLOADS[args.workload] != c]
+    next_rows = bench_next_rows(args) if args.other_configs and rank == 0 and world == 1 else None
 
     if rank != 0:
         if dist is not None:
@@ -598,6 +658,8 @@ def run_product(args):
         line["network"] = net
     if others:
         line["other_configs"] = others
+    if next_rows:
+        line["next_rows"] = next_rows
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
