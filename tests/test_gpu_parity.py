@@ -408,3 +408,63 @@ def test_fused_sqrt_is_the_ieee_sqrt():
     print("fused sqrt mismatches: %d of %d, worst |y*r-1| = %.3e" % (bad.value, a.size, worst.value))
     assert bad.value == 0
     assert worst.value < 1e-15
+
+
+def test_repeated_calls_do_not_grow_device_memory():
+    """Per-call volume arenas and threshold tables come from the library's device pool: a service that grids
+    volume after volume (different shapes included) must not accumulate device memory or change its answers."""
+    torch = pytest.importorskip("torch")
+    cfg = synth.config(3, style="stress", scale=0.05)
+    va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
+    gx, gy, lv = cfg["GridX"], cfg["GridY"], cfg["levels"]
+    first = G.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, "hybrid")
+
+    def one_round(i):
+        n = 5 + (i % 4)                                   # sweep count and grid shape vary from call to call
+        out = G.get_CAPPI_3d(va[:n], vr[:n], fe[:n], vv[:n], h, gx[: 20 + i % 7], gy[: 20 + i % 7], lv[:: 1 + i % 3],
+                             FILL, None, BLINDS[i % len(BLINDS)])
+        G.get_CR_xy(va[:n], vr[:n], fe[:n], vv[:n], h, gx, gy, FILL)
+        return out
+
+    for i in range(8):
+        one_round(i)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for i in range(60):
+        one_round(i)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, "device memory grew by %.1f MB over 60 calls" % ((free0 - free1) / 2 ** 20)
+    again = G.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, "hybrid")
+    assert np.array_equal(first, again)
+
+
+def test_concurrent_callers_get_their_own_answers():
+    """ctypes releases the GIL: several host threads may be inside the library at once (a product server
+    gridding different radars).  Entry points serialise on the library's lock; results must not mix."""
+    import threading
+    cfgs = [synth.config(3, style="stress", scale=0.03), synth.config(2, style="stress", scale=0.05)]
+    jobs = []
+    for i, cfg in enumerate(cfgs * 2):
+        va, vr, fe, vv, h = synth.vol_tuple(cfg["volume"])
+        jobs.append((va, vr, fe, vv, h, cfg["GridX"], cfg["GridY"], cfg["levels"], BLINDS[(i + 3) % len(BLINDS)]))
+    want = [G.get_CAPPI_3d(*j[:8], FILL, None, j[8]) for j in jobs]
+    got = [[None] * 4 for _ in jobs]
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(4):
+                got[t][rep] = G.get_CAPPI_3d(*jobs[t][:8], FILL, None, jobs[t][8])
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for t in range(len(jobs)):
+        for rep in range(4):
+            assert np.array_equal(got[t][rep], want[t]), "thread %d call %d" % (t, rep)
