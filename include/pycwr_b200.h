@@ -80,6 +80,18 @@ int64_t pcg_launch_count(void);
 int pcg_volume_create(int ne, const int *naz, const int *ng, const double *const *az,
                       const double *const *rng, int nfield, const double *const *const *val,
                       const double *fix_elev, double fill, int value_dtype, pcg_volume **out);
+
+/* The packer itself on the device (PRD.get_vol_data / _extract_sweep_volume,
+ * `pycwr/core/NRadar.py:665-712,1931-1961`): same result as pcg_volume_create, but the inputs are the sweeps
+ * as the file reader left them — az[s] and the rows of val[f][s] in SCAN order, NaN for missing.  The host
+ * supplies ray_order[s] = argsort(az[s]) (naz[s] ints, `:705-707`) and val_ld[s] = elements between
+ * consecutive rays of val[f][s] (>= ng[s]; NULL = ng[s]): ng[s] may be smaller than the stored ray length,
+ * which is the max_range_km clip of `:655-663` (a prefix of every ray).  The row gather, the clip and the
+ * NaN -> fill substitution (`:1956`) run inside the pack kernels; sweeps are passed in fixed-angle order. */
+int pcg_volume_create_raw(int ne, const int *naz, const int *ng, const double *const *az,
+                          const double *const *rng, int nfield, const double *const *const *val,
+                          const long long *val_ld, const int *const *ray_order, const double *fix_elev,
+                          double fill, int value_dtype, pcg_volume **out);
 int pcg_volume_destroy(pcg_volume *vol);
 int pcg_volume_info(const pcg_volume *vol, int *ne, int *nfield, int *value_dtype,
                     size_t *device_bytes);

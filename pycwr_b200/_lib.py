@@ -34,6 +34,8 @@ SIGNATURES = {
     "pcg_volume_create": (_i, [_i, c_int_p, c_int_p, c_double_pp, c_double_pp, _i, c_double_ppp,
                                c_double_p, _d, _i, c_void_pp]),
     "pcg_volume_destroy": (_i, [_vp]),
+    "pcg_volume_create_raw": (_i, [_i, c_int_p, c_int_p, c_double_pp, c_double_pp, _i, c_double_ppp, _vp,
+                                   ctypes.POINTER(c_int_p), c_double_p, _d, _i, ctypes.POINTER(ctypes.c_void_p)]),
     "pcg_volume_info": (_i, [_vp, c_int_p, c_int_p, c_int_p, ctypes.POINTER(ctypes.c_size_t)]),
     "pcg_get_cappi3d": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, c_double_p, _i, _d, _i, _d, _vp, _vp]),
     "pcg_get_cr": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, _d, _vp]),

@@ -718,9 +718,17 @@ int pcg_host_free(void* ptr) {
 
 int64_t pcg_launch_count(void) { return (int64_t)g_launches.load(); }
 
-int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const* az,
-                      const double* const* rng, int nfield, const double* const* const* val,
-                      const double* fix_elev, double fill, int value_dtype, pcg_volume** out) {
+}  // extern "C"
+
+// Shared body of pcg_volume_create / pcg_volume_create_raw.  `az` is sorted; when `ray_order` is given the
+// moments are still in scan order (row i of the packed sweep is raw row ray_order[s][i]) with NaN for
+// missing, `val_ld[s]` elements between consecutive raw rows: the permutation, the range clip and the
+// NaN -> fill substitution of the reference's packer happen inside the pack kernels.
+static int volume_create_impl(int ne, const int* naz, const int* ng, const double* const* az,
+                              const double* const* rng, int nfield, const double* const* const* val,
+                              const long long* val_ld, const int* const* ray_order,
+                              const double* fix_elev, double fill, int value_dtype, pcg_volume** out) {
+    const bool raw = ray_order != nullptr;
     if (!out) return fail(PCG_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (ne < 0 || ne > kMaxSweeps) return fail(PCG_ERR_ARG, "ne must be in [0, %d]", kMaxSweeps);
@@ -846,10 +854,17 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         VOL_TRY(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
     double* tmp = nullptr;
-    if (packed) {
+    int* d_order = nullptr;
+    if (packed || raw) {
         // one float64 staging tile; uploads and pack kernels are ordered by the stream
         if (g_scratch[S_TMP0].ensure(max_sweep * sizeof(double)) != PCG_OK) { cleanup(); return PCG_ERR_NOMEM; }
         tmp = (double*)g_scratch[S_TMP0].ptr;
+    }
+    if (raw) {
+        size_t max_naz = 1;
+        for (int s = 0; s < ne; ++s) if ((size_t)naz[s] > max_naz) max_naz = (size_t)naz[s];
+        if (g_scratch[S_TMP2].ensure(max_naz * sizeof(int)) != PCG_OK) { cleanup(); return PCG_ERR_NOMEM; }
+        d_order = (int*)g_scratch[S_TMP2].ptr;
     }
     for (int s = 0; s < ne; ++s) {
         const SweepDesc& d = v->sweeps[s];
@@ -866,12 +881,28 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
         }
         const size_t cnt = (size_t)d.naz * (size_t)d.ng;
         if (!cnt) continue;
+        if (raw) VOL_TRY(cudaMemcpyAsync(d_order, ray_order[s], (size_t)d.naz * sizeof(int), cudaMemcpyHostToDevice, st));
         for (int f = 0; f < nfield; ++f) {
-            if (packed) {
+            if (raw) {
+                // scan-order rows (clipped to the first ng gates of each ray) -> staging tile -> packed layout
+                const size_t ld = val_ld ? (size_t)val_ld[s] : (size_t)d.ng;
+                VOL_TRY(cudaMemcpy2DAsync(tmp, (size_t)d.ng * sizeof(double), val[f][s], ld * sizeof(double),
+                                          (size_t)d.ng * sizeof(double), (size_t)d.naz, cudaMemcpyHostToDevice, st));
+                const unsigned blocks = (unsigned)((cnt + 255) / 256 < 148 * 16 ? (cnt + 255) / 256 : 148 * 16);
+                if (packed)
+                    pack_quads_kernel<<<blocks, 256, 0, st>>>(tmp, (float4*)v->d_val[f] + d.val_off, d.naz, d.ng,
+                                                              fill, (float)fill, d_order, 1);
+                else
+                    permute_rows_kernel<<<blocks, 256, 0, st>>>(tmp, (double*)v->d_val[f] + d.val_off, d.naz, d.ng,
+                                                                fill, d_order);
+                minmax_kernel<<<blocks, 256, 0, st>>>(tmp, cnt, fill, d_mm + 3 * f);
+                g_launches.fetch_add(2);
+                VOL_TRY(cudaGetLastError());
+            } else if (packed) {
                 VOL_TRY(cudaMemcpyAsync(tmp, val[f][s], cnt * sizeof(double), cudaMemcpyHostToDevice, st));
                 const unsigned blocks = (unsigned)((cnt + 255) / 256 < 148 * 16 ? (cnt + 255) / 256 : 148 * 16);
                 pack_quads_kernel<<<blocks, 256, 0, st>>>(tmp, (float4*)v->d_val[f] + d.val_off, d.naz, d.ng,
-                                                          fill, (float)fill);
+                                                          fill, (float)fill, nullptr, 0);
                 minmax_kernel<<<blocks, 256, 0, st>>>(tmp, cnt, fill, d_mm + 3 * f);
                 g_launches.fetch_add(2);
                 VOL_TRY(cudaGetLastError());
@@ -1002,6 +1033,41 @@ int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const
     }
     *out = v;
     return PCG_OK;
+}
+
+extern "C" {
+
+int pcg_volume_create(int ne, const int* naz, const int* ng, const double* const* az,
+                      const double* const* rng, int nfield, const double* const* const* val,
+                      const double* fix_elev, double fill, int value_dtype, pcg_volume** out) {
+    return volume_create_impl(ne, naz, ng, az, rng, nfield, val, nullptr, nullptr, fix_elev, fill, value_dtype, out);
+}
+
+int pcg_volume_create_raw(int ne, const int* naz, const int* ng, const double* const* az,
+                          const double* const* rng, int nfield, const double* const* const* val,
+                          const long long* val_ld, const int* const* ray_order, const double* fix_elev,
+                          double fill, int value_dtype, pcg_volume** out) {
+    if (!out) return fail(PCG_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (ne < 0 || ne > kMaxSweeps) return fail(PCG_ERR_ARG, "ne must be in [0, %d]", kMaxSweeps);
+    if (ne > 0 && (!naz || !ng || !az || !ray_order)) return fail(PCG_ERR_ARG, "NULL table pointer");
+    // the azimuth tables in packed order (host: a few hundred values per sweep)
+    std::vector<std::vector<double>> sorted(ne > 0 ? ne : 1);
+    std::vector<const double*> azp(ne > 0 ? ne : 1, nullptr);
+    for (int s = 0; s < ne; ++s) {
+        if (naz[s] < 0 || ng[s] < 0) return fail(PCG_ERR_ARG, "negative table length in sweep %d", s);
+        if (naz[s] > 0 && (!az[s] || !ray_order[s])) return fail(PCG_ERR_ARG, "NULL azimuth / ray order (sweep %d)", s);
+        if (val_ld && val_ld[s] < ng[s]) return fail(PCG_ERR_ARG, "val_ld[%d] is smaller than ng[%d]", s, s);
+        sorted[s].resize(naz[s]);
+        for (int i = 0; i < naz[s]; ++i) {
+            const int r = ray_order[s][i];
+            if (r < 0 || r >= naz[s]) return fail(PCG_ERR_ARG, "ray_order[%d][%d] = %d out of range", s, i, r);
+            sorted[s][i] = az[s][r];
+        }
+        azp[s] = sorted[s].data();
+    }
+    return volume_create_impl(ne, naz, ng, azp.data(), rng, nfield, val, val_ld, ray_order, fix_elev, fill,
+                              value_dtype, out);
 }
 
 int pcg_volume_destroy(pcg_volume* v) {

@@ -206,6 +206,19 @@ def _prd_volume(prd, field_name, fillvalue, range_mode, max_range_km):
     return vol_azimuth, vol_range, np.asarray(fix_elevation, dtype=np.float64), vol_value, float(radar_height), range_mode
 
 
+def _prd_device_volume(prd, field_name, fillvalue, range_mode, max_range_km):
+    """(DeviceVolume, radar height, range mode used, owned): the PRD's cached device volume when it offers one
+    (``get_device_volume``: packed by the GPU from the raw sweeps), else a fresh upload of ``prd.vol``."""
+    if hasattr(prd, "get_device_volume"):
+        if hasattr(prd, "_resolve_field_range_mode"):
+            range_mode = prd._resolve_field_range_mode(field_name, range_mode=range_mode)
+        dv = prd.get_device_volume(field_name=field_name, fillvalue=fillvalue, range_mode=range_mode,
+                                   max_range_km=max_range_km)
+        return dv, float(prd.radar_height), range_mode, False
+    va, vr, fe, vv, h, used = _prd_volume(prd, field_name, fillvalue, range_mode, max_range_km)
+    return DeviceVolume(va, vr, fe, vv, fillvalue=fillvalue, value_dtype="f32"), h, used, True
+
+
 def _sanity_filter(grid_value, vol_value, fillvalue):
     """RadarInterp.py:1003-1014 on the host, for volumes the fused kernel cannot take."""
     lo, hi = np.inf, -np.inf
@@ -493,13 +506,14 @@ def run_radar_network_3d(radars, radar_lonlat, lon_min, lon_max, lat_min, lat_ma
     product_volume = None
     for field in field_names:
         mode = range_modes.get(field, "native" if field == "dBZ" else None)   # RadarInterp.py:271-272
-        vols, heights, bws, actual = [], [], [], {}
+        vols, heights, bws, actual, owned = [], [], [], {}, []
         for i, prd in enumerate(radars):
-            va, vr, fe, vv, h, used = _prd_volume(prd, field, fillvalue, mode, max_range_km)
-            vols.append(DeviceVolume(va, vr, fe, vv, fillvalue=fillvalue, value_dtype="f32"))
+            dv, h, used, mine = _prd_device_volume(prd, field, fillvalue, mode, max_range_km)
+            vols.append(dv)
+            owned.append(mine)
             heights.append(h)
-            bws.append(_get_sweep_beam_widths(prd, len(fe)))
-            actual[str(i)] = max(float(r[-1]) for r in vr) / 1000.0
+            bws.append(_get_sweep_beam_widths(prd, dv.ne))
+            actual[str(i)] = float(np.nanmax(dv.last_gate)) / 1000.0
             range_modes[field] = used
         try:
             is_ref = field == "dBZ"
@@ -530,8 +544,9 @@ def run_radar_network_3d(radars, radar_lonlat, lon_min, lon_max, lat_min, lat_ma
                     product_volume = np.asarray(network_compose(vols, sites, heights, grid_x, grid_y, product_levels,
                                                                 beam_widths=bws, outputs=(), **kw)["composite"])
         finally:
-            for v in vols:
-                v.close()
+            for v, mine in zip(vols, owned):
+                if mine:
+                    v.close()
     if product_volume is not None and ("VIL" in output_products or "ET" in output_products):
         from .products import column_products
         prod = column_products(product_volume, product_levels, fillvalue=fillvalue,

@@ -69,6 +69,7 @@ class ArrayPRD(object):
         self.scan_info["latitude"] = _Values(np.float64(lat))
         self.product = SimpleDataset({})
         self._vol_cache = {}
+        self._dev_cache = {}
         self.vol = None
 
     @staticmethod
@@ -89,6 +90,20 @@ class ArrayPRD(object):
                                                self.lon, self.lat, fillvalue, max_range_km)
         self.vol = self._vol_cache[key]
         return self.vol
+
+    def get_device_volume(self, field_name="dBZ", fillvalue=FILL, range_mode=None, max_range_km=None,
+                          value_dtype="f32"):
+        """The device form of ``get_vol_data``: the sweeps go to the GPU as stored (scan order,
+        NaN) and are sorted / clipped / fill-marked by the pack kernels; cached per key like ``_vol_cache``."""
+        if field_name not in self.fields:
+            raise KeyError(field_name)
+        key = (field_name, float(fillvalue), range_mode, max_range_km, value_dtype)
+        if key not in self._dev_cache:
+            from .runtime import DeviceVolume
+            self._dev_cache[key] = DeviceVolume.from_sweeps(self.fields[field_name], self.fix_elevation,
+                                                            fillvalue=fillvalue, value_dtype=value_dtype,
+                                                            max_range_km=max_range_km)
+        return self._dev_cache[key]
 
     # vertical sections (SURVEY §8 f3): NRadar.py:1008-1121,1123-1200 on the GPU
     def extract_section(self, start, end, field_name="dBZ", point_units="km", interpolation="linear",
@@ -173,6 +188,9 @@ _Y_ATTRS = {"units": "meters", "long_name": "north_distance_from_radar", "axis":
 
 def _volume_of(prd, range_mode, field_name="dBZ", fillvalue=FILL):
     range_mode = prd._resolve_field_range_mode(field_name, range_mode=range_mode)
+    if hasattr(prd, "get_device_volume"):       # packed on the device, resident across products
+        dv = prd.get_device_volume(field_name=field_name, fillvalue=fillvalue, range_mode=range_mode)
+        return range_mode, None, None, None, dv, float(prd.radar_height)
     prd.get_vol_data(field_name=field_name, fillvalue=fillvalue, range_mode=range_mode)
     return (range_mode,) + tuple(prd.vol[:5])
 

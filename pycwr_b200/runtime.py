@@ -82,9 +82,13 @@ class DeviceVolume:
             ctypes.cast(azp, _lib.c_double_pp), ctypes.cast(rgp, _lib.c_double_pp), len(fld),
             ctypes.cast(fpp, _lib.c_double_ppp), fix.ctypes.data_as(_lib.c_double_p), float(fillvalue),
             dtype_code, ctypes.byref(handle)))
+        self._adopt(handle, naz, ng, fix, rg, fillvalue, len(fld))
+
+    def _adopt(self, handle, naz, ng, fix, rg, fillvalue, nfield):
+        lib = _lib.load()
         self.handle = handle
-        self.ne = ne
-        self.nfield = len(fld)
+        self.ne = int(fix.shape[0])
+        self.nfield = int(nfield)
         self.fillvalue = float(fillvalue)
         used = ctypes.c_int(0)
         _lib.check(lib.pcg_volume_info(handle, None, None, ctypes.byref(used), None))
@@ -97,6 +101,85 @@ class DeviceVolume:
         self.nvalues = int(sum(int(a) * int(b) for a, b in zip(naz, ng)))
         self.table_bytes = int(8 * (naz.sum() + ng.sum()))
         self._finalizer = weakref.finalize(self, lib.pcg_volume_destroy, handle)
+
+    @classmethod
+    def from_sweeps(cls, sweeps, fix_elevation, fillvalue=-999.0, value_dtype="f32", max_range_km=None):
+        """Pack sweeps as the file reader left them — ``[(azimuth, ranges, values), ...]`` in scan order, rays
+        unsorted, NaN for missing; ``values`` one ``(naz, ng)`` array or a list of them (several moments) —
+        the work of ``PRD.get_vol_data`` / ``_extract_sweep_volume`` (``pycwr/core/NRadar.py:665-712,1931-1961``)
+        without its host passes: the host only argsorts the azimuths; the row gather, the ``max_range_km`` clip
+        (``:655-663``) and NaN -> ``fillvalue`` run inside the device pack kernels (``pcg_volume_create_raw``)."""
+        lib = _lib.load()
+        fix_all = _f64_1d(fix_elevation, "fix_elevation")
+        if len(sweeps) != fix_all.shape[0]:
+            raise ValueError("one fixed elevation per sweep is required")
+        order = np.argsort(fix_all)                                   # _fixed_angle_sort_index
+        fix = np.ascontiguousarray(fix_all[order])
+        ne = int(fix.shape[0])
+        az, rg, rays, lds, keep_alive = [], [], [], [], []
+        nfield, vals = None, None
+        for s in order:
+            a, r, v = sweeps[int(s)]
+            a = _f64_1d(a, "azimuth")
+            r = _f64_1d(r, "ranges")
+            moments = list(v) if isinstance(v, (list, tuple)) else [v]
+            if nfield is None:
+                nfield, vals = len(moments), [[] for _ in moments]
+            if len(moments) != nfield:
+                raise ValueError("every sweep must carry the same moments")
+            n_used = r.shape[0]
+            mask = None
+            if max_range_km is not None:                              # NRadar.py:655-663
+                keep = r <= float(max_range_km) * 1000.0
+                k = int(keep.sum())
+                if k == 0:
+                    n_used = min(1, r.shape[0])
+                elif keep[:k].all():
+                    n_used = k                                        # a prefix of every ray: no copy
+                else:
+                    mask = keep
+            if mask is not None:
+                r = np.ascontiguousarray(r[mask])
+                n_used = r.shape[0]
+            ld = None
+            for f, m in enumerate(moments):
+                m = np.asarray(m)
+                if m.dtype != np.float64 or m.ndim != 2 or not m.flags.c_contiguous:
+                    m = np.ascontiguousarray(m, dtype=np.float64)
+                    if m.ndim != 2:
+                        raise ValueError("Sweep field must be 2-D for Cartesian gridding.")
+                if mask is not None:
+                    m = np.ascontiguousarray(m[:, mask])
+                if m.shape[0] < a.shape[0] or m.shape[1] < n_used:
+                    raise IndexError("sweep %d: value array smaller than its azimuth/range tables" % int(s))
+                ld = m.shape[1] if ld is None else ld
+                if m.shape[1] != ld:
+                    raise ValueError("moments of one sweep must share their shape")
+                vals[f].append(m)
+            az.append(a)
+            rg.append(np.ascontiguousarray(r[:n_used]))
+            rays.append(np.ascontiguousarray(np.argsort(a), dtype=np.int32))
+            lds.append(ld if ld is not None else n_used)
+        naz = np.array([a.shape[0] for a in az], dtype=np.int32)
+        ng = np.array([r.shape[0] for r in rg], dtype=np.int32)
+        n1 = max(ne, 1)
+        azp = (_lib.c_double_p * n1)(*[a.ctypes.data_as(_lib.c_double_p) for a in az])
+        rgp = (_lib.c_double_p * n1)(*[a.ctypes.data_as(_lib.c_double_p) for a in rg])
+        orp = (_lib.c_int_p * n1)(*[a.ctypes.data_as(_lib.c_int_p) for a in rays])
+        ldv = np.array(lds if lds else [0], dtype=np.int64)
+        fld = [(_lib.c_double_p * n1)(*[a.ctypes.data_as(_lib.c_double_p) for a in f]) for f in (vals or [[]])]
+        fpp = (_lib.c_double_pp * len(fld))(*[ctypes.cast(x, _lib.c_double_pp) for x in fld])
+        handle = ctypes.c_void_p()
+        dtype_code = {"f64": _lib.VALUE_F64, "f32": _lib.VALUE_F32}[value_dtype]
+        _lib.check(lib.pcg_volume_create_raw(
+            ne, naz.ctypes.data_as(_lib.c_int_p), ng.ctypes.data_as(_lib.c_int_p),
+            ctypes.cast(azp, _lib.c_double_pp), ctypes.cast(rgp, _lib.c_double_pp), len(fld),
+            ctypes.cast(fpp, _lib.c_double_ppp), ldv.ctypes.data, ctypes.cast(orp, ctypes.POINTER(_lib.c_int_p)),
+            fix.ctypes.data_as(_lib.c_double_p), float(fillvalue), dtype_code, ctypes.byref(handle)))
+        self = cls.__new__(cls)
+        self._adopt(handle, naz, ng, fix, rg, fillvalue, len(fld))
+        self.sweep_order = order
+        return self
 
     def close(self):
         self._finalizer()
