@@ -112,6 +112,18 @@ int pcg_get_cr(const pcg_volume *vol, double radar_height, double effective_eart
                const double *grid_x, const double *grid_y, int nx, int ny, double fill,
                double *out);
 
+/* Same calls with the missing-value marker of the RESULT chosen by the caller: cells the gridding leaves at
+ * `fill` are stored as `out_missing` (typically NaN) before the result is copied back — the
+ * `np.where(GridV == fillvalue, np.nan, GridV)` pass of the product wrappers (`pycwr/core/NRadar.py:1339,
+ * 1374-1392,1420-1437`) without a host sweep over the volume.  out_missing == fill is the plain call. */
+int pcg_get_cappi3d_ex(const pcg_volume *vol, double radar_height, double effective_earth_radius,
+                       const double *grid_x, const double *grid_y, int nx, int ny,
+                       const double *level_heights, int nz, double fill, int blind_code,
+                       double beam_width_deg, double out_missing, double *out, int32_t *index_out);
+int pcg_get_cr_ex(const pcg_volume *vol, double radar_height, double effective_earth_radius,
+                  const double *grid_x, const double *grid_y, int nx, int ny, double fill, double out_missing,
+                  double *out);
+
 /* ppi_to_grid (`RadarGridC.pyx:303-352`): sweep `sweep` of the packed volume gridded at
  * elevation `elevation_deg`.  out: [nx*ny]; index_out optional [nx*ny][PCG_IDX_STRIDE]. */
 int pcg_ppi_to_grid(const pcg_volume *vol, int sweep, double elevation_deg, double radar_height,

@@ -239,8 +239,10 @@ def ppi_to_grid(azimuth, ranges, elevation, mat_ppi, radar_height, GridX, GridY,
 
 
 def get_CR_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height, GridX, GridY, fillvalue,
-              effective_earth_radius=None):
-    """Composite reflectivity: max over sweeps, fill ignored (RadarGridC.pyx:596-624)."""
+              effective_earth_radius=None, *, missing=None):
+    """Composite reflectivity: max over sweeps, fill ignored (RadarGridC.pyx:596-624).
+    ``missing`` (extension, keyword-only): value stored in empty cells instead of ``fillvalue`` —
+    ``np.nan`` fuses the wrappers' ``np.where(GridV == fillvalue, np.nan, GridV)`` into the device call."""
     gx = _f64_2d(GridX, "GridX")
     gy = _f64_2d(GridY, "GridY")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
@@ -250,12 +252,12 @@ def get_CR_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height, Gr
     out = _new_output((nx, ny))
     try:
         if vol.ne == 0:
-            out.fill(fillvalue)
+            out.fill(fillvalue if missing is None else missing)
         else:
             for _ in range(2):
-                rc = _lib.check(_lib.load().pcg_get_cr(
+                rc = _lib.check(_lib.load().pcg_get_cr_ex(
                     vol.handle, float(radar_height), radius, _lib.as_ptr(gx), _lib.as_ptr(gy), nx, ny,
-                    float(fillvalue), _lib.as_ptr(out)))
+                    float(fillvalue), float(fillvalue if missing is None else missing), _lib.as_ptr(out)))
                 redo = _redo_in_f64(rc, vol, owned, pack_args)
                 if redo is None:
                     break
@@ -267,7 +269,7 @@ def get_CR_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height, Gr
 
 
 def _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code, beam_width_deg,
-           return_index):
+           return_index, missing=None):
     nx, ny = gx.shape[0], gx.shape[1]
     nz = int(levels.shape[0])
     shape = (nz, nx, ny) if vol.nfield == 1 else (vol.nfield, nz, nx, ny)
@@ -275,17 +277,18 @@ def _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code, bea
     idx = np.empty((nz, nx, ny, _lib.IDX_STRIDE), dtype=np.int32) if return_index else None
     rc = _lib.PCG_OK
     if out.size:
-        rc = _lib.check(_lib.load().pcg_get_cappi3d(
+        rc = _lib.check(_lib.load().pcg_get_cappi3d_ex(
             vol.handle, float(radar_height), radius, _lib.as_ptr(gx), _lib.as_ptr(gy), nx, ny,
             levels.ctypes.data_as(_lib.c_double_p), nz, float(fillvalue), blind_code,
-            float(beam_width_deg), _lib.as_ptr(out), _lib.as_ptr(idx) if idx is not None else None))
+            float(beam_width_deg), float(fillvalue if missing is None else missing), _lib.as_ptr(out),
+            _lib.as_ptr(idx) if idx is not None else None))
     return out, idx, rc
 
 
 def get_CAPPI_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height, GridX, GridY,
                  level_height, fillvalue, effective_earth_radius=None, blind_method="mask",
-                 beam_width_deg=1.0, return_index=False):
-    """One CAPPI level (RadarGridC.pyx:356-477)."""
+                 beam_width_deg=1.0, return_index=False, *, missing=None):
+    """One CAPPI level (RadarGridC.pyx:356-477); ``missing``: see ``get_CR_xy``."""
     gx = _f64_2d(GridX, "GridX")
     gy = _f64_2d(GridY, "GridY")
     radius = _resolve_effective_earth_radius(effective_earth_radius)
@@ -296,7 +299,7 @@ def get_CAPPI_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height,
         levels = np.array([float(level_height)], dtype=np.float64)
         for _ in range(2):
             out, idx, rc = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code,
-                                  float(beam_width_deg), return_index)
+                                  float(beam_width_deg), return_index, missing)
             redo = _redo_in_f64(rc, vol, owned, pack_args)
             if redo is None:
                 break
@@ -310,9 +313,9 @@ def get_CAPPI_xy(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height,
 
 def get_CAPPI_3d(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height, GridX, GridY,
                  level_heights, fillvalue, effective_earth_radius=None, blind_method="mask",
-                 return_index=False):
+                 return_index=False, *, missing=None):
     """3-D CAPPI volume, shape (nz, nx, ny) (RadarGridC.pyx:485-521; beam width is not forwarded
-    by the reference, so the single-sweep gate always uses 1.0 degree here too)."""
+    by the reference, so the single-sweep gate always uses 1.0 degree here too); ``missing``: see ``get_CR_xy``."""
     gx = _f64_2d(GridX, "GridX")
     gy = _f64_2d(GridY, "GridY")
     levels = _f64_1d(level_heights, "level_heights")
@@ -323,7 +326,7 @@ def get_CAPPI_3d(vol_azimuth, vol_range, fix_elevation, vol_value, radar_height,
     try:
         for _ in range(2):
             out, idx, rc = _cappi(vol, radar_height, gx, gy, levels, fillvalue, radius, blind_code, 1.0,
-                                  return_index)
+                                  return_index, missing)
             redo = _redo_in_f64(rc, vol, owned, pack_args)
             if redo is None:
                 break

@@ -39,6 +39,8 @@ SIGNATURES = {
     "pcg_volume_info": (_i, [_vp, c_int_p, c_int_p, c_int_p, ctypes.POINTER(ctypes.c_size_t)]),
     "pcg_get_cappi3d": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, c_double_p, _i, _d, _i, _d, _vp, _vp]),
     "pcg_get_cr": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, _d, _vp]),
+    "pcg_get_cappi3d_ex": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, c_double_p, _i, _d, _i, _d, _d, _vp, _vp]),
+    "pcg_get_cr_ex": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, _d, _d, _vp]),
     "pcg_ppi_to_grid": (_i, [_vp, _i, _d, _d, _d, _vp, _vp, _i, _i, _d, _i, _vp, _vp]),
     "pcg_get_mosaic_cappi3d": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p,
                                     _vp, _vp, _i, _i, c_double_p, _i, _d, _vp]),

@@ -685,6 +685,22 @@ int enqueue_cr(const pcg_volume* vol, double h, double Re, const double* d_gx, c
 
 }  // namespace
 
+// the product wrappers' `np.where(grid == fillvalue, np.nan, grid)` (NRadar.py:1339,1392,...) on the device, before
+// the result crosses PCIe: a host pass over a 461 MB volume costs more than the whole gridding call
+__global__ void relabel_kernel(double* __restrict__ data, size_t n, double from, double to) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (data[i] == from) data[i] = to;
+}
+
+static int relabel_missing(double* d_data, size_t n, double fill, double out_missing, cudaStream_t st) {
+    if (n == 0 || memcmp(&fill, &out_missing, sizeof(double)) == 0) return PCG_OK;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    relabel_kernel<<<blocks, 256, 0, st>>>(d_data, n, fill, out_missing);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return PCG_OK;
+}
+
 extern "C" {
 
 const char* pcg_last_error(void) { return g_err; }
@@ -1127,6 +1143,14 @@ int pcg_get_cappi3d(const pcg_volume* vol, double radar_height, double effective
                     const double* grid_x, const double* grid_y, int nx, int ny,
                     const double* level_heights, int nz, double fill, int blind_code,
                     double beam_width_deg, double* out, int32_t* index_out) {
+    return pcg_get_cappi3d_ex(vol, radar_height, effective_earth_radius, grid_x, grid_y, nx, ny, level_heights, nz,
+                              fill, blind_code, beam_width_deg, fill, out, index_out);
+}
+
+int pcg_get_cappi3d_ex(const pcg_volume* vol, double radar_height, double effective_earth_radius,
+                       const double* grid_x, const double* grid_y, int nx, int ny,
+                       const double* level_heights, int nz, double fill, int blind_code,
+                       double beam_width_deg, double out_missing, double* out, int32_t* index_out) {
     int rc = check_volume(vol);
     if (rc) return rc;
     rc = check_common(effective_earth_radius, nx, ny);
@@ -1155,6 +1179,7 @@ int pcg_get_cappi3d(const pcg_volume* vol, double radar_height, double effective
                        blind_code, beam_width_deg, 0.0, 0.0, 0, 0, (double*)g_scratch[S_OUT].ptr, d_idx, st);
     g_nonfinite_flag = nullptr;
     if (rc) return rc;
+    if ((rc = relabel_missing((double*)g_scratch[S_OUT].ptr, nout, fill, out_missing, st))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, g_scratch[S_OUT].ptr, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (index_out)
         CUDA_TRY(cudaMemcpyAsync(index_out, d_idx, (size_t)nz * ncol * kIdxStride * sizeof(int32_t),
@@ -1167,6 +1192,12 @@ int pcg_get_cappi3d(const pcg_volume* vol, double radar_height, double effective
 
 int pcg_get_cr(const pcg_volume* vol, double radar_height, double effective_earth_radius,
                const double* grid_x, const double* grid_y, int nx, int ny, double fill, double* out) {
+    return pcg_get_cr_ex(vol, radar_height, effective_earth_radius, grid_x, grid_y, nx, ny, fill, fill, out);
+}
+
+int pcg_get_cr_ex(const pcg_volume* vol, double radar_height, double effective_earth_radius,
+                  const double* grid_x, const double* grid_y, int nx, int ny, double fill, double out_missing,
+                  double* out) {
     int rc = check_volume(vol);
     if (rc) return rc;
     rc = check_common(effective_earth_radius, nx, ny);
@@ -1189,6 +1220,7 @@ int pcg_get_cr(const pcg_volume* vol, double radar_height, double effective_eart
                     (double*)g_scratch[S_OUT].ptr, nullptr, st);
     g_nonfinite_flag = nullptr;
     if (rc) return rc;
+    if ((rc = relabel_missing((double*)g_scratch[S_OUT].ptr, ncol, fill, out_missing, st))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, g_scratch[S_OUT].ptr, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
     int flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, g_scratch[S_TMP2].ptr, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -205,8 +205,9 @@ def _put(prd, name, dims, values, attrs):
     prd.product[name].attrs = dict(attrs)
 
 
-def _nan(grid, fillvalue=FILL):
-    return np.where(grid == fillvalue, np.nan, grid)
+# The reference's wrappers end with ``np.where(GridV == fillvalue, np.nan, GridV)`` (NRadar.py:1339,1392,1437): a
+# host pass that costs more than the gridding call at C3 size.  Here the gridding call itself stores NaN in the
+# empty cells (``missing=np.nan`` -> pcg_get_*_ex) before the result leaves the device.
 
 
 def _local_grid(prd, XLon, YLat):
@@ -224,12 +225,12 @@ def add_product_CR_xy(prd, XRange, YRange, range_mode=None):
     """NRadar.py:1322-1356."""
     GridX, GridY = np.meshgrid(XRange, YRange, indexing="ij")
     mode, va, vr, fe, vv, h = _volume_of(prd, range_mode)
-    GridV = G.get_CR_xy(va, vr, fe, vv, h, GridX.astype(np.float64), GridY.astype(np.float64), FILL,
-                        prd.effective_earth_radius)
+    GridV = G.get_CR_xy(va, vr, fe, vv, h, np.asarray(GridX, dtype=np.float64), np.asarray(GridY, dtype=np.float64), FILL,
+                        prd.effective_earth_radius, missing=np.nan)
     name = prd._product_name("CR", mode)
     _set_coord(prd, "x_cr", XRange, dict(_X_ATTRS, standard_name="CR_product_x_axis "))
     _set_coord(prd, "y_cr", YRange, dict(_Y_ATTRS, standard_name="CR_product_y_axis "))
-    _put(prd, name, ("x_cr", "y_cr"), _nan(GridV),
+    _put(prd, name, ("x_cr", "y_cr"), GridV,
          {"units": "dBZ", "standard_name": "Composite_reflectivity_factor",
           "long_name": "Composite_reflectivity_factor", "axis": "xy_coordinate",
           "comment": "Maximum reflectance of all level"})
@@ -239,13 +240,13 @@ def add_product_CAPPI_xy(prd, XRange, YRange, level_height, range_mode=None):
     """NRadar.py:1358-1394."""
     GridX, GridY = np.meshgrid(XRange, YRange, indexing="ij")
     mode, va, vr, fe, vv, h = _volume_of(prd, range_mode)
-    GridV = G.get_CAPPI_xy(va, vr, fe, vv, h, GridX.astype(np.float64), GridY.astype(np.float64), level_height, FILL,
-                           prd.effective_earth_radius)
+    GridV = G.get_CAPPI_xy(va, vr, fe, vv, h, np.asarray(GridX, dtype=np.float64), np.asarray(GridY, dtype=np.float64), level_height, FILL,
+                           prd.effective_earth_radius, missing=np.nan)
     name = prd._product_name("CAPPI_%d" % level_height, mode)
     xn, yn = "x_cappi_%d" % level_height, "y_cappi_%d" % level_height
     _set_coord(prd, xn, XRange, dict(_X_ATTRS, standard_name="CAPPI_product_x_axis "))
     _set_coord(prd, yn, YRange, dict(_Y_ATTRS, standard_name="CAPPI_product_y_axis "))
-    _put(prd, name, (xn, yn), _nan(GridV),
+    _put(prd, name, (xn, yn), GridV,
          {"units": "dBZ", "standard_name": "Constant_altitude_plan_position_indicator",
           "long_name": "Constant_altitude_plan_position_indicator", "axis": "xy_coordinate",
           "comment": "CAPPI of level %d m." % level_height})
@@ -256,13 +257,13 @@ def add_product_CAPPI_3d_xy(prd, XRange, YRange, level_heights, range_mode=None)
     GridX, GridY = np.meshgrid(XRange, YRange, indexing="ij")
     mode, va, vr, fe, vv, h = _volume_of(prd, range_mode)
     level_heights = np.asarray(level_heights, dtype=np.float64)
-    GridV = G.get_CAPPI_3d(va, vr, fe, vv, h, GridX.astype(np.float64), GridY.astype(np.float64), level_heights, FILL,
-                           prd.effective_earth_radius)
+    GridV = G.get_CAPPI_3d(va, vr, fe, vv, h, np.asarray(GridX, dtype=np.float64), np.asarray(GridY, dtype=np.float64), level_heights, FILL,
+                           prd.effective_earth_radius, missing=np.nan)
     _set_coord(prd, "z_cappi", level_heights, {"units": "meters", "standard_name": "CAPPI_product_z_axis ",
                                                 "long_name": "height_above_mean_sea_level", "axis": "z_coordinate"})
     _set_coord(prd, "x_cappi_3d", XRange, dict(_X_ATTRS, standard_name="CAPPI_product_x_axis "))
     _set_coord(prd, "y_cappi_3d", YRange, dict(_Y_ATTRS, standard_name="CAPPI_product_y_axis "))
-    _put(prd, prd._product_name("CAPPI_3D", mode), ("z_cappi", "x_cappi_3d", "y_cappi_3d"), _nan(GridV),
+    _put(prd, prd._product_name("CAPPI_3D", mode), ("z_cappi", "x_cappi_3d", "y_cappi_3d"), GridV,
          {"units": "dBZ", "standard_name": "Constant_altitude_plan_position_indicator",
           "long_name": "3D_constant_altitude_plan_position_indicator", "axis": "xyz_coordinate",
           "comment": "3D CAPPI volume for the current radar"})
@@ -272,10 +273,10 @@ def add_product_CR_lonlat(prd, XLon, YLat, range_mode=None):
     """NRadar.py:1746-1780."""
     GridX, GridY = _local_grid(prd, XLon, YLat)
     mode, va, vr, fe, vv, h = _volume_of(prd, range_mode)
-    GridV = G.get_CR_xy(va, vr, fe, vv, h, GridX, GridY, FILL, prd.effective_earth_radius)
+    GridV = G.get_CR_xy(va, vr, fe, vv, h, GridX, GridY, FILL, prd.effective_earth_radius, missing=np.nan)
     _set_coord(prd, "lon_cr", XLon, {"units": "degrees", "long_name": "longitude"})
     _set_coord(prd, "lat_cr", YLat, {"units": "degrees", "long_name": "latitude"})
-    _put(prd, prd._product_name("CR_geo", mode), ("lon_cr", "lat_cr"), _nan(GridV),
+    _put(prd, prd._product_name("CR_geo", mode), ("lon_cr", "lat_cr"), GridV,
          {"units": "dBZ", "standard_name": "Composite_reflectivity_factor_lonlat_grid",
           "long_name": "Composite_reflectivity_factor", "axis": "lonlat_coordinate"})
 
@@ -284,11 +285,12 @@ def add_product_CAPPI_lonlat(prd, XLon, YLat, level_height, range_mode=None):
     """NRadar.py:1782-1818."""
     GridX, GridY = _local_grid(prd, XLon, YLat)
     mode, va, vr, fe, vv, h = _volume_of(prd, range_mode)
-    GridV = G.get_CAPPI_xy(va, vr, fe, vv, h, GridX, GridY, level_height, FILL, prd.effective_earth_radius)
+    GridV = G.get_CAPPI_xy(va, vr, fe, vv, h, GridX, GridY, level_height, FILL, prd.effective_earth_radius,
+                           missing=np.nan)
     xn, yn = "lon_cappi_%d" % level_height, "lat_cappi_%d" % level_height
     _set_coord(prd, xn, XLon, {"units": "degrees", "long_name": "longitude"})
     _set_coord(prd, yn, YLat, {"units": "degrees", "long_name": "latitude"})
-    _put(prd, prd._product_name("CAPPI_geo_%d" % level_height, mode), (xn, yn), _nan(GridV),
+    _put(prd, prd._product_name("CAPPI_geo_%d" % level_height, mode), (xn, yn), GridV,
          {"units": "dBZ", "standard_name": "Constant_altitude_plan_position_indicator",
           "long_name": "Constant_altitude_plan_position_indicator", "axis": "lonlat_coordinate",
           "comment": "CAPPI of level %d m" % level_height})
@@ -299,7 +301,7 @@ def grid_reflectivity_volume_xy(prd, XRange, YRange, level_heights, range_mode=N
     GridX, GridY = np.meshgrid(XRange, YRange, indexing="ij")
     level_heights = np.asarray(level_heights, dtype=np.float64)
     mode, va, vr, fe, vv, h = _volume_of(prd, range_mode)
-    GridV = G.get_CAPPI_3d(va, vr, fe, vv, h, GridX.astype(np.float64), GridY.astype(np.float64), level_heights, FILL,
+    GridV = G.get_CAPPI_3d(va, vr, fe, vv, h, np.asarray(GridX, dtype=np.float64), np.asarray(GridY, dtype=np.float64), level_heights, FILL,
                            prd.effective_earth_radius, blind_method)
     return mode, FILL, level_heights, GridV
 
@@ -343,7 +345,7 @@ def grid_3d_network_xy(radars, XRange, YRange, level_heights, field_name="dBZ", 
         rx[i], ry[i], rh[i] = float(x), float(y), h
         radii.append(getattr(radar, "effective_earth_radius", None))
         va.append(a); vr.append(r); fe.append(e); vv.append(v)
-    GridV = G.get_mosaic_CAPPI_3d(va, vr, fe, vv, rx, ry, rh, GridX.astype(np.float64), GridY.astype(np.float64),
+    GridV = G.get_mosaic_CAPPI_3d(va, vr, fe, vv, rx, ry, rh, np.asarray(GridX, dtype=np.float64), np.asarray(GridY, dtype=np.float64),
                                   level_heights, fillvalue, radii)
     product = _new_dataset({"z": level_heights, "x": XRange, "y": YRange})
     product["network_3d"] = (("z", "x", "y"), np.where(GridV == fillvalue, np.nan, GridV))

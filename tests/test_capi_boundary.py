@@ -31,7 +31,9 @@ def test_module_exports_reference_names_and_signatures():
              "xye_to_antenna"]        # pycwr/core/RadarGridC.py:25-37
     assert sorted(G.__all__) == sorted(names)
     def params(fn):
-        return [p for p in inspect.signature(fn).parameters if p != "return_index"]
+        # the reference's positional parameters; extensions are `return_index` and keyword-only options
+        return [n for n, p in inspect.signature(fn).parameters.items()
+                if n != "return_index" and p.kind != inspect.Parameter.KEYWORD_ONLY]
     assert params(G.get_CR_xy) == ["vol_azimuth", "vol_range", "fix_elevation", "vol_value", "radar_height",
                                    "GridX", "GridY", "fillvalue", "effective_earth_radius"]
     assert params(G.get_CAPPI_xy) == ["vol_azimuth", "vol_range", "fix_elevation", "vol_value", "radar_height",

@@ -114,3 +114,21 @@ def test_prd_products_use_the_device_packer_and_match_the_host_path():
     lib = _lib.load()
     h_ = ctypes.c_void_p()
     assert lib.pcg_volume_create_raw(1, None, None, None, None, 1, None, None, None, None, FILL, 1, ctypes.byref(h_)) == -1
+
+
+def test_missing_marker_is_applied_on_the_device():
+    """`missing=np.nan` == the wrappers' `np.where(GridV == fillvalue, np.nan, GridV)` (NRadar.py:1339,1392,1437)."""
+    sweeps, fix = raw_sweeps(31, ne=6, fields=2)
+    gx, gy, lv = grids(32, ext=60e3)
+    dv = DeviceVolume.from_sweeps(sweeps, fix, fillvalue=FILL)
+    plain = G.get_CAPPI_3d(None, None, None, dv, 40.0, gx, gy, lv, FILL, None, "hybrid")
+    nan = G.get_CAPPI_3d(None, None, None, dv, 40.0, gx, gy, lv, FILL, None, "hybrid", missing=np.nan)
+    assert (plain == FILL).any() and np.array_equal(np.where(plain == FILL, np.nan, plain), nan, equal_nan=True)
+    one = G.get_CAPPI_xy(None, None, None, dv, 40.0, gx, gy, 1500.0, FILL, missing=-1.0)
+    ref = G.get_CAPPI_xy(None, None, None, dv, 40.0, gx, gy, 1500.0, FILL)
+    assert (ref == FILL).any() and np.array_equal(np.where(ref == FILL, -1.0, ref), one)
+    single = DeviceVolume.from_sweeps([(a, r, v[0]) for a, r, v in sweeps], fix, fillvalue=FILL)
+    cr = G.get_CR_xy(None, None, None, single, 40.0, gx, gy, FILL)
+    crn = G.get_CR_xy(None, None, None, single, 40.0, gx, gy, FILL, missing=np.nan)
+    assert np.array_equal(np.where(cr == FILL, np.nan, cr), crn, equal_nan=True)
+    dv.close(); single.close()
