@@ -308,10 +308,32 @@ def bench_network(args, torch, dist, dev, rank, world):
         dist.all_reduce(nrad, op=dist.ReduceOp.SUM)
     voxels = nz * nlat * nlon
     valid_frac = float((comp != FILL).double().mean().item()) if rows else 0.0
-    for v in vols:
-        v.close()
     del comp, cov, blind, cr, flush
     torch.cuda.empty_cache()
+    e2e = None
+    if world == 1 and n:
+        # end to end through the host-facing call of the network product (host grids in; composite with NaN in
+        # its empty cells, coverage, blind mask, CR, VIL, ET and the topped flag out, every copy timed)
+        import time
+
+        from pycwr_b200 import interp
+        call = lambda: interp.network_compose(                                                  # noqa: E731
+            vols, sites[mine], heights, gx_h, gy_h, levels, fillvalue=FILL, beam_widths=bws, missing=float("nan"),
+            outputs=("coverage_count", "blind_mask", "CR"), column_products=(18.0, 56.0, 18.0))
+        res = call()
+        res = call()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            res = call()
+        dt = (time.perf_counter() - t0) / reps
+        out_bytes = sum(int(_np.asarray(a).nbytes) for k, a in res.items() if k != "tie_voxels")
+        e2e = {"value": voxels / dt, "unit": UNIT, "ms_per_call": dt * 1e3,
+               "h2d_bytes_per_step": int(gx_h.nbytes + gy_h.nbytes), "d2h_bytes_per_step": out_bytes,
+               "api": "pycwr_b200.interp.network_compose (host grids in; composite(NaN), coverage, blind, CR, VIL, ET out)"}
+        del res
+    for v in vols:
+        v.close()
     if rank != 0:
         return None
     peak, _ = read_peaks()
@@ -328,7 +350,7 @@ def bench_network(args, torch, dist, dev, rank, world):
         "collective": "all_gather of finished composite slabs (NCCL)" if world > 1 else "none",
         "radars_per_rank_mean": float(nrad.item()) / world, "composite_method": "quality_weighted",
         "blind_method": "hybrid", "style": "stress", "gpu_launches": int(launches),
-        "valid_fraction_rank0": valid_frac,
+        "valid_fraction_rank0": valid_frac, "e2e": e2e,
         "roofline": {"bound": "hbm", "achieved": balg / kern_s / 1e9, "peak": peak * world, "unit": "GB/s",
                      "frac": balg / kern_s / 1e9 / (peak * world), "algorithmic_bytes": int(balg),
                      "kernel": "pcg::net_radar_kernel<3,1> x radars + net_cull_kernel + net_finalize_kernel<3>"},

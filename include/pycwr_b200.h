@@ -188,6 +188,20 @@ int pcg_network_compose(int nradar, const pcg_volume *const *vols, const double 
                         int nx, int ny, const double *level_heights, int nz, double fill,
                         double *composite, int16_t *valid_count, int16_t *coverage_count,
                         int8_t *blind_mask, double *cr, double *quality, uint64_t *tie_voxels);
+/* pcg_network_compose with (a) the missing-value marker of the composite chosen by the caller (`out_missing`,
+ * typically NaN: the `np.where(values == fillvalue, np.nan, values)` of build_network_dataset, `RadarInterp.py:1539`)
+ * and (b) the column products of the composite computed while it is still on the device: column_params =
+ * {vil_min_dbz, vil_max_dbz_cap, et_threshold_dbz} (NULL: none) -> vil, et [nx*ny] (NaN where undefined) and
+ * et_topped [nx*ny] uint8 (`RadarInterp.py:2064-2119`, derive_vil / derive_et `pycwr/core/RadarProduct.py:33-85`);
+ * composite may be NULL when only the column products are wanted (the product-level pass of `:1971-2000`). */
+int pcg_network_compose_ex(int nradar, const pcg_volume *const *vols, const double *radar_x,
+                           const double *radar_y, const double *radar_height,
+                           const double *effective_earth_radius, const double *const *beam_widths,
+                           const pcg_network_params *params, const double *grid_x, const double *grid_y,
+                           int nx, int ny, const double *level_heights, int nz, double fill, double out_missing,
+                           double *composite, int16_t *valid_count, int16_t *coverage_count,
+                           int8_t *blind_mask, double *cr, double *quality, uint64_t *tie_voxels,
+                           const double *column_params, double *vil, double *et, unsigned char *et_topped);
 int pcg_network_compose_dev(int nradar, const pcg_volume *const *vols, const double *radar_x,
                             const double *radar_y, const double *radar_height,
                             const double *effective_earth_radius, const double *const *beam_widths,

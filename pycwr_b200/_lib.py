@@ -51,6 +51,9 @@ SIGNATURES = {
     "pcg_network_compose": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_pp, _vp,
                                  _vp, _vp, _i, _i, c_double_p, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp,
                                  ctypes.POINTER(ctypes.c_uint64)]),
+    "pcg_network_compose_ex": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_pp, _vp,
+                                    _vp, _vp, _i, _i, c_double_p, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    ctypes.POINTER(ctypes.c_uint64), c_double_p, _vp, _vp, _vp]),
     "pcg_network_compose_dev": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_pp,
                                      _vp, _vp, _vp, _i, _i, c_double_p, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcg_network_gates": (_i, [_i, c_double_p, c_double_p, c_double_p, c_double_p, _d, _d, _d, _d, _vp, _vp, _i, _i,

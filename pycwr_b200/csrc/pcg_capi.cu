@@ -1771,6 +1771,12 @@ extern "C" int pcg_network_compose_dev(int nradar, const pcg_volume* const* vols
                            (cudaStream_t)stream);
 }
 
+namespace {
+int enqueue_columns(const double* d_vol, const double* d_levels, int nz, long long ncol, double fill, double min_dbz,
+                    double max_dbz_cap, double threshold, double* d_cr, double* d_vil, double* d_et,
+                    unsigned char* d_topped, cudaStream_t st);
+}
+
 extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, const double* radar_x,
                                    const double* radar_y, const double* radar_height,
                                    const double* effective_earth_radius, const double* const* beam_widths,
@@ -1778,8 +1784,25 @@ extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, co
                                    int nx, int ny, const double* level_heights, int nz, double fill,
                                    double* composite, int16_t* valid_count, int16_t* coverage_count,
                                    int8_t* blind_mask, double* cr, double* quality, uint64_t* tie_voxels) {
-    if (nx < 0 || ny < 0 || nz < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
     if (!composite) return fail(PCG_ERR_ARG, "composite is NULL");
+    return pcg_network_compose_ex(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths,
+                                  params, grid_x, grid_y, nx, ny, level_heights, nz, fill, fill, composite,
+                                  valid_count, coverage_count, blind_mask, cr, quality, tie_voxels, nullptr, nullptr,
+                                  nullptr, nullptr);
+}
+
+extern "C" int pcg_network_compose_ex(int nradar, const pcg_volume* const* vols, const double* radar_x,
+                                      const double* radar_y, const double* radar_height,
+                                      const double* effective_earth_radius, const double* const* beam_widths,
+                                      const pcg_network_params* params, const double* grid_x, const double* grid_y,
+                                      int nx, int ny, const double* level_heights, int nz, double fill,
+                                      double out_missing, double* composite, int16_t* valid_count,
+                                      int16_t* coverage_count, int8_t* blind_mask, double* cr, double* quality,
+                                      uint64_t* tie_voxels, const double* column_params, double* vil, double* et,
+                                      unsigned char* et_topped) {
+    if (nx < 0 || ny < 0 || nz < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
+    const bool columns = column_params && (vil || et || et_topped);
+    if (!composite && !columns) return fail(PCG_ERR_ARG, "composite is NULL");
     const size_t ncol = (size_t)nx * (size_t)ny;
     const size_t nvox = (size_t)nz * ncol;
     if (tie_voxels) *tie_voxels = 0;
@@ -1810,7 +1833,26 @@ extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, co
                          quality ? (double*)g_scratch[S_AUX4].ptr : nullptr,
                          (unsigned long long*)g_scratch[S_TMP2].ptr, st);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(composite, g_scratch[S_OUT].ptr, nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (columns && ncol) {
+        // VIL / ET of the composite while it is still on the device (RadarInterp.py:2064-2119 -> derive_vil /
+        // derive_et, RadarProduct.py:33-85): no second trip of the volume over PCIe
+        if ((rc = g_scratch[S_TMP0].ensure((size_t)(nz ? nz : 1) * sizeof(double)))) return rc;
+        if ((rc = g_scratch[S_ACC0].ensure(2 * ncol * sizeof(double) + ncol))) return rc;
+        if (nz) CUDA_TRY(cudaMemcpyAsync(g_scratch[S_TMP0].ptr, level_heights, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, st));
+        double* d2 = (double*)g_scratch[S_ACC0].ptr;
+        unsigned char* dt = (unsigned char*)(d2 + 2 * ncol);
+        rc = enqueue_columns((const double*)g_scratch[S_OUT].ptr, (const double*)g_scratch[S_TMP0].ptr, nz, (long long)ncol,
+                             fill, column_params[0], column_params[1], column_params[2], nullptr, vil ? d2 : nullptr,
+                             et ? d2 + ncol : nullptr, et_topped ? dt : nullptr, st);
+        if (rc) return rc;
+        if (vil) CUDA_TRY(cudaMemcpyAsync(vil, d2, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (et) CUDA_TRY(cudaMemcpyAsync(et, d2 + ncol, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (et_topped) CUDA_TRY(cudaMemcpyAsync(et_topped, dt, ncol, cudaMemcpyDeviceToHost, st));
+    }
+    if (composite) {
+        if ((rc = relabel_missing((double*)g_scratch[S_OUT].ptr, nvox, fill, out_missing, st))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(composite, g_scratch[S_OUT].ptr, nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     if (valid_count) CUDA_TRY(cudaMemcpyAsync(valid_count, g_scratch[S_AUX0].ptr, nvox * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
     if (coverage_count) CUDA_TRY(cudaMemcpyAsync(coverage_count, g_scratch[S_AUX1].ptr, nvox * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
     if (blind_mask) CUDA_TRY(cudaMemcpyAsync(blind_mask, g_scratch[S_AUX2].ptr, nvox * sizeof(int8_t), cudaMemcpyDeviceToHost, st));

@@ -280,7 +280,7 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
                     quality_weight_terms=("range", "beam", "vertical"), range_decay_m=230000.0,
                     beam_radius_ref_m=3000.0, vertical_gap_ref_deg=0.5, beam_widths=None, effective_earth_radius=None,
                     sanity_filter=True, outputs=("valid_count", "coverage_count", "blind_mask", "CR"), rows=None,
-                    allow_empty=False):
+                    allow_empty=False, missing=None, column_products=None, composite=True):
     """All radars of one field merged in one fused kernel launch.
 
     ``volumes``: packed :class:`DeviceVolume` per radar (field 0 is used).  ``rows=(r0, r1)``
@@ -289,6 +289,10 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
     (``valid_count`` int16, ``coverage_count`` int16, ``blind_mask`` int8, ``CR`` with NaN where
     no echo, ``quality`` = weight of the last radar) plus ``tie_voxels``.  ``allow_empty``: an empty
     radar list (a slab no radar reaches) yields the all-fill result instead of the reference's error.
+    ``missing``: value stored in empty composite cells instead of ``fillvalue`` (``np.nan`` = the dataset layout
+    of ``build_network_dataset``, applied on the device).  ``column_products=(vil_min_dbz, vil_max_dbz_cap,
+    et_threshold_dbz)`` adds ``VIL`` / ``ET`` / ``ET_TOPPED`` of the composite, computed before it leaves the
+    device; ``composite=False`` then skips returning the volume itself.
     """
     method = _check_method(method)
     gx = _f64_2d(grid_x, "grid_x")
@@ -306,7 +310,11 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
             raise ValueError("radar_volumes must contain at least one volume.")
         shape = (int(levels.size),) + gx.shape
         want = set(outputs or ())
-        res = {"composite": np.full(shape, float(fillvalue)), "tie_voxels": 0}
+        res = {"composite": np.full(shape, float(fillvalue if missing is None else missing)), "tie_voxels": 0}
+        if column_products is not None:
+            res["VIL"] = np.full(gx.shape, np.nan)
+            res["ET"] = np.full(gx.shape, np.nan)
+            res["ET_TOPPED"] = np.zeros(gx.shape, dtype=np.uint8)
         if "valid_count" in want:
             res["valid_count"] = np.zeros(shape, dtype=np.int16)
         if "coverage_count" in want or "blind_mask" in want:
@@ -354,16 +362,26 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
     nz, (nx, ny) = int(levels.size), gx.shape
     shape = (nz, nx, ny)
     want = set(outputs or ())
-    res = {"composite": pinned_empty(shape, np.float64)}
+    res = {}
+    if composite or column_products is None:
+        res["composite"] = pinned_empty(shape, np.float64)
+    cpar = None
+    if column_products is not None:
+        cpar = np.ascontiguousarray(column_products, dtype=np.float64).ravel()
+        if cpar.size != 3:
+            raise ValueError("column_products must be (vil_min_dbz, vil_max_dbz_cap, et_threshold_dbz)")
+        res["VIL"] = np.full((nx, ny), np.nan)
+        res["ET"] = np.full((nx, ny), np.nan)
+        res["ET_TOPPED"] = np.zeros((nx, ny), dtype=np.uint8)
     if "valid_count" in want:
-        res["valid_count"] = np.empty(shape, dtype=np.int16)
+        res["valid_count"] = pinned_empty(shape, np.int16)
     if "coverage_count" in want or "blind_mask" in want:
-        res["coverage_count"] = np.empty(shape, dtype=np.int16)
-        res["blind_mask"] = np.empty(shape, dtype=np.int8)
+        res["coverage_count"] = pinned_empty(shape, np.int16)
+        res["blind_mask"] = pinned_empty(shape, np.int8)
     if "CR" in want:
         res["CR"] = np.empty((nx, ny), dtype=np.float64)
     if "quality" in want:
-        res["quality"] = np.empty(shape, dtype=np.float64)
+        res["quality"] = pinned_empty(shape, np.float64)
     ties = ctypes.c_uint64(0)
     handles = (ctypes.c_void_p * n)(*[v.handle for v in volumes])
 
@@ -371,12 +389,14 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
         return _lib.as_ptr(res[key]) if key in res else None
 
     if gx.size and (nz or "CR" in want):
-        _lib.check(_lib.load().pcg_network_compose(
+        _lib.check(_lib.load().pcg_network_compose_ex(
             n, handles, rx.ctypes.data_as(_lib.c_double_p), ry.ctypes.data_as(_lib.c_double_p),
             rh.ctypes.data_as(_lib.c_double_p), re.ctypes.data_as(_lib.c_double_p), bwp, ctypes.byref(prm),
             _lib.as_ptr(gx), _lib.as_ptr(gy), nx, ny, levels.ctypes.data_as(_lib.c_double_p), nz, float(fillvalue),
+            float(fillvalue if missing is None else missing),
             ptr("composite"), ptr("valid_count"), ptr("coverage_count"), ptr("blind_mask"), ptr("CR"), ptr("quality"),
-            ctypes.byref(ties)))
+            ctypes.byref(ties), None if cpar is None else cpar.ctypes.data_as(_lib.c_double_p),
+            ptr("VIL"), ptr("ET"), ptr("ET_TOPPED")))
     res["tie_voxels"] = int(ties.value)
     return res
 
@@ -503,7 +523,7 @@ def run_radar_network_3d(radars, radar_lonlat, lon_min, lon_max, lat_min, lat_ma
               beam_radius_ref_m=float(opt(beam_radius_ref_m, "beam_radius_ref_m")),
               vertical_gap_ref_deg=float(opt(vertical_gap_ref_deg, "vertical_gap_ref_deg")),
               effective_earth_radius=effective_earth_radius, rows=rows)
-    product_volume = None
+    prod = None
     for field in field_names:
         mode = range_modes.get(field, "native" if field == "dBZ" else None)   # RadarInterp.py:271-272
         vols, heights, bws, actual, owned = [], [], [], {}, []
@@ -517,10 +537,16 @@ def run_radar_network_3d(radars, radar_lonlat, lon_min, lon_max, lat_min, lat_ma
             range_modes[field] = used
         try:
             is_ref = field == "dBZ"
+            want_cols = is_ref and ("VIL" in output_products or "ET" in output_products) and product_levels.size
+            same_levels = bool(want_cols) and np.array_equal(product_levels, level_heights)
+            cpar = (float(opt(vil_min_dbz, "vil_min_dbz")), float(opt(vil_max_dbz_cap, "vil_max_dbz_cap")),
+                    float(opt(et_threshold_dbz, "et_threshold_dbz")))
+            # the composite leaves the device with NaN in its empty cells (build_network_dataset's np.where,
+            # RadarInterp.py:1539) and with its column products already derived (no host pass, no re-upload)
             res = network_compose(vols, sites, heights, grid_x, grid_y, level_heights, beam_widths=bws,
-                                  outputs=("coverage_count", "blind_mask", "CR") if is_ref else (), **kw)
-            comp = np.asarray(res["composite"])
-            ds[field] = (("z", "lat", "lon"), np.where(comp == fillvalue, np.nan, comp))
+                                  outputs=("coverage_count", "blind_mask", "CR") if is_ref else (), missing=np.nan,
+                                  column_products=cpar if same_levels else None, **kw)
+            ds[field] = (("z", "lat", "lon"), np.asarray(res["composite"]))
             ds[field].attrs = {
                 "standard_name": "radar_volume_mosaic", "long_name": "%s 3D radar network mosaic" % field,
                 "coordinates": "z lat lon", "range_mode": range_modes[field],
@@ -538,21 +564,16 @@ def run_radar_network_3d(radars, radar_lonlat, lon_min, lon_max, lat_min, lat_ma
                     ds["CR"] = (("lat", "lon"), res["CR"])
                     ds["CR"].attrs = {"units": "dBZ", "long_name": "network_composite_reflectivity",
                                       "composite_method": "max"}
-                product_volume = comp
-                if ("VIL" in output_products or "ET" in output_products) and product_levels.size and \
-                        not np.array_equal(product_levels, level_heights):       # RadarInterp.py:1971-2000
-                    product_volume = np.asarray(network_compose(vols, sites, heights, grid_x, grid_y, product_levels,
-                                                                beam_widths=bws, outputs=(), **kw)["composite"])
+                if same_levels:
+                    prod = res
+                elif want_cols:                                                  # RadarInterp.py:1971-2000
+                    prod = network_compose(vols, sites, heights, grid_x, grid_y, product_levels, beam_widths=bws,
+                                           outputs=(), column_products=cpar, composite=False, **kw)
         finally:
             for v, mine in zip(vols, owned):
                 if mine:
                     v.close()
-    if product_volume is not None and ("VIL" in output_products or "ET" in output_products):
-        from .products import column_products
-        prod = column_products(product_volume, product_levels, fillvalue=fillvalue,
-                               min_dbz=float(opt(vil_min_dbz, "vil_min_dbz")),
-                               max_dbz_cap=float(opt(vil_max_dbz_cap, "vil_max_dbz_cap")),
-                               threshold_dbz=float(opt(et_threshold_dbz, "et_threshold_dbz")))
+    if prod is not None and ("VIL" in output_products or "ET" in output_products):
         levels_json = json.dumps(product_levels.tolist())
         if "VIL" in output_products:             # RadarInterp.py:2064-2084
             ds["VIL"] = (("lat", "lon"), prod["VIL"])
