@@ -240,6 +240,15 @@ int pcg_compose_volumes(int nradar, const double *const *volumes, const double *
 int pcg_column_products(const double *volume, const double *level_heights, int nz, int nx, int ny,
                         double fill, double min_dbz, double max_dbz_cap, double threshold_dbz,
                         double *cr, double *vil, double *et, unsigned char *topped);
+/* Grid one radar's volume (pcg_get_cappi3d, one moment) and reduce its columns in the same call: only the
+ * (nx, ny) planes come back — the flow of PRD.add_product_VIL_xy / add_product_ET_xy
+ * (`pycwr/core/NRadar.py:1459-1572`: _grid_reflectivity_volume_xy then derive_vil / derive_et) without the
+ * volume's round trip over PCIe.  Any of cr / vil / et / et_topped may be NULL. */
+int pcg_get_column_products(const pcg_volume *vol, double radar_height, double effective_earth_radius,
+                            const double *grid_x, const double *grid_y, int nx, int ny,
+                            const double *level_heights, int nz, double fill, int blind_code,
+                            double min_dbz, double max_dbz_cap, double threshold_dbz, double *cr,
+                            double *vil, double *et, unsigned char *et_topped);
 int pcg_column_products_dev(const double *d_volume, const double *d_levels, int nz, int nx, int ny,
                             double fill, double min_dbz, double max_dbz_cap, double threshold_dbz,
                             double *d_cr, double *d_vil, double *d_et, unsigned char *d_topped,

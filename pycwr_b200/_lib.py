@@ -60,6 +60,8 @@ SIGNATURES = {
                                c_double_p, _i, _i, _d, _d, _d, _vp, _vp]),
     "pcg_compose_volumes": (_i, [_i, c_double_pp, c_double_pp, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
     "pcg_column_products": (_i, [_vp, c_double_p, _i, _i, _i, _d, _d, _d, _d, _vp, _vp, _vp, _vp]),
+    "pcg_get_column_products": (_i, [_vp, _d, _d, _vp, _vp, _i, _i, c_double_p, _i, _d, _i, _d, _d, _d, _vp, _vp, _vp,
+                                     _vp]),
     "pcg_column_products_dev": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "pcg_wind_gather": (_i, [_vp, ctypes.c_longlong, _vp, _vp, ctypes.c_longlong, _d, _d, _i, _d, _vp, _vp, _vp]),
     "pcg_wind_vertical": (_i, [_vp, _i, ctypes.c_longlong, c_double_p, _i, _d, _d, _vp, _vp, _vp]),

@@ -2278,3 +2278,52 @@ extern "C" int pcg_vvp_local(const double* azimuth, const double* elevation, con
     CUDA_TRY(cudaStreamSynchronize(st));
     return PCG_OK;
 }
+
+// ---- f1 fused: grid one radar's volume and reduce its columns without returning the volume ------
+extern "C" int pcg_get_column_products(const pcg_volume* vol, double radar_height, double effective_earth_radius,
+                                       const double* grid_x, const double* grid_y, int nx, int ny,
+                                       const double* level_heights, int nz, double fill, int blind_code,
+                                       double min_dbz, double max_dbz_cap, double threshold_dbz, double* cr,
+                                       double* vil, double* et, unsigned char* et_topped) {
+    int rc = check_volume(vol);
+    if (rc) return rc;
+    if ((rc = check_common(effective_earth_radius, nx, ny))) return rc;
+    if (nz < 0) return fail(PCG_ERR_ARG, "nz must be non-negative");
+    if (vol->nfield != 1) return fail(PCG_ERR_ARG, "column products take a single-moment volume");
+    const size_t ncol = (size_t)nx * (size_t)ny, nvox = ncol * (size_t)nz;
+    if (ncol == 0) return PCG_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    cudaStream_t st;
+    if ((rc = lib_stream(&st))) return rc;
+    if ((rc = g_scratch[S_GX].ensure(ncol * sizeof(double))) || (rc = g_scratch[S_GY].ensure(ncol * sizeof(double))) ||
+        (rc = g_scratch[S_OUT].ensure((nvox ? nvox : 1) * sizeof(double))) ||
+        (rc = g_scratch[S_TMP0].ensure((size_t)(nz ? nz : 1) * sizeof(double))) ||
+        (rc = g_scratch[S_AUX3].ensure(3 * ncol * sizeof(double))) || (rc = g_scratch[S_AUX2].ensure(ncol)) ||
+        (rc = g_scratch[S_TMP2].ensure(sizeof(int))))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nz) CUDA_TRY(cudaMemcpyAsync(g_scratch[S_TMP0].ptr, level_heights, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(g_scratch[S_TMP2].ptr, 0, sizeof(int), st));
+    if (nz) {
+        g_nonfinite_flag = (int*)g_scratch[S_TMP2].ptr;
+        rc = enqueue_cappi(vol, radar_height, effective_earth_radius, (const double*)g_scratch[S_GX].ptr,
+                           (const double*)g_scratch[S_GY].ptr, (long long)ncol, ny, level_heights, nz, fill, blind_code,
+                           1.0, 0.0, 0.0, 0, 0, (double*)g_scratch[S_OUT].ptr, nullptr, st);
+        g_nonfinite_flag = nullptr;
+        if (rc) return rc;
+    }
+    double* d3 = (double*)g_scratch[S_AUX3].ptr;
+    rc = enqueue_columns((const double*)g_scratch[S_OUT].ptr, (const double*)g_scratch[S_TMP0].ptr, nz, (long long)ncol, fill,
+                         min_dbz, max_dbz_cap, threshold_dbz, cr ? d3 : nullptr, vil ? d3 + ncol : nullptr,
+                         et ? d3 + 2 * ncol : nullptr, et_topped ? (unsigned char*)g_scratch[S_AUX2].ptr : nullptr, st);
+    if (rc) return rc;
+    if (cr) CUDA_TRY(cudaMemcpyAsync(cr, d3, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (vil) CUDA_TRY(cudaMemcpyAsync(vil, d3 + ncol, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (et) CUDA_TRY(cudaMemcpyAsync(et, d3 + 2 * ncol, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (et_topped) CUDA_TRY(cudaMemcpyAsync(et_topped, g_scratch[S_AUX2].ptr, ncol, cudaMemcpyDeviceToHost, st));
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, g_scratch[S_TMP2].ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return flag ? PCG_WARN_NONFINITE : PCG_OK;
+}

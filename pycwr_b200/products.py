@@ -306,12 +306,43 @@ def grid_reflectivity_volume_xy(prd, XRange, YRange, level_heights, range_mode=N
     return mode, FILL, level_heights, GridV
 
 
+def volume_column_products(prd, XRange, YRange, level_heights, range_mode=None, blind_method="mask", min_dbz=18.0,
+                           max_dbz_cap=56.0, threshold_dbz=18.0):
+    """CR / VIL / ET / ET_TOPPED planes of one radar: ``_grid_reflectivity_volume_xy`` + ``derive_*`` (NRadar.py:
+    1276-1297,1459-1572) in one device call — the gridded volume never leaves the GPU (``pcg_get_column_products``)."""
+    from .runtime import DeviceVolume
+    GridX, GridY = np.meshgrid(XRange, YRange, indexing="ij")
+    gx = np.ascontiguousarray(GridX, dtype=np.float64)
+    gy = np.ascontiguousarray(GridY, dtype=np.float64)
+    levels = np.ascontiguousarray(np.asarray(level_heights, dtype=np.float64).ravel())
+    mode, va, vr, fe, vv, h = _volume_of(prd, range_mode)
+    owned = not isinstance(vv, DeviceVolume)
+    dv = DeviceVolume(va, vr, fe, vv, fillvalue=FILL) if owned else vv
+    nx, ny = gx.shape
+    out = {"CR": np.full((nx, ny), np.nan), "VIL": np.full((nx, ny), np.nan), "ET": np.full((nx, ny), np.nan),
+           "ET_TOPPED": np.zeros((nx, ny), dtype=np.uint8)}
+    try:
+        if nx * ny:
+            rc = _lib.check(_lib.load().pcg_get_column_products(
+                dv.handle, float(h), G._resolve_effective_earth_radius(prd.effective_earth_radius), _lib.as_ptr(gx),
+                _lib.as_ptr(gy), nx, ny, levels.ctypes.data_as(_lib.c_double_p), int(levels.size), FILL,
+                G._resolve_blind_code(blind_method), float(min_dbz), float(max_dbz_cap), float(threshold_dbz),
+                _lib.as_ptr(out["CR"]), _lib.as_ptr(out["VIL"]), _lib.as_ptr(out["ET"]), _lib.as_ptr(out["ET_TOPPED"])))
+            if rc == _lib.PCG_WARN_NONFINITE:      # NaN / inf targets: the operation-by-operation path decides
+                _, fill, lv, GridV = grid_reflectivity_volume_xy(prd, XRange, YRange, level_heights, range_mode, blind_method)
+                out = column_products(GridV, lv, fill, min_dbz, max_dbz_cap, threshold_dbz)
+    finally:
+        if owned:
+            dv.close()
+    return mode, out
+
+
 def add_product_VIL_ET_xy(prd, XRange, YRange, level_heights, range_mode=None, blind_method="mask", min_dbz=18.0,
                           max_dbz_cap=56.0, threshold_dbz=18.0):
     """VIL, ET and ET_TOPPED of one radar from one gridded volume (NRadar.py:1459-1572): the volume
     is gridded once and reduced on the device."""
-    mode, fill, levels, GridV = grid_reflectivity_volume_xy(prd, XRange, YRange, level_heights, range_mode, blind_method)
-    prod = column_products(GridV, levels, fill, min_dbz, max_dbz_cap, threshold_dbz)
+    mode, prod = volume_column_products(prd, XRange, YRange, level_heights, range_mode, blind_method, min_dbz,
+                                        max_dbz_cap, threshold_dbz)
     _set_coord(prd, "x_vil", XRange, _X_ATTRS)
     _set_coord(prd, "y_vil", YRange, _Y_ATTRS)
     _put(prd, prd._product_name("VIL", mode), ("x_vil", "y_vil"), prod["VIL"], {"units": "kg m-2"})
