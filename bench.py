@@ -206,6 +206,111 @@ def run_reference(args):
 # network composite (BASELINE config C4): 32 radars -> 3000 x 3000 x 30, row slabs over the ranks
 # --------------------------------------------------------------------------------------------
 
+class _DevArray(object):
+    """A float64 device buffer owned by the library, viewable as a torch tensor (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def _fused_gather(torch, dist, dev, rank, world, lib, launch_args, nlat, r0, steps, flush, reference):
+    """Network composite with the slab gather fused into net_finalize_kernel (pcg_network_compose_gather_dev):
+    timed like the NCCL variant (CUDA events around the launch, max over ranks, barrier outside the events) and
+    checked bit for bit against the NCCL all_gather of the same slabs."""
+    import ctypes
+
+    from pycwr_b200 import _lib
+    a = launch_args
+    nz, nlon = a["nz"], a["nlon"]
+    nbytes = nz * nlat * nlon * 8
+    full = ctypes.c_void_p()
+    handle = (ctypes.c_ubyte * 64)()
+    peers, opened, err = [], [], None
+
+    def agree(ok):
+        """Every rank must take the same branch: a failure anywhere cancels the fused run everywhere."""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
+    try:
+        _lib.check(lib.pcg_peer_alloc(nbytes, ctypes.byref(full), handle))
+    except Exception as exc:  # noqa: BLE001
+        err = exc
+    if not agree(err is None):
+        if full.value:
+            lib.pcg_peer_free(full)
+        raise RuntimeError("peer buffer allocation failed on a rank: %r" % (err,))
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(handle))
+    try:
+        for r in range(world):
+            if r == rank:
+                peers.append(full.value)
+                continue
+            p = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+            _lib.check(lib.pcg_peer_open(buf, ctypes.byref(p)))
+            peers.append(p.value)
+            opened.append(p)
+    except Exception as exc:  # noqa: BLE001
+        err = exc
+    if not agree(err is None):
+        for p in opened:
+            lib.pcg_peer_close(p)
+        dist.barrier()
+        lib.pcg_peer_free(full)
+        raise RuntimeError("peer mapping failed on a rank: %r" % (err,))
+    parr = (ctypes.c_void_p * world)(*peers)
+    dp = _lib.c_double_p
+
+    def launch():
+        if a["n"] == 0 or a["rows"] == 0:
+            return
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.pcg_network_compose_gather_dev(
+            a["n"], a["handles"], a["rx"].ctypes.data_as(dp), a["ry"].ctypes.data_as(dp), a["rh"].ctypes.data_as(dp),
+            a["re"].ctypes.data_as(dp), a["bwp"], ctypes.byref(a["prm"]), a["gx"].data_ptr(), a["gy"].data_ptr(),
+            a["rows"], nlon, a["levels"].ctypes.data_as(dp), nz, FILL, None, None, a["cov"].data_ptr(),
+            a["blind"].data_ptr(), a["cr"].data_ptr(), world, parr, nlat, r0, st))
+
+    try:
+        for _ in range(2):
+            launch()
+            torch.cuda.synchronize()
+            dist.barrier()
+        # every rank now holds the full grid: compare with the NCCL-gathered slabs
+        parts, bounds = reference
+        mine = torch.as_tensor(_DevArray(full.value, (nz, nlat, nlon)), device=dev)
+        same = True
+        for r, (b0, b1) in enumerate(bounds):
+            same = same and bool(torch.equal(mine[:, b0:b1], parts[r][:, : b1 - b0]))
+        ok = torch.tensor([1 if same else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for e0, e1 in ev:
+            flush.zero_()
+            dist.barrier()
+            e0.record()
+            launch()
+            e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in ev)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        del mine
+        return {"ms_per_step": float(t[0].item()) / steps, "check": "bit-identical to the NCCL all_gather" if int(ok.item())
+                else "MISMATCH against the NCCL all_gather",
+                "how": "net_finalize_kernel stores each slab into every peer's grid (NVLink P2P, CUDA IPC mappings)"}
+    finally:
+        torch.cuda.synchronize()
+        dist.barrier()
+        for p in opened:
+            lib.pcg_peer_close(p)
+        dist.barrier()
+        lib.pcg_peer_free(full)
+
+
 def bench_network(args, torch, dist, dev, rank, world):
     """Fused network kernel on this rank's row slab (inputs resident in HBM), then the NCCL gather
     of the finished composite slabs.  Returns the `network` object of the JSON line (rank 0)."""
@@ -284,6 +389,7 @@ def bench_network(args, torch, dist, dev, rank, world):
     ms = float(sum(a.elapsed_time(b) for a, b in ev))
     # gather of the finished composite slabs (NCCL all_gather, padded slabs), timed on the device
     gather_ms = 0.0
+    fused = None
     if dist is not None:
         maxrows = max(b[1] - b[0] for b in bounds)
         padded = torch.zeros((nz, maxrows, nlon), dtype=torch.float64, device=dev)
@@ -302,6 +408,15 @@ def bench_network(args, torch, dist, dev, rank, world):
         t = torch.tensor([ms, gather_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, gather_ms = float(t[0].item()), float(t[1].item())
+        # the same product with the gather fused into the finalize kernel: every rank stores its slab straight
+        # into the full composite grid of every peer over NVLink (IPC-mapped buffers, no NCCL on the data path)
+        try:
+            fused = _fused_gather(torch, dist, dev, rank, world, lib, launch_args=dict(
+                n=n, handles=handles, rx=rx, ry=ry, rh=rh, re=re, bwp=bwp, prm=prm, gx=gx, gy=gy, rows=rows, nlon=nlon,
+                levels=levels, nz=nz, cov=cov, blind=blind, cr=cr), nlat=nlat, r0=r0, steps=steps, flush=flush,
+                reference=(parts, bounds))
+        except Exception as exc:  # noqa: BLE001 — peer mapping unavailable: the NCCL numbers stand
+            fused = {"error": repr(exc)[:200]}
         del parts, padded
     nrad = torch.tensor([n], dtype=torch.int64, device=dev)
     if dist is not None:
@@ -345,6 +460,8 @@ def bench_network(args, torch, dist, dev, rank, world):
         "workload": "C4_network_%dr_%dx%dx%d" % (args.network_radars, nlat, nlon, nz),
         "value": voxels * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
         "value_with_gather": voxels * steps / ((ms + gather_ms) * 1e-3), "gather_ms_per_step": gather_ms / steps,
+        "fused_gather": None if fused is None else (fused if "error" in fused else dict(
+            fused, value=voxels / (fused["ms_per_step"] * 1e-3), unit=UNIT)),
         "n_gpus": world, "scaling": "strong", "partition": "row slabs of the output grid balanced by (column, radar) pairs, radars culled per slab",
         "slab_rows": [b[1] - b[0] for b in bounds],
         "collective": "all_gather of finished composite slabs (NCCL)" if world > 1 else "none",

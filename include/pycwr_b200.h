@@ -210,6 +210,27 @@ int pcg_network_compose_dev(int nradar, const pcg_volume *const *vols, const dou
                             int nz, double fill, double *d_composite, int16_t *d_valid_count,
                             int16_t *d_coverage_count, int8_t *d_blind_mask, double *d_cr,
                             double *d_quality, void *stream);
+/* Multi-GPU network composite (row slabs of the output grid, one process per GPU).  The finished slab
+ * of every rank has to reach every rank (the all-gather that follows the merge); here the finalize kernel itself
+ * stores the slab into the FULL composite grid of each peer through NVLink peer mappings, so producing the slab
+ * and gathering it are one kernel.  pcg_peer_alloc: device buffer + its 64-byte CUDA IPC handle (exchange the
+ * handles with any host-side collective); pcg_peer_open / pcg_peer_close: map / unmap a peer's buffer.
+ * pcg_network_compose_gather_dev: pcg_network_compose_dev for rows [row_offset, row_offset + nx) of a grid of
+ * full_rows rows whose composite is also written to peer_full[0..npeer) (each [nz][full_rows][ny]; list the own
+ * buffer too); d_composite (the slab alone) may be NULL.  The caller synchronises the ranks afterwards. */
+int pcg_peer_alloc(size_t bytes, void **dptr, unsigned char *handle64);
+int pcg_peer_open(const unsigned char *handle64, void **dptr);
+int pcg_peer_close(void *dptr);
+int pcg_peer_free(void *dptr);
+int pcg_network_compose_gather_dev(int nradar, const pcg_volume *const *vols, const double *radar_x,
+                                   const double *radar_y, const double *radar_height,
+                                   const double *effective_earth_radius, const double *const *beam_widths,
+                                   const pcg_network_params *params, const double *d_grid_x,
+                                   const double *d_grid_y, int nx, int ny, const double *level_heights, int nz,
+                                   double fill, double *d_composite, int16_t *d_valid_count,
+                                   int16_t *d_coverage_count, int8_t *d_blind_mask, double *d_cr,
+                                   int npeer, double *const *peer_full, long long full_rows,
+                                   long long row_offset, void *stream);
 /* min / max / count of the valid (finite, != fill) source values of one moment: the window of the
  * range-sanity filter (`pycwr/interp/RadarInterp.py:1003-1007`), reduced on the device at pack time */
 int pcg_volume_value_range(const pcg_volume *vol, int field, double *vmin, double *vmax, uint64_t *count);

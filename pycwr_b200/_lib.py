@@ -54,6 +54,13 @@ SIGNATURES = {
     "pcg_network_compose_ex": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_pp, _vp,
                                     _vp, _vp, _i, _i, c_double_p, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp,
                                     ctypes.POINTER(ctypes.c_uint64), c_double_p, _vp, _vp, _vp]),
+    "pcg_peer_alloc": (_i, [ctypes.c_size_t, c_void_pp, _vp]),
+    "pcg_peer_open": (_i, [_vp, c_void_pp]),
+    "pcg_peer_close": (_i, [_vp]),
+    "pcg_peer_free": (_i, [_vp]),
+    "pcg_network_compose_gather_dev": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p,
+                                            c_double_pp, _vp, _vp, _vp, _i, _i, c_double_p, _i, _d, _vp, _vp, _vp,
+                                            _vp, _vp, _i, c_void_pp, ctypes.c_longlong, ctypes.c_longlong, _vp]),
     "pcg_network_compose_dev": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_pp,
                                      _vp, _vp, _vp, _i, _i, c_double_p, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcg_network_gates": (_i, [_i, c_double_p, c_double_p, c_double_p, c_double_p, _d, _d, _d, _d, _vp, _vp, _i, _i,

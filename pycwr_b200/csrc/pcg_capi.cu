@@ -1477,6 +1477,10 @@ void key_put(std::vector<char>* key, const T* p, size_t n) {
     key->insert(key->end(), b, b + n * sizeof(T));
 }
 
+// peers of the next enqueue_network call (set and cleared by pcg_network_compose_gather_dev under g_mutex)
+struct NetPeers { int n = 0; long long plane = 0, off = 0; double* ptr[kNetMaxPeers] = {}; };
+NetPeers g_net_peers;
+
 int enqueue_network(int nradar, const pcg_volume* const* vols, const double* radar_x, const double* radar_y,
                     const double* radar_height, const double* re, const double* const* beam_widths,
                     const pcg_network_params* prm, const double* d_gx, const double* d_gy, long long ncol, int ny,
@@ -1663,6 +1667,8 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     A.lowest_sweep = (prm->blind_code == 2 || prm->blind_code == 3 || prm->blind_code == 4);
     A.highest_sweep = (prm->blind_code == 4);
     A.composite = d_comp; A.valid_count = d_valid; A.coverage = d_cov; A.blind = d_blind; A.cr = d_cr;
+    A.npeer = g_net_peers.n; A.peer_plane = g_net_peers.plane; A.peer_off = g_net_peers.off;
+    for (int q = 0; q < g_net_peers.n; ++q) A.peer[q] = g_net_peers.ptr[q];
     A.quality_out = d_quality; A.tie_count = d_ties;
 
     // accumulators (one 16-byte cell per voxel) and per-radar tile lists
@@ -1775,6 +1781,64 @@ namespace {
 int enqueue_columns(const double* d_vol, const double* d_levels, int nz, long long ncol, double fill, double min_dbz,
                     double max_dbz_cap, double threshold, double* d_cr, double* d_vil, double* d_et,
                     unsigned char* d_topped, cudaStream_t st);
+}
+
+// ---- multi-GPU: the finished slab goes straight into every peer's grid --------------------------
+extern "C" int pcg_peer_alloc(size_t bytes, void** dptr, unsigned char* handle64) {
+    if (!dptr || !handle64) return fail(PCG_ERR_ARG, "NULL pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    *dptr = nullptr;
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(PCG_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, *dptr);
+    if (e != cudaSuccess) { cudaFree(*dptr); *dptr = nullptr; return fail(PCG_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+    memcpy(handle64, &h, 64);
+    return PCG_OK;
+}
+
+extern "C" int pcg_peer_open(const unsigned char* handle64, void** dptr) {
+    if (!dptr || !handle64) return fail(PCG_ERR_ARG, "NULL pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PCG_OK;
+}
+
+extern "C" int pcg_peer_close(void* dptr) {
+    if (dptr) CUDA_TRY(cudaIpcCloseMemHandle(dptr));
+    return PCG_OK;
+}
+
+extern "C" int pcg_peer_free(void* dptr) {
+    if (dptr) CUDA_TRY(cudaFree(dptr));
+    return PCG_OK;
+}
+
+extern "C" int pcg_network_compose_gather_dev(int nradar, const pcg_volume* const* vols, const double* radar_x,
+                                              const double* radar_y, const double* radar_height,
+                                              const double* effective_earth_radius, const double* const* beam_widths,
+                                              const pcg_network_params* params, const double* d_grid_x,
+                                              const double* d_grid_y, int nx, int ny, const double* level_heights,
+                                              int nz, double fill, double* d_composite, int16_t* d_valid_count,
+                                              int16_t* d_coverage_count, int8_t* d_blind_mask, double* d_cr,
+                                              int npeer, double* const* peer_full, long long full_rows,
+                                              long long row_offset, void* stream) {
+    if (nx < 0 || ny < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
+    if (npeer < 0 || npeer > kNetMaxPeers) return fail(PCG_ERR_ARG, "npeer must be in [0, %d]", kNetMaxPeers);
+    if (npeer && (!peer_full || row_offset < 0 || row_offset + nx > full_rows))
+        return fail(PCG_ERR_ARG, "slab rows [%lld, %lld) do not fit a grid of %lld rows", row_offset, row_offset + nx, full_rows);
+    std::lock_guard<std::mutex> lock(g_mutex);
+    g_net_peers.n = npeer;
+    g_net_peers.plane = full_rows * (long long)ny;
+    g_net_peers.off = row_offset * (long long)ny;
+    for (int q = 0; q < npeer; ++q) g_net_peers.ptr[q] = peer_full[q];
+    const int rc = enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths,
+                                   params, d_grid_x, d_grid_y, (long long)nx * ny, ny, level_heights, nz, fill,
+                                   d_composite, d_valid_count, d_coverage_count, d_blind_mask, d_cr, nullptr, nullptr,
+                                   (cudaStream_t)stream);
+    g_net_peers.n = 0;
+    return rc;
 }
 
 extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, const double* radar_x,
