@@ -32,11 +32,7 @@ using namespace pcg;
 namespace {
 
 thread_local char g_err[512] = "";
-// device flag the packed kernels raise on NaN / inf target coordinates; set by the host-buffer entry points
-// (under g_mutex) around their launches, NULL otherwise
-int* g_nonfinite_flag = nullptr;
 std::atomic<long long> g_launches{0};
-std::mutex g_mutex;   // guards the scratch arena and the library stream
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -137,22 +133,84 @@ struct DevPool {
 DevPool g_pool;
 
 enum { S_GX = 0, S_GY, S_OUT, S_IDX, S_TMP0, S_TMP1, S_TMP2, S_NET, S_AUX0, S_AUX1, S_AUX2, S_AUX3, S_AUX4, S_ACC0, S_ACC4, S_ACC5, S_ACC6, S_COUNT };
-Scratch g_scratch[S_COUNT];
-cudaStream_t g_stream[16] = {};
+
+constexpr int kMaxDevices = 16;
+constexpr int kNetStreams = 6;
+struct NetStreams {
+    cudaStream_t side[kNetStreams] = {};
+    cudaEvent_t ev_side[kNetStreams] = {};
+    cudaEvent_t ev_class = nullptr;
+    bool ready = false;
+};
+// peers of the next enqueue_network call (set and cleared by pcg_network_compose_gather_dev under the device lock)
+struct NetPeers { int n = 0; long long plane = 0, off = 0; double* ptr[kNetMaxPeers] = {}; };
+
+// Everything a call needs besides its arguments lives in the context of the CURRENT device (cudaSetDevice is
+// per host thread): scratch arena, library stream, table cache, side streams — one host thread per GPU can
+// therefore drive its device without meeting the other threads (the reference fans out over processes,
+// pycwr/interp/RadarInterp.py:1816-1861; here the fan-out is over the GPUs of one box).
+struct DeviceCtx {
+    std::mutex mutex;                   // guards this device's scratch arena, library stream and table cache
+    Scratch scratch[S_COUNT];
+    cudaStream_t stream = nullptr;
+    int* nonfinite_flag = nullptr;      // raised by the packed kernels on NaN / inf targets (host entry points)
+    std::vector<char> net_key;          // what the cached network tables were built from
+    void* net_ptr = nullptr;
+    NetPeers net_peers;
+    NetStreams net_streams;
+    // the last enqueue that used the shared scratch: a following call on ANOTHER stream waits for it
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
+};
+DeviceCtx g_ctx[kMaxDevices];
+
+DeviceCtx& cur_ctx() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return g_ctx[dev];
+}
+#define g_scratch (cur_ctx().scratch)
+#define g_mutex (cur_ctx().mutex)
+#define g_nonfinite_flag (cur_ctx().nonfinite_flag)
+#define g_net_key (cur_ctx().net_key)
+#define g_net_ptr (cur_ctx().net_ptr)
+#define g_net_peers (cur_ctx().net_peers)
+
+// Stream order across calls that share the device's scratch: `st` first waits for the previous enqueue if that
+// ran on a different stream; `scratch_done` marks the end of this one.
+int scratch_begin(cudaStream_t st) {
+    DeviceCtx& c = cur_ctx();
+    if (c.has_last && c.last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, c.ev_last, 0));
+    return PCG_OK;
+}
+int scratch_done(cudaStream_t st) {
+    DeviceCtx& c = cur_ctx();
+    if (!c.ev_last) CUDA_TRY(cudaEventCreateWithFlags(&c.ev_last, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(c.ev_last, st));
+    c.last_stream = st;
+    c.has_last = true;
+    return PCG_OK;
+}
 
 int lib_stream(cudaStream_t* out) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) return fail(PCG_ERR_ARG, "device index %d out of range", dev);
-    if (!g_stream[dev]) CUDA_TRY(cudaStreamCreateWithFlags(&g_stream[dev], cudaStreamNonBlocking));
-    *out = g_stream[dev];
+    if (dev < 0 || dev >= kMaxDevices) return fail(PCG_ERR_ARG, "device index %d out of range", dev);
+    DeviceCtx& c = g_ctx[dev];
+    if (!c.stream) CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    *out = c.stream;
     return PCG_OK;
 }
 
 
 }  // namespace
 
+std::atomic<unsigned long long> g_volume_uid{0};
+
 struct pcg_volume {
+    // never reused, unlike the handle's address: what the network table cache is keyed by
+    unsigned long long uid = ++g_volume_uid;
     int ne = 0;
     int nfield = 0;
     int dtype = PCG_VALUE_F64;
@@ -1088,7 +1146,18 @@ int pcg_volume_create_raw(int ne, const int* naz, const int* ng, const double* c
 
 int pcg_volume_destroy(pcg_volume* v) {
     if (!v) return PCG_OK;
+    // the arenas belong to v->device, whatever device the calling thread happens to be on
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != v->device) cudaSetDevice(v->device);
     cudaDeviceSynchronize();          // nothing may still be reading the arenas when they go back to the pool
+    if (v->device >= 0 && v->device < kMaxDevices) {
+        // cached network tables hold this volume's arena pointers: drop them with it
+        DeviceCtx& c = g_ctx[v->device];
+        std::lock_guard<std::mutex> lock(c.mutex);
+        c.net_key.clear();
+        c.net_ptr = nullptr;
+    }
     g_pool.release(v->d_az);
     g_pool.release(v->d_rng);
     g_pool.release(v->d_sweeps);
@@ -1099,6 +1168,7 @@ int pcg_volume_destroy(pcg_volume* v) {
     g_pool.release(v->d_gt);
     g_pool.release(v->d_ht);
     for (int f = 0; f < kMaxFields; ++f) g_pool.release(v->d_val[f]);
+    if (prev >= 0 && prev != v->device) cudaSetDevice(prev);
     delete v;
     return PCG_OK;
 }
@@ -1440,20 +1510,8 @@ int launch_finalize(const NetArgs& a, const NetAcc& acc, int method, cudaStream_
     return PCG_OK;
 }
 
-constexpr int kNetStreams = 6;
-struct NetStreams {
-    cudaStream_t side[kNetStreams] = {};
-    cudaEvent_t ev_side[kNetStreams] = {};
-    cudaEvent_t ev_class = nullptr;
-    bool ready = false;
-};
-NetStreams g_net_streams[16];
-
 int net_streams(NetStreams** out) {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) return fail(PCG_ERR_ARG, "device index %d out of range", dev);
-    NetStreams& n = g_net_streams[dev];
+    NetStreams& n = cur_ctx().net_streams;
     if (!n.ready) {
         for (int k = 0; k < kNetStreams; ++k) {
             CUDA_TRY(cudaStreamCreateWithFlags(&n.side[k], cudaStreamNonBlocking));
@@ -1468,8 +1526,6 @@ int net_streams(NetStreams** out) {
 
 // d_* pointers are DEVICE pointers; tables are built on the host and uploaded through S_NET.  The blob of
 // the last call is kept: repeated calls with the same radars / geometry / options only launch.
-std::vector<char> g_net_key;
-void* g_net_ptr = nullptr;
 
 template <typename T>
 void key_put(std::vector<char>* key, const T* p, size_t n) {
@@ -1477,9 +1533,6 @@ void key_put(std::vector<char>* key, const T* p, size_t n) {
     key->insert(key->end(), b, b + n * sizeof(T));
 }
 
-// peers of the next enqueue_network call (set and cleared by pcg_network_compose_gather_dev under g_mutex)
-struct NetPeers { int n = 0; long long plane = 0, off = 0; double* ptr[kNetMaxPeers] = {}; };
-NetPeers g_net_peers;
 
 int enqueue_network(int nradar, const pcg_volume* const* vols, const double* radar_x, const double* radar_y,
                     const double* radar_height, const double* re, const double* const* beam_widths,
@@ -1543,7 +1596,8 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     // everything the tables depend on
     std::vector<char> key;
     key_put(&key, &nradar, 1); key_put(&key, &nz, 1); key_put(&key, prm, 1); key_put(&key, &fill, 1);
-    key_put(&key, vols, nradar); key_put(&key, radar_x, nradar); key_put(&key, radar_y, nradar);
+    for (int i = 0; i < nradar; ++i) key_put(&key, &vols[i]->uid, 1);
+    key_put(&key, radar_x, nradar); key_put(&key, radar_y, nradar);
     key_put(&key, radar_height, nradar); key_put(&key, re, nradar); key_put(&key, levels, nz);
     for (int i = 0; i < nradar; ++i) {
         const double* bw = beam_widths ? beam_widths[i] : nullptr;

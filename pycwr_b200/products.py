@@ -306,12 +306,9 @@ def grid_reflectivity_volume_xy(prd, XRange, YRange, level_heights, range_mode=N
     return mode, FILL, level_heights, GridV
 
 
-def volume_column_products(prd, XRange, YRange, level_heights, range_mode=None, blind_method="mask", min_dbz=18.0,
-                           max_dbz_cap=56.0, threshold_dbz=18.0):
-    """CR / VIL / ET / ET_TOPPED planes of one radar: ``_grid_reflectivity_volume_xy`` + ``derive_*`` (NRadar.py:
-    1276-1297,1459-1572) in one device call — the gridded volume never leaves the GPU (``pcg_get_column_products``)."""
+def _column_products_on(prd, GridX, GridY, level_heights, range_mode, blind_method, min_dbz, max_dbz_cap,
+                        threshold_dbz):
     from .runtime import DeviceVolume
-    GridX, GridY = np.meshgrid(XRange, YRange, indexing="ij")
     gx = np.ascontiguousarray(GridX, dtype=np.float64)
     gy = np.ascontiguousarray(GridY, dtype=np.float64)
     levels = np.ascontiguousarray(np.asarray(level_heights, dtype=np.float64).ravel())
@@ -329,27 +326,136 @@ def volume_column_products(prd, XRange, YRange, level_heights, range_mode=None, 
                 G._resolve_blind_code(blind_method), float(min_dbz), float(max_dbz_cap), float(threshold_dbz),
                 _lib.as_ptr(out["CR"]), _lib.as_ptr(out["VIL"]), _lib.as_ptr(out["ET"]), _lib.as_ptr(out["ET_TOPPED"])))
             if rc == _lib.PCG_WARN_NONFINITE:      # NaN / inf targets: the operation-by-operation path decides
-                _, fill, lv, GridV = grid_reflectivity_volume_xy(prd, XRange, YRange, level_heights, range_mode, blind_method)
-                out = column_products(GridV, lv, fill, min_dbz, max_dbz_cap, threshold_dbz)
+                GridV = G.get_CAPPI_3d(None, None, None, dv, h, gx, gy, levels, FILL, prd.effective_earth_radius,
+                                       blind_method)
+                out = column_products(GridV, levels, FILL, min_dbz, max_dbz_cap, threshold_dbz)
     finally:
         if owned:
             dv.close()
     return mode, out
 
 
+def volume_column_products(prd, XRange, YRange, level_heights, range_mode=None, blind_method="mask", min_dbz=18.0,
+                           max_dbz_cap=56.0, threshold_dbz=18.0):
+    """CR / VIL / ET / ET_TOPPED planes of one radar: ``_grid_reflectivity_volume_xy`` + ``derive_*`` (NRadar.py:
+    1276-1297,1459-1572) in one device call — the gridded volume never leaves the GPU (``pcg_get_column_products``)."""
+    GridX, GridY = np.meshgrid(XRange, YRange, indexing="ij")
+    return _column_products_on(prd, GridX, GridY, level_heights, range_mode, blind_method, min_dbz, max_dbz_cap,
+                               threshold_dbz)
+
+
+def grid_reflectivity_volume_lonlat(prd, XLon, YLat, level_heights, range_mode=None, blind_method="mask"):
+    """NRadar.py:1298-1320 (the volume behind add_product_VIL_lonlat / ET_lonlat)."""
+    GridX, GridY = _local_grid(prd, XLon, YLat)
+    level_heights = np.asarray(level_heights, dtype=np.float64)
+    mode, va, vr, fe, vv, h = _volume_of(prd, range_mode)
+    GridV = G.get_CAPPI_3d(va, vr, fe, vv, h, GridX, GridY, level_heights, FILL, prd.effective_earth_radius,
+                           blind_method)
+    return mode, FILL, level_heights, GridV
+
+
+def volume_column_products_lonlat(prd, XLon, YLat, level_heights, range_mode=None, blind_method="mask", min_dbz=18.0,
+                                  max_dbz_cap=56.0, threshold_dbz=18.0):
+    """The lon/lat twin of :func:`volume_column_products` (NRadar.py:1298-1320 + derive_*)."""
+    GridX, GridY = _local_grid(prd, XLon, YLat)
+    return _column_products_on(prd, GridX, GridY, level_heights, range_mode, blind_method, min_dbz, max_dbz_cap,
+                               threshold_dbz)
+
+
+# PRODUCT_REFERENCE_NOTES of pycwr/core/RadarProduct.py:4-13 (attribute payload of the VIL / ET products)
+PRODUCT_REFERENCE_NOTES = {
+    "VIL": [
+        "Greene and Clark (1972), Monthly Weather Review, doi:10.1175/1520-0493(1972)100<0548:VILWNA>2.3.CO;2",
+        "NOAA WDTD VIL product guidance: https://vlab.noaa.gov/web/wdtd/-/vertically-integrated-liquid-vil-",
+    ],
+    "ET": [
+        "Lakshmanan et al. (2013), Weather and Forecasting, doi:10.1175/WAF-D-12-00084.1",
+        "NOAA WDTD xx dBZ Echo Top guidance: https://vlab.noaa.gov/web/wdtd/-/xx-dbz-echo-top-et-",
+        "WSR-88D ROC ICD 2620003Y (Enhanced Echo Tops): https://www.roc.noaa.gov/public-documents/icds/2620003Y.pdf",
+    ],
+}
+
+# what differs between the Cartesian and the lon/lat flavour of a column product: coordinate names and attrs,
+# product-name suffix, standard_name suffix, axis label (NRadar.py:1459-1572 vs :1820-1929)
+_FLAVOUR = {
+    False: {"xc": "x_%s", "yc": "y_%s", "suffix": "", "std": "", "axis": "xy_coordinate",
+            "x": lambda tag: {"units": "meters", "standard_name": "%s_product_x_axis " % tag,
+                              "long_name": "east_distance_from_radar", "axis": "xy_coordinate",
+                              "comment": "Distance from radar in east"},
+            "y": lambda tag: {"units": "meters", "standard_name": "%s_product_y_axis " % tag,
+                              "long_name": "north_distance_from_radar", "axis": "xy_coordinate",
+                              "comment": "Distance from radar in north"}},
+    True: {"xc": "lon_%s", "yc": "lat_%s", "suffix": "_geo", "std": "_lonlat_grid", "axis": "lonlat_coordinate",
+           "x": lambda tag: {"units": "degrees", "standard_name": "%s_product_lon_axis " % tag,
+                             "long_name": "longitude_%s" % tag.lower(), "axis": "lonlat_coordinate"},
+           "y": lambda tag: {"units": "degrees", "standard_name": "%s_product_lat_axis " % tag,
+                             "long_name": "latitude_%s" % tag.lower(), "axis": "lonlat_coordinate"}},
+}
+
+
+def _add_column_product(prd, geo, tag, X, Y, level_heights, range_mode, blind_method, min_dbz=18.0, max_dbz_cap=56.0,
+                        threshold_dbz=18.0):
+    """One of VIL / ET on either grid flavour: the volume is gridded and reduced in one device call
+    (``pcg_get_column_products``) and the planes are written with the reference's names and attrs."""
+    import json
+    fl = _FLAVOUR[bool(geo)]
+    levels = np.asarray(level_heights, dtype=np.float64)
+    call = volume_column_products_lonlat if geo else volume_column_products
+    mode, prod = call(prd, X, Y, levels, range_mode, blind_method, min_dbz, max_dbz_cap, threshold_dbz)
+    xc, yc = fl["xc"] % tag.lower(), fl["yc"] % tag.lower()
+    _set_coord(prd, xc, X, fl["x"](tag))
+    _set_coord(prd, yc, Y, fl["y"](tag))
+    src = json.dumps(levels.tolist())
+    refs = json.dumps(PRODUCT_REFERENCE_NOTES[tag], ensure_ascii=False)
+    if tag == "VIL":
+        _put(prd, prd._product_name("VIL" + fl["suffix"], mode), (xc, yc), prod["VIL"],
+             {"units": "kg m-2", "standard_name": "Vertically_integrated_liquid_water" + fl["std"],
+              "long_name": "Vertically_integrated_liquid_water", "axis": fl["axis"], "source_levels": src,
+              "min_dbz": float(min_dbz), "max_dbz_cap": float(max_dbz_cap), "references": refs})
+        return
+    _put(prd, prd._product_name("ET" + fl["suffix"], mode), (xc, yc), prod["ET"],
+         {"units": "meters", "standard_name": "Echo_top_height" + fl["std"], "long_name": "Echo_top_height",
+          "axis": fl["axis"], "source_levels": src, "threshold_dbz": float(threshold_dbz), "references": refs})
+    _put(prd, prd._product_name("ET_TOPPED" + fl["suffix"], mode), (xc, yc),
+         np.asarray(prod["ET_TOPPED"], dtype=np.uint8),
+         {"units": "1", "standard_name": "Echo_top_topped_flag" + fl["std"], "long_name": "Echo_top_topped_flag",
+          "axis": fl["axis"], "flag_values": np.array([0, 1], dtype=np.uint8),
+          "flag_meanings": "resolved topped_at_highest_sampled_level", "source_levels": src,
+          "threshold_dbz": float(threshold_dbz), "references": refs})
+
+
+def add_product_VIL_xy(prd, XRange, YRange, level_heights, range_mode=None, blind_method="mask", min_dbz=18.0,
+                       max_dbz_cap=56.0):
+    """NRadar.py:1459-1506."""
+    _add_column_product(prd, False, "VIL", XRange, YRange, level_heights, range_mode, blind_method, min_dbz=min_dbz,
+                        max_dbz_cap=max_dbz_cap)
+
+
+def add_product_ET_xy(prd, XRange, YRange, level_heights, range_mode=None, blind_method="mask", threshold_dbz=18.0):
+    """NRadar.py:1508-1572."""
+    _add_column_product(prd, False, "ET", XRange, YRange, level_heights, range_mode, blind_method,
+                        threshold_dbz=threshold_dbz)
+
+
+def add_product_VIL_lonlat(prd, XLon, YLat, level_heights, range_mode=None, blind_method="mask", min_dbz=18.0,
+                           max_dbz_cap=56.0):
+    """NRadar.py:1820-1866."""
+    _add_column_product(prd, True, "VIL", XLon, YLat, level_heights, range_mode, blind_method, min_dbz=min_dbz,
+                        max_dbz_cap=max_dbz_cap)
+
+
+def add_product_ET_lonlat(prd, XLon, YLat, level_heights, range_mode=None, blind_method="mask", threshold_dbz=18.0):
+    """NRadar.py:1868-1929."""
+    _add_column_product(prd, True, "ET", XLon, YLat, level_heights, range_mode, blind_method,
+                        threshold_dbz=threshold_dbz)
+
+
 def add_product_VIL_ET_xy(prd, XRange, YRange, level_heights, range_mode=None, blind_method="mask", min_dbz=18.0,
                           max_dbz_cap=56.0, threshold_dbz=18.0):
-    """VIL, ET and ET_TOPPED of one radar from one gridded volume (NRadar.py:1459-1572): the volume
-    is gridded once and reduced on the device."""
-    mode, prod = volume_column_products(prd, XRange, YRange, level_heights, range_mode, blind_method, min_dbz,
-                                        max_dbz_cap, threshold_dbz)
-    _set_coord(prd, "x_vil", XRange, _X_ATTRS)
-    _set_coord(prd, "y_vil", YRange, _Y_ATTRS)
-    _put(prd, prd._product_name("VIL", mode), ("x_vil", "y_vil"), prod["VIL"], {"units": "kg m-2"})
-    _set_coord(prd, "x_et", XRange, _X_ATTRS)
-    _set_coord(prd, "y_et", YRange, _Y_ATTRS)
-    _put(prd, prd._product_name("ET", mode), ("x_et", "y_et"), prod["ET"], {"units": "m"})
-    _put(prd, prd._product_name("ET_TOPPED", mode), ("x_et", "y_et"), prod["ET_TOPPED"], {"units": "1"})
+    """VIL, ET and ET_TOPPED of one radar from ONE gridded volume (the reference grids it twice, once per
+    ``add_product_VIL_xy`` / ``add_product_ET_xy`` call, NRadar.py:1459-1572); same names and attrs."""
+    add_product_VIL_xy(prd, XRange, YRange, level_heights, range_mode, blind_method, min_dbz, max_dbz_cap)
+    add_product_ET_xy(prd, XRange, YRange, level_heights, range_mode, blind_method, threshold_dbz)
 
 
 def grid_3d_network_xy(radars, XRange, YRange, level_heights, field_name="dBZ", fillvalue=FILL, lon_0=None,
@@ -397,6 +503,11 @@ class B200ProductMixin(object):
     add_product_CR_lonlat = add_product_CR_lonlat
     add_product_CAPPI_lonlat = add_product_CAPPI_lonlat
     _grid_reflectivity_volume_xy = grid_reflectivity_volume_xy
+    _grid_reflectivity_volume_lonlat = grid_reflectivity_volume_lonlat
+    add_product_VIL_xy = add_product_VIL_xy
+    add_product_ET_xy = add_product_ET_xy
+    add_product_VIL_lonlat = add_product_VIL_lonlat
+    add_product_ET_lonlat = add_product_ET_lonlat
 
     @staticmethod
     def _interpolate_ppi_strip_arrays(azimuth, ranges, values, target_azimuth, target_range):

@@ -93,6 +93,9 @@ class DeviceVolume:
         used = ctypes.c_int(0)
         _lib.check(lib.pcg_volume_info(handle, None, None, ctypes.byref(used), None))
         self.value_dtype = "f32" if used.value == _lib.VALUE_F32 else "f64"
+        # the fused network kernels take packed volumes of at most 32 sweeps (kNetMaxSweeps); anything else is
+        # composited through the reference's per-radar flow (interp._network_field_unfused)
+        self.network_ready = self.value_dtype == "f32" and 2 <= int(fix.shape[0]) <= 32
         self.naz = naz
         self.ng = ng
         self.fix_elevation = fix.copy()
