@@ -747,7 +747,7 @@ def run_product(args):
         net = bench_network(args, torch, dist, dev, rank, world)
     others = None
     if args.other_configs and rank == 0 and world == 1:
-        others = [bench_extra_config(c, args, torch, dev) for c in (1, 2) if WORKLOADS[args.workload] != c]
+        others = [bench_extra_config(c, args, torch, dev) for c in (1, 2, 5) if WORKLOADS[args.workload] != c]
     next_rows = bench_next_rows(args) if args.other_configs and rank == 0 and world == 1 else None
 
     if rank != 0:
@@ -823,7 +823,7 @@ def main():
                     help="also run the C4 network composite sharded over the ranks (default)")
     ap.add_argument("--no-network", dest="network", action="store_false")
     ap.add_argument("--no-other-configs", dest="other_configs", action="store_false", default=True,
-                    help="skip the kernel-only timing of C1 / C2 (N = 1 only)")
+                    help="skip the kernel-only timing of C1 / C2 / C5 (N = 1 only)")
     ap.add_argument("--network-radars", type=int, default=32)
     ap.add_argument("--network-scale", type=float, default=1.0, help="1.0 = 3000 x 3000 x 30")
     args = ap.parse_args()

@@ -56,8 +56,11 @@ class ArrayPRD(object):
     ``.vol`` like ``NRadar.PRD`` and caches per ``(field, fill, mode, max_range)`` (``:1938-1941``)."""
 
     def __init__(self, fields, fix_elevation, radar_height, lon=0.0, lat=0.0, beam_width=None,
-                 effective_earth_radius=None):
+                 effective_earth_radius=None, native_fields=None):
         self.fields = fields                     # {name: [(azimuth, ranges, values), ...] in scan order}
+        # native-range copies of a moment (the reference's ``extended_fields``, NRadar.py:669-680): used by
+        # ``range_mode="native"`` when present, else the aligned sweeps serve both modes
+        self.native_fields = dict(native_fields or {})
         self.fix_elevation = np.asarray(fix_elevation, dtype=np.float64)
         self.radar_height = float(radar_height)
         self.lon, self.lat = float(lon), float(lat)
@@ -78,15 +81,25 @@ class ArrayPRD(object):
 
     def _resolve_field_range_mode(self, field_name, range_mode=None):   # NRadar.py:233-235,256-261
         if range_mode is not None:
+            if range_mode not in ("aligned", "native"):
+                raise ValueError("range_mode must be 'aligned' or 'native'.")
             return range_mode
-        return "native" if field_name == "dBZ" else "aligned"
+        return "native" if str(field_name) in ("dBZ", "Zc") else "aligned"
 
-    def get_vol_data(self, field_name="dBZ", fillvalue=FILL, range_mode=None, max_range_km=None):
+    def _sweeps_of(self, field_name, range_mode):
         if field_name not in self.fields:
             raise KeyError(field_name)
+        if range_mode == "native" and field_name in self.native_fields:
+            return self.native_fields[field_name]
+        return self.fields[field_name]
+
+    def get_vol_data(self, field_name="dBZ", fillvalue=FILL, range_mode=None, max_range_km=None):
+        range_mode = self._resolve_field_range_mode(field_name, range_mode=range_mode)
+        max_range_km = None if max_range_km is None else float(max_range_km)
+        sweeps = self._sweeps_of(field_name, range_mode)
         key = (field_name, float(fillvalue), range_mode, max_range_km)
         if key not in self._vol_cache:
-            self._vol_cache[key] = pack_volume(self.fields[field_name], self.fix_elevation, self.radar_height,
+            self._vol_cache[key] = pack_volume(sweeps, self.fix_elevation, self.radar_height,
                                                self.lon, self.lat, fillvalue, max_range_km)
         self.vol = self._vol_cache[key]
         return self.vol
@@ -95,12 +108,13 @@ class ArrayPRD(object):
                           value_dtype="f32"):
         """The device form of ``get_vol_data``: the sweeps go to the GPU as stored (scan order,
         NaN) and are sorted / clipped / fill-marked by the pack kernels; cached per key like ``_vol_cache``."""
-        if field_name not in self.fields:
-            raise KeyError(field_name)
+        range_mode = self._resolve_field_range_mode(field_name, range_mode=range_mode)
+        max_range_km = None if max_range_km is None else float(max_range_km)
+        sweeps = self._sweeps_of(field_name, range_mode)
         key = (field_name, float(fillvalue), range_mode, max_range_km, value_dtype)
         if key not in self._dev_cache:
             from .runtime import DeviceVolume
-            self._dev_cache[key] = DeviceVolume.from_sweeps(self.fields[field_name], self.fix_elevation,
+            self._dev_cache[key] = DeviceVolume.from_sweeps(sweeps, self.fix_elevation,
                                                             fillvalue=fillvalue, value_dtype=value_dtype,
                                                             max_range_km=max_range_km)
         return self._dev_cache[key]
