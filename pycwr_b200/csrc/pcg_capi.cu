@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -21,6 +22,7 @@
 #include "pcg_fast.cuh"
 #include "pcg_kernels.cuh"
 #include "pcg_r2.cuh"
+#include "pcg_r3.cuh"
 #include "pcg_network.cuh"
 #include "pcg_products.cuh"
 #include "pcg_wind.cuh"
@@ -513,6 +515,50 @@ int launch_fast_flags(const R2Args& args, bool uni, bool lazy, dim3 grid, dim3 b
                 : launch_fast_one<NF, EMIT, false, false>(args, grid, block, smem, st);
 }
 
+// kernel v8 (pcg_r3.cuh): eager azimuth tables only (<= 16 sweeps)
+template <int NF, bool EMIT, bool UNI, bool MERGE>
+int launch_r3_one(const R2Args& args, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(cappi3d_r3_kernel<NF, EMIT, UNI, MERGE>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cappi3d_r3_kernel<NF, EMIT, UNI, MERGE><<<grid, block, smem, st>>>(args);
+    return PCG_OK;
+}
+
+template <int NF, bool EMIT>
+int launch_r3_flags(const R2Args& args, bool uni, bool merge, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    if (uni) return merge ? launch_r3_one<NF, EMIT, true, true>(args, grid, block, smem, st)
+                          : launch_r3_one<NF, EMIT, true, false>(args, grid, block, smem, st);
+    return merge ? launch_r3_one<NF, EMIT, false, true>(args, grid, block, smem, st)
+                 : launch_r3_one<NF, EMIT, false, false>(args, grid, block, smem, st);
+}
+
+template <bool EMIT>
+int launch_r3_nf(const R2Args& args, int nf, bool uni, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    const bool merge = args.base.merge_max != 0;
+    int rc;
+    switch (nf) {
+        case 1: rc = launch_r3_flags<1, EMIT>(args, uni, merge, grid, block, smem, st); break;
+        case 2: rc = launch_r3_flags<2, EMIT>(args, uni, merge, grid, block, smem, st); break;
+        case 3: rc = launch_r3_flags<3, EMIT>(args, uni, merge, grid, block, smem, st); break;
+        case 4: rc = launch_r3_flags<4, EMIT>(args, uni, merge, grid, block, smem, st); break;
+        default: return fail(PCG_ERR_ARG, "nfield must be 1..%d", kMaxFields);
+    }
+    if (rc != PCG_OK) return rc;
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return PCG_OK;
+}
+
+// PCG_KERNEL=r2 keeps the v7 kernel (A/B runs); default: v8 wherever it applies
+bool use_r3_kernel() {
+    static const int choice = [] {
+        const char* e = getenv("PCG_KERNEL");
+        return (e && strcmp(e, "r2") == 0) ? 0 : 1;
+    }();
+    return choice != 0;
+}
+
 template <bool EMIT>
 int launch_fast_nf(const R2Args& args, int nf, bool uni, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
     const bool lazy = args.lazy_az != 0;
@@ -602,11 +648,13 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     const size_t fixed = (size_t)vol->ne * (sizeof(SweepDesc) + sizeof(FastSweep)) + (size_t)(vol->ne - 1) * sizeof(PairDesc);
     // azimuth brackets: a [sweep] table per column up to 16 sweeps, on demand (2-entry cache) beyond
     RA.lazy_az = vol->ne > 16 ? 1 : 0;
+    const bool r3 = !RA.lazy_az && use_r3_kernel();
     const size_t per_thread = RA.lazy_az ? 2 * (sizeof(AzEntry) + sizeof(int) + (d_idx ? sizeof(int) : 0))
                                          : (size_t)vol->ne * (sizeof(AzEntry) + (d_idx ? sizeof(int) : 0));
     int threads = 256;
-    while (threads > 32 && fixed + per_thread * threads > 56 * 1024) threads >>= 1;
-    const size_t smem = fixed + per_thread * threads;
+    const size_t fixed_all = fixed + (r3 ? (size_t)vol->ne * sizeof(AzDesc) : 0);
+    while (threads > 32 && fixed_all + per_thread * threads > 56 * 1024) threads >>= 1;
+    const size_t smem = fixed_all + per_thread * threads;
     const dim3 block(threads);
     // block tile: (warps/2 ... ) see cappi3d_r2_kernel: tile_y = 4 warps x PY columns, tile_x = rest
     const int PY = 1 << A.grid.py_log2, PX = 32 / PY, warps = threads / 32;
@@ -623,8 +671,12 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
         RA.r2.lp = reinterpret_cast<const LevelPair*>(d_ls) + (size_t)z0 * (2 * ne + 3);
         A.out = d_out + (size_t)z0 * (size_t)ncol;
         A.idx = d_idx ? d_idx + (size_t)z0 * (size_t)ncol * kIdxStride : nullptr;
-        rc = d_idx ? launch_fast_nf<true>(RA, nfield, vol->uniform, grid, block, smem, st)
-                   : launch_fast_nf<false>(RA, nfield, vol->uniform, grid, block, smem, st);
+        if (r3)
+            rc = d_idx ? launch_r3_nf<true>(RA, nfield, vol->uniform, grid, block, smem, st)
+                       : launch_r3_nf<false>(RA, nfield, vol->uniform, grid, block, smem, st);
+        else
+            rc = d_idx ? launch_fast_nf<true>(RA, nfield, vol->uniform, grid, block, smem, st)
+                       : launch_fast_nf<false>(RA, nfield, vol->uniform, grid, block, smem, st);
     }
     return rc;
 }

@@ -1,0 +1,422 @@
+// pcg_r3.cuh — kernel v8 of get_CAPPI_3d: the r2-space voxel path of pcg_r2.cuh with level-to-level reuse.
+//
+// Along a grid column the slant range and the elevation grow monotonically with the level, so consecutive
+// levels mostly fall between the same two sweeps AND between the same two gates (measured on config C3: 81 % keep
+// their sweep pair, 63 % their sweep pair and gate).  The reference re-derives everything per voxel
+// (RadarGridC.pyx:404-477); v7 (pcg_r2.cuh) still re-issued, per voxel, the gate-threshold gather, two 128-bit
+// quad gathers, the azimuth entries and four azimuth lerps.  Here a thread keeps, across levels,
+//   * the gate band [tg[j], tg[j+1]) of its current bracket as two doubles: `r2` inside it <=> same gate (exact,
+//     the very comparison v7 made after its gather), and
+//   * the four azimuth-interpolated samples of both sweeps at that gate pair,
+// and only the lanes that left their band redo the gathers (predicated: fewer active lanes per request, fewer
+// L1 wavefronts).  What every voxel still pays is r2, the sweep-pair confirmation, the two FP32 weights and three
+// lerps.  The quads are resolved against missing data in RANGE as well at pack time (pack_quads_kernel), so
+// the range lerp needs no fill test: a quad is either all-fill or fill-free.
+//
+// Also new against v7: azimuth table [sweep][thread] (conflict-free shared-memory reads), a straight-line
+// azimuth bracket for interior guesses, the slow path takes its arguments by value (the hot loop holds no
+// ColumnCtx, hence no local memory), merge-max as a template parameter.
+#pragma once
+#include "pcg_r2.cuh"
+
+namespace pcg {
+
+struct AzDesc {                   // what the azimuth prologue needs of a sweep: 32 bytes, two 128-bit loads
+    double az_first, az_inv_step;
+    unsigned az_off;
+    int naz;
+    unsigned val_off;
+    int ng;
+};
+
+// general azimuth bracket (ends of the table, wrap, repairs, irregular tables): out of line
+__device__ __noinline__ void az_bracket_general(const SweepDesc* d, const double2* azt, double az, AzEntry* e, int* rec) {
+    AzEntry ee;
+    int rr;
+    az_bracket_one(*d, azt, az, ee, rr);
+    *e = ee;
+    *rec = rr;
+}
+
+// the reference chain for one voxel, everything by value (rare: guard bands, flagged levels, ragged or degenerate
+// tables, range gating / clamping, wrong gate guesses)
+struct SlowArgs {
+    const SweepDesc* s_sw;
+    const PairDesc* s_pr;
+    const AzEntry* my_az;
+    const int* my_iaz;
+    const double2* rg_t;
+    const void* const* val;
+    unsigned az_stride;
+    int ne;
+    double a2, twoa, guard, inv_twoa;
+    float fill32;
+    int blind;                    // bit 0 nearest_gate, 1 lowest_sweep, 2 highest_sweep
+};
+
+template <int NF, bool EMIT>
+__device__ __noinline__ void r3_slow_voxel(const SlowArgs* a, const LevelConst* lc, double cphi, int* k6, float* res,
+                                           VoxelInfo* vi) {
+    ColumnCtx c;
+    c.s_sw = a->s_sw; c.s_pr = a->s_pr; c.my_az = a->my_az; c.my_iaz = a->my_iaz; c.az_stride = a->az_stride;
+    c.ne = a->ne; c.rg_t = a->rg_t; c.a2 = a->a2; c.twoa = a->twoa; c.guard = a->guard; c.inv_twoa = a->inv_twoa;
+    c.fill32 = a->fill32;
+    c.nearest_gate = (a->blind & 1) != 0; c.lowest_sweep = (a->blind & 2) != 0; c.highest_sweep = (a->blind & 4) != 0;
+    c.my_tag = nullptr; c.azt = nullptr; c.az = 0.0;
+    float tmp[NF];
+    int k = *k6;
+    VoxelInfo v;
+    fast_voxel<NF, EMIT, false>(c, a->val, *lc, cphi, k, tmp, v);
+    *k6 = k;
+    *vi = v;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) res[f] = tmp[f];
+}
+
+#ifndef R3_MINB
+#define R3_MINB 4
+#endif
+// Loop-invariant kernel parameters the level loop reads: held in registers (an opaque asm keeps the compiler from
+// re-materialising them from the constant bank on every level, one issue slot each).  -DR3_NOPIN: leave it to ptxas.
+#ifndef R3_NOPIN
+// (adding a run-time zero ptxas cannot prove to be zero: an empty asm, a mov or a self-shuffle are all seen through)
+__device__ __forceinline__ float r3_pin(float v, int z) { return __int_as_float(__float_as_int(v) + z); }
+__device__ __forceinline__ int r3_pin(int v, int z) { return v + z; }
+__device__ __forceinline__ unsigned r3_pin(unsigned v, int z) { return v + (unsigned)z; }
+template <typename T>
+__device__ __forceinline__ const T* r3_pin(const T* v, int z) {
+    return reinterpret_cast<const T*>(reinterpret_cast<const char*>(v) + z);
+}
+#define R3_PIN(x) x = r3_pin(x, pin_zero)
+#else
+#define R3_PIN(x)
+#endif
+
+// shared-memory reads of the level loop through 32-bit shared addresses held in registers (the compiler would
+// otherwise rebuild the carve-up offsets from `ne` at every use)
+__device__ __forceinline__ AzEntry lds_az(unsigned addr) {
+    AzEntry e;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.row), "=f"(e.w) : "r"(addr) : "memory");
+    return e;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_f(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int NF, bool EMIT, bool UNI, bool MERGE>
+__global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_constant__ R2Args P) {
+    const FastArgs& p = P.base;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ne = p.vol.ne;
+    const unsigned T = blockDim.x;
+    SweepDesc* s_sw = reinterpret_cast<SweepDesc*>(smem_raw);
+    PairDesc* s_pr = reinterpret_cast<PairDesc*>(s_sw + ne);
+    FastSweep* s_fs = reinterpret_cast<FastSweep*>(s_pr + (ne - 1));
+    AzDesc* s_ad = reinterpret_cast<AzDesc*>(s_fs + ne);
+    AzEntry* s_az = reinterpret_cast<AzEntry*>(s_ad + ne);                 // [sweep][thread]
+    int* s_iaz = reinterpret_cast<int*>(s_az + (size_t)ne * T);            // EMIT only, [sweep][thread]
+    stage_sweeps(s_sw, p.vol.sweeps, ne);
+    stage_pairs(s_pr, p.pairs, ne - 1, p.twoa);
+    {
+        const int words = ne * (int)(sizeof(FastSweep) / sizeof(int));
+        const int* src = reinterpret_cast<const int*>(P.r2.fs);
+        int* dst = reinterpret_cast<int*>(s_fs);
+        for (int i = threadIdx.x; i < words; i += T) dst[i] = src[i];
+        for (int i = threadIdx.x; i < ne; i += T) {
+            const SweepDesc d = p.vol.sweeps[i];
+            AzDesc a;
+            a.az_first = d.az_first; a.az_inv_step = d.az_inv_step; a.az_off = d.az_off;
+            a.naz = (d.naz >= 2 && d.ng >= 2) ? d.naz : 0;                 // 0: degenerate, general path
+            a.val_off = (unsigned)d.val_off; a.ng = d.ng;
+            s_ad[i] = a;
+        }
+    }
+    __syncthreads();
+
+    const long long ncol = p.grid.ncol;
+    long long col;
+    {
+        const int pyl = p.grid.py_log2;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = T >> 5;
+        const int wy = nwarp >= 4 ? 4 : nwarp;
+        const int ly = lane & ((1 << pyl) - 1), lx = lane >> pyl;
+        const int by = blockIdx.x % p.grid.tiles_y, bx = blockIdx.x / p.grid.tiles_y;
+        const int iy = ((by * wy + (warp % wy)) << pyl) + ly;
+        const int ix = (bx * (nwarp / wy) + (warp / wy)) * (32 >> pyl) + lx;
+        if (ix >= p.grid.nx || iy >= p.grid.ny) return;
+        col = (long long)ix * p.grid.ny + iy;
+    }
+
+    double x = p.grid.gx[col], y = p.grid.gy[col];
+    if (p.grid.shift) { x = sub(x, p.grid.radar_x); y = sub(y, p.grid.radar_y); }
+    // column invariants (RadarGridC.pyx:142-146,158)
+    const double s = sqrt_rn(add(mul(x, x), mul(y, y)));
+    if (P.nonfinite && !(s < __longlong_as_double(0x7ff0000000000000LL))) *P.nonfinite = 1;
+    const double cphi = cos_small(div(s, p.Re));
+    AzEntry* my_az = s_az + threadIdx.x;
+    int* my_iaz = s_iaz + threadIdx.x;
+    {
+        // the column's azimuth bracket of every sweep (RadarGridC.pyx:282-289): interior guesses verified in
+        // line against the two entries they bracket, anything else through the general routine
+        const double az = azimuth_from_xy(x, y);
+        const double2* __restrict__ azt = P.r2.az_t;
+#pragma unroll 1
+        for (int sw = 0; sw < ne; ++sw) {
+            const AzDesc d = s_ad[sw];
+            const int g = __double2int_rd(mul(sub(az, d.az_first), d.az_inv_step)) + 1;
+            AzEntry e;
+            int rec;
+            bool done = false;
+            if (g >= 1 && g < d.naz) {
+                const double2* Tt = azt + d.az_off + (unsigned)(g - 1);
+                const double2 lo = __ldg(Tt);
+                const double hi = __ldg(&Tt[1].x);
+                if (!(az < lo.x) && (az < hi)) {
+                    e.row = d.val_off + (unsigned)(g - 1) * (unsigned)d.ng;
+                    e.w = (float)sub(az, lo.x) * (float)lo.y;
+                    rec = g;
+                    done = true;
+                }
+            }
+            if (!done) az_bracket_general(s_sw + sw, azt, az, &e, &rec);
+            my_az[(size_t)sw * T] = e;
+            if (EMIT) my_iaz[(size_t)sw * T] = rec;
+        }
+    }
+
+    float fill32 = p.fill32, inv2a = P.r2.inv2a;
+    float u_inv_step = P.r2.u_inv_step, u_c0 = P.r2.u_c0, u_step = P.r2.u_step, u_r_first = P.r2.u_r_first;
+    int u_ngm1 = P.r2.u_ngm1;
+    unsigned u_rng_off = P.r2.u_rng_off;
+    const double2* g_t = P.r2.g_t;
+    const float4* val0 = static_cast<const float4*>(p.vol.val[0]);
+    const bool lowest_sweep = p.lowest_sweep != 0, highest_sweep = p.highest_sweep != 0;
+    // blind-zone rules (RadarGridC.pyx:424-433) as one window test on k: sampled iff k_first <= k <= k_last
+    int k_first = lowest_sweep ? -1 : 0;
+    unsigned k_span = (unsigned)((highest_sweep ? ne - 1 : ne - 2) - k_first);
+    unsigned row_bytes = (unsigned)(2 * ne + 3) * 32u;     // one level row: [LevelPair x (ne+1)][LevelSweep x (ne+2)]
+    unsigned ls_off = (unsigned)(ne + 1) * 32u;            // the LevelSweep half of a row
+    unsigned pair_top = (unsigned)(ne - 1);                // k < pair_top (unsigned): between two sweeps
+    unsigned az_addr = (unsigned)__cvta_generic_to_shared(my_az), az_pitch = T * (unsigned)sizeof(AzEntry);
+    unsigned fs_addr = (unsigned)__cvta_generic_to_shared(&s_fs[0].q1);
+    {
+        const int pin_zero = (int)((unsigned long long)clock64() >> 63);     // 0, unknown to the compiler
+        (void)pin_zero;
+        R3_PIN(fill32); R3_PIN(inv2a); R3_PIN(g_t); R3_PIN(val0);
+        R3_PIN(k_first); R3_PIN(k_span); R3_PIN(row_bytes); R3_PIN(ls_off); R3_PIN(pair_top);
+        R3_PIN(az_addr); R3_PIN(az_pitch); R3_PIN(fs_addr);
+        if (UNI) { R3_PIN(u_inv_step); R3_PIN(u_c0); R3_PIN(u_step); R3_PIN(u_r_first); R3_PIN(u_ngm1); R3_PIN(u_rng_off); }
+    }
+    const char* lrow = reinterpret_cast<const char*>(P.r2.lp);   // this level's row (block-uniform)
+    int k = -1, k6 = 0;
+    // the cached bracket: gate band in r2 space (empty = nothing cached), R[j], 1 / dR, the azimuth-lerped samples
+    double c_lo = __longlong_as_double(0x7ff0000000000000LL), c_hi = 0.0;
+    float c_rj = 0.f, c_idr = UNI ? u_inv_step : 0.f;
+    int c_gi = 0;
+    float ca0[NF], ca1[NF], cb0[NF], cb1[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) { ca0[f] = ca1[f] = cb0[f] = cb1[f] = fill32; }
+    char* out_b = reinterpret_cast<char*>(p.out + col);
+    const size_t lvl_bytes = (size_t)ncol * sizeof(double);
+    // levels whose voxel needs the reference chain are only MARKED here and resolved after the loop: the hot
+    // loop then contains no call, so its state stays in registers (kMaxLevelsPerLaunch <= 64)
+    unsigned long long slow_mask = 0ull;
+
+#pragma unroll 1
+    for (int iz = 0; iz < p.nz; ++iz, lrow += row_bytes, out_b += lvl_bytes) {
+        float res[NF];
+        int st_state = kEmpty, st_lower = -1, st_upper = -1, r_iaz0 = -1, r_ir0 = -1, r_fl0 = -1, r_iaz1 = -1, r_ir1 = -1,
+            r_fl1 = -1;
+        // RadarGridC.pyx:146-149 — the reference's own operations: r2 is bit-identical
+        const double r2 = sub(p.levels[iz].a2g2, mul(p.levels[iz].twoag, cphi));
+        bool slow = false;
+        {
+            const double2 cf = __ldg(reinterpret_cast<const double2*>(lrow + (unsigned)(k + 1) * 32u));
+            if (!((r2 < cf.x) & (r2 > cf.y))) {
+                // the column left its sweep pair: walk the per-sweep bands (pcg_r2.cuh), drop the cached bracket
+                const char* ls = lrow + ls_off;
+                c_lo = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll 1
+                for (;;) {
+                    const double2* row = reinterpret_cast<const double2*>(ls + (unsigned)(k + 1) * 32u);
+                    const double2 cur = __ldg(row);
+                    const double2 nxt = __ldg(row + 2);
+                    if ((r2 < cur.x) & (r2 > nxt.y)) break;
+                    if (r2 > cur.y) { --k; continue; }
+                    if (r2 < nxt.x) { ++k; continue; }
+                    slow = true;
+                    break;
+                }
+            }
+        }
+        if (!slow) {
+            const bool pair = (unsigned)k < pair_top;
+            const bool skip = (unsigned)(k - k_first) > k_span;
+            const int lower = max(k, 0);
+            if (EMIT) {
+                st_state = skip ? (pair ? kPair : (k < 0 ? kSkipLow : kSkipHigh)) : (pair ? kPair : kSingle);
+                st_lower = lower; st_upper = lower + (pair ? 1 : 0);
+            }
+            if (skip) {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) res[f] = fill32;
+            } else {
+                const float r2f = (float)r2;
+                const float rinv = rsqrt_approx(r2f);
+                const float rf = r2f * rinv;
+                if (!((r2 >= c_lo) & (r2 < c_hi))) {
+                    // ---- new gate (or new sweep pair): bracket, gather, azimuth lerps ----
+                    const FastSweep* f = s_fs + lower;
+                    unsigned rng_off = u_rng_off;
+                    int ngm1 = u_ngm1;
+                    float inv_step = u_inv_step, c0 = u_c0;
+                    bool usable = true;
+                    if (!UNI) {
+                        const int4 tab = *reinterpret_cast<const int4*>(&f->rng_off);
+                        rng_off = (unsigned)tab.x; ngm1 = tab.y; c0 = __int_as_float(tab.z); inv_step = __int_as_float(tab.w);
+                        const int need = pair ? (kFsPolyOk | kFsShared | kFsUsable) : kFsUsable;
+                        usable = (f->flags & need) == need;
+                    }
+                    const int gi = usable ? min(max(__float2int_rd(fmaf(rf, inv_step, c0)), 1), ngm1) : 1;
+                    const unsigned gidx = usable ? rng_off + (unsigned)(gi - 1) : u_rng_off;
+                    const double2 tg = __ldg(g_t + gidx);        // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
+                    if (usable & (r2 >= tg.x) & (r2 < tg.y)) {
+                        c_lo = tg.x; c_hi = tg.y;
+                        if (UNI) {
+                            c_rj = fmaf((float)(gi - 1), u_step, u_r_first);
+                        } else {
+                            const int4 hv = __ldg(reinterpret_cast<const int4*>(P.r2.h_t + gidx));   // {R^2, R, 1/dR}
+                            c_rj = __int_as_float(hv.z); c_idr = __int_as_float(hv.w);
+                        }
+                        if (EMIT) c_gi = gi;
+                        const AzEntry ea = lds_az(az_addr + (unsigned)lower * az_pitch);
+#pragma unroll
+                        for (int fi = 0; fi < NF; ++fi) {
+                            const float4 q = __ldg((fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi])) + (ea.row + (unsigned)gi));
+                            ca0[fi] = fmaf(ea.w, q.y - q.x, q.x);
+                            ca1[fi] = fmaf(ea.w, q.w - q.z, q.z);
+                        }
+                        if (pair) {
+                            const AzEntry eb = lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
+#pragma unroll
+                            for (int fi = 0; fi < NF; ++fi) {
+                                const float4 q = __ldg((fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi])) + (eb.row + (unsigned)gi));
+                                cb0[fi] = fmaf(eb.w, q.y - q.x, q.x);
+                                cb1[fi] = fmaf(eb.w, q.w - q.z, q.z);
+                            }
+                        }
+                    } else {
+                        slow = true;
+                    }
+                }
+                if (!slow) {
+                    // ---- every voxel: the two weights and three lerps (RadarGridC.pyx:297-299,469-476) ----
+                    // tg[j] is R[j]^2 to within two ulps: w_r = (r^2 - R[j]^2) / ((r + R[j]) dR)
+                    const float w_r = (float)sub(r2, c_lo) * c_idr * rcp_approx(rf + c_rj);
+                    if (pair) {
+                        const int4 lk = __ldg(reinterpret_cast<const int4*>(lrow + (unsigned)(k + 1) * 32u) + 1);   // {rho2, rho, b1}
+                        const float u = (float)sub(r2, __hiloint2double(lk.y, lk.x)) * rcp_approx(rf + __int_as_float(lk.z)) *
+                                        fmaf(__int_as_float(lk.w), rinv, inv2a);
+                        const unsigned fa = fs_addr + (unsigned)lower * (unsigned)sizeof(FastSweep);
+                        const float4 qa = lds_f4(fa);                 // q1 .. q4
+                        float w_el = fmaf(lds_f(fa + 16u), u, qa.w);  // q5
+                        w_el = fmaf(w_el, u, qa.z);
+                        w_el = fmaf(w_el, u, qa.y);
+                        w_el = fmaf(w_el, u, qa.x);
+                        w_el *= u;
+#pragma unroll
+                        for (int fi = 0; fi < NF; ++fi) {
+                            const float v0 = fmaf(w_r, ca1[fi] - ca0[fi], ca0[fi]);
+                            const float v1 = fmaf(w_r, cb1[fi] - cb0[fi], cb0[fi]);
+                            res[fi] = lerp_fill(w_el, v0, v1, fill32);
+                        }
+                    } else {
+#pragma unroll
+                        for (int fi = 0; fi < NF; ++fi) res[fi] = fmaf(w_r, ca1[fi] - ca0[fi], ca0[fi]);
+                    }
+                    if (EMIT) {
+                        const int ra = my_iaz[(size_t)lower * T];
+                        r_ir0 = c_gi; r_iaz0 = ra & 0x3fffffff; r_fl0 = (ra >> 30) & 1;
+                        if (pair) {
+                            const int rb2 = my_iaz[(size_t)(lower + 1) * T];
+                            r_ir1 = c_gi; r_iaz1 = rb2 & 0x3fffffff; r_fl1 = (rb2 >> 30) & 1;
+                        }
+                    }
+                }
+            }
+        }
+        if (slow) { slow_mask |= 1ull << iz; continue; }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            double* dst = reinterpret_cast<double*>(out_b) + (size_t)f * (size_t)p.field_stride;
+            // the fill value is float-representable (checked on the host), so widening res restores it
+            const double v = (double)res[f];
+            if (MERGE) {
+                if (res[f] != fill32) {
+                    const double cur = *dst;
+                    if (cur == p.fill || v > cur) *dst = v;
+                }
+            } else {
+                *dst = v;
+            }
+        }
+        if (EMIT) {
+            int32_t* rec = p.idx + ((size_t)iz * (size_t)ncol + (size_t)col) * kIdxStride;
+            const bool have0 = (st_state == kSingle || st_state == kPair), have1 = (st_state == kPair);
+            rec[0] = st_state;
+            rec[1] = have0 ? st_lower : -1; rec[2] = have0 ? st_upper : -1;
+            rec[3] = have0 ? r_iaz0 : -1; rec[4] = have0 ? r_ir0 : -1; rec[5] = have0 ? r_fl0 : -1;
+            rec[6] = have1 ? r_iaz1 : -1; rec[7] = have1 ? r_ir1 : -1; rec[8] = have1 ? r_fl1 : -1;
+            rec[9] = -1;
+        }
+    }
+
+    // ---- the marked voxels: the reference's own chain (guard band, flagged level, r2 <= 0, ragged or degenerate
+    //      tables, range gating / clamping, gate guess off), pcg_fast.cuh fast_voxel ----
+    if (slow_mask) {
+        SlowArgs sa;
+        sa.s_sw = s_sw; sa.s_pr = s_pr; sa.my_az = my_az; sa.my_iaz = EMIT ? my_iaz : nullptr;
+        sa.rg_t = reinterpret_cast<const double2*>(p.vol.rng); sa.val = p.vol.val; sa.az_stride = T; sa.ne = ne;
+        sa.a2 = p.a2; sa.twoa = p.twoa; sa.guard = p.guard; sa.inv_twoa = p.inv_twoa; sa.fill32 = fill32;
+        sa.blind = (p.nearest_gate != 0 ? 1 : 0) | (lowest_sweep ? 2 : 0) | (highest_sweep ? 4 : 0);
+#pragma unroll 1
+        while (slow_mask) {
+            const int iz = __ffsll((long long)slow_mask) - 1;
+            slow_mask &= slow_mask - 1;
+            VoxelInfo vi;
+            float tmp[NF];
+            r3_slow_voxel<NF, EMIT>(&sa, &p.levels[iz], cphi, &k6, tmp, &vi);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                double* dst = p.out + (size_t)f * (size_t)p.field_stride + (size_t)iz * (size_t)ncol + (size_t)col;
+                const double v = (double)tmp[f];
+                if (MERGE) {
+                    if (tmp[f] != fill32) {
+                        const double cur = *dst;
+                        if (cur == p.fill || v > cur) *dst = v;
+                    }
+                } else {
+                    *dst = v;
+                }
+            }
+            if (EMIT) {
+                int32_t* rec = p.idx + ((size_t)iz * (size_t)ncol + (size_t)col) * kIdxStride;
+                const bool have0 = (vi.state == kSingle || vi.state == kPair), have1 = (vi.state == kPair);
+                rec[0] = vi.state;
+                rec[1] = have0 ? vi.lower : -1; rec[2] = have0 ? vi.upper : -1;
+                rec[3] = have0 ? vi.iaz0 : -1; rec[4] = have0 ? vi.ir0 : -1; rec[5] = have0 ? vi.fl0 : -1;
+                rec[6] = have1 ? vi.iaz1 : -1; rec[7] = have1 ? vi.ir1 : -1; rec[8] = have1 ? vi.fl1 : -1;
+                rec[9] = -1;
+            }
+        }
+    }
+}
+
+}  // namespace pcg
