@@ -202,6 +202,22 @@ int pcg_network_compose_ex(int nradar, const pcg_volume *const *vols, const doub
                            double *composite, int16_t *valid_count, int16_t *coverage_count,
                            int8_t *blind_mask, double *cr, double *quality, uint64_t *tie_voxels,
                            const double *column_params, double *vil, double *et, unsigned char *et_topped);
+/* pcg_network_compose_ex for rows [row_offset, row_offset + nrows) of a grid of full_rows rows: grid_x / grid_y and
+ * every output are the FULL host arrays ([full_rows][ny] planes, [nz][full_rows][ny] volumes); only the slab's rows
+ * are uploaded, composited and written.  One host thread per GPU (pcg_set_device is per thread; all library state is
+ * per device) calls it for its slab with the radars that reach the slab, so the GPUs of a box fill one product over
+ * their own PCIe links — the device form of the reference's fork pool over radars
+ * (`pycwr/interp/RadarInterp.py:1816-1861`; SURVEY 8e "D2H-copying each slab from its own GPU").  The slab's rows of
+ * the result are bit-identical to the same rows of the unsharded call. */
+int pcg_network_compose_rows(int nradar, const pcg_volume *const *vols, const double *radar_x,
+                             const double *radar_y, const double *radar_height,
+                             const double *effective_earth_radius, const double *const *beam_widths,
+                             const pcg_network_params *params, const double *grid_x, const double *grid_y,
+                             long long full_rows, long long row_offset, int nrows, int ny,
+                             const double *level_heights, int nz, double fill, double out_missing,
+                             double *composite, int16_t *valid_count, int16_t *coverage_count,
+                             int8_t *blind_mask, double *cr, uint64_t *tie_voxels,
+                             const double *column_params, double *vil, double *et, unsigned char *et_topped);
 int pcg_network_compose_dev(int nradar, const pcg_volume *const *vols, const double *radar_x,
                             const double *radar_y, const double *radar_height,
                             const double *effective_earth_radius, const double *const *beam_widths,

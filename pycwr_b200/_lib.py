@@ -5,6 +5,7 @@ points fail loudly — there is no CPU fallback.
 """
 import ctypes
 import os
+import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # PYCWR_B200_LIB selects another build of the same library (kernel tuning variants)
@@ -54,6 +55,10 @@ SIGNATURES = {
     "pcg_network_compose_ex": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_pp, _vp,
                                     _vp, _vp, _i, _i, c_double_p, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp,
                                     ctypes.POINTER(ctypes.c_uint64), c_double_p, _vp, _vp, _vp]),
+    "pcg_network_compose_rows": (_i, [_i, c_void_pp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_pp, _vp,
+                                      _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _i, _i, c_double_p, _i, _d, _d,
+                                      _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_uint64), c_double_p, _vp, _vp,
+                                      _vp]),
     "pcg_peer_alloc": (_i, [ctypes.c_size_t, c_void_pp, _vp]),
     "pcg_peer_open": (_i, [_vp, c_void_pp]),
     "pcg_peer_close": (_i, [_vp]),
@@ -137,6 +142,21 @@ def device_count():
 
 def launch_count():
     return int(load().pcg_launch_count())
+
+
+_tls = threading.local()
+
+
+def set_device(device):
+    """``pcg_set_device`` for the calling thread (CUDA's current device is per host thread; all library state
+    is per device, so one thread per GPU can drive the GPUs of a box side by side)."""
+    check(load().pcg_set_device(int(device)))
+    _tls.device = int(device)
+
+
+def current_device():
+    """The device this thread last selected through :func:`set_device` (0 before any call)."""
+    return getattr(_tls, "device", 0)
 
 
 def as_ptr(arr):

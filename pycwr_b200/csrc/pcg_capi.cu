@@ -13,6 +13,7 @@
 
 #include <atomic>
 #include <map>
+#include <memory>
 #include <unordered_map>
 #include <mutex>
 #include <new>
@@ -24,6 +25,7 @@
 #include "pcg_r2.cuh"
 #include "pcg_r3.cuh"
 #include "pcg_network.cuh"
+#include "pcg_net2.cuh"
 #include "pcg_products.cuh"
 #include "pcg_wind.cuh"
 #include "pcg_section.cuh"
@@ -231,6 +233,8 @@ struct pcg_volume {
     mutable std::vector<double> ls_key;
     mutable LevelSweep* d_ls = nullptr;      // followed in the same allocation by the LevelPair table
     mutable std::vector<unsigned char> ls_slow;
+    mutable std::vector<LevelSweep> ls_host;  // host copy of the same table (rows go into the kernel parameters)
+    std::vector<FastSweep> fs_host;           // host copy of d_fs (pair polynomials go into the kernel parameters)
     bool uniform = false;            // one range table shared by every sweep, every sweep / pair usable + validated
     unsigned uni_rng_off = 0;
     int uni_ngm1 = 0;
@@ -516,32 +520,38 @@ int launch_fast_flags(const R2Args& args, bool uni, bool lazy, dim3 grid, dim3 b
 }
 
 // kernel v8 (pcg_r3.cuh): eager azimuth tables only (<= 16 sweeps)
-template <int NF, bool EMIT, bool UNI, bool MERGE>
-int launch_r3_one(const R2Args& args, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+template <int NF, bool EMIT, bool UNI, bool MERGE, bool CT>
+int launch_r3_one(const R3Args& args, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024)
-        CUDA_TRY(cudaFuncSetAttribute(cappi3d_r3_kernel<NF, EMIT, UNI, MERGE>,
+        CUDA_TRY(cudaFuncSetAttribute(cappi3d_r3_kernel<NF, EMIT, UNI, MERGE, CT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cappi3d_r3_kernel<NF, EMIT, UNI, MERGE><<<grid, block, smem, st>>>(args);
+    cappi3d_r3_kernel<NF, EMIT, UNI, MERGE, CT><<<grid, block, smem, st>>>(args);
     return PCG_OK;
 }
 
+template <int NF, bool EMIT, bool CT>
+int launch_r3_flags(const R3Args& args, bool uni, bool merge, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    if (uni) return merge ? launch_r3_one<NF, EMIT, true, true, CT>(args, grid, block, smem, st)
+                          : launch_r3_one<NF, EMIT, true, false, CT>(args, grid, block, smem, st);
+    return merge ? launch_r3_one<NF, EMIT, false, true, CT>(args, grid, block, smem, st)
+                 : launch_r3_one<NF, EMIT, false, false, CT>(args, grid, block, smem, st);
+}
+
 template <int NF, bool EMIT>
-int launch_r3_flags(const R2Args& args, bool uni, bool merge, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
-    if (uni) return merge ? launch_r3_one<NF, EMIT, true, true>(args, grid, block, smem, st)
-                          : launch_r3_one<NF, EMIT, true, false>(args, grid, block, smem, st);
-    return merge ? launch_r3_one<NF, EMIT, false, true>(args, grid, block, smem, st)
-                 : launch_r3_one<NF, EMIT, false, false>(args, grid, block, smem, st);
+int launch_r3_ct(const R3Args& args, bool ct, bool uni, bool merge, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    return ct ? launch_r3_flags<NF, EMIT, true>(args, uni, merge, grid, block, smem, st)
+              : launch_r3_flags<NF, EMIT, false>(args, uni, merge, grid, block, smem, st);
 }
 
 template <bool EMIT>
-int launch_r3_nf(const R2Args& args, int nf, bool uni, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
-    const bool merge = args.base.merge_max != 0;
+int launch_r3_nf(const R3Args& args, bool ct, int nf, bool uni, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    const bool merge = args.a.base.merge_max != 0;
     int rc;
     switch (nf) {
-        case 1: rc = launch_r3_flags<1, EMIT>(args, uni, merge, grid, block, smem, st); break;
-        case 2: rc = launch_r3_flags<2, EMIT>(args, uni, merge, grid, block, smem, st); break;
-        case 3: rc = launch_r3_flags<3, EMIT>(args, uni, merge, grid, block, smem, st); break;
-        case 4: rc = launch_r3_flags<4, EMIT>(args, uni, merge, grid, block, smem, st); break;
+        case 1: rc = launch_r3_ct<1, EMIT>(args, ct, uni, merge, grid, block, smem, st); break;
+        case 2: rc = launch_r3_ct<2, EMIT>(args, ct, uni, merge, grid, block, smem, st); break;
+        case 3: rc = launch_r3_ct<3, EMIT>(args, ct, uni, merge, grid, block, smem, st); break;
+        case 4: rc = launch_r3_ct<4, EMIT>(args, ct, uni, merge, grid, block, smem, st); break;
         default: return fail(PCG_ERR_ARG, "nfield must be 1..%d", kMaxFields);
     }
     if (rc != PCG_OK) return rc;
@@ -555,6 +565,15 @@ bool use_r3_kernel() {
     static const int choice = [] {
         const char* e = getenv("PCG_KERNEL");
         return (e && strcmp(e, "r2") == 0) ? 0 : 1;
+    }();
+    return choice != 0;
+}
+
+// PCG_TABLES=global keeps the threshold rows in global memory (A/B runs)
+bool use_const_tables() {
+    static const int choice = [] {
+        const char* e = getenv("PCG_TABLES");
+        return (e && strcmp(e, "global") == 0) ? 0 : 1;
     }();
     return choice != 0;
 }
@@ -609,6 +628,7 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     // r2-space thresholds of this (radar height, level set): built on the host, stream-ordered upload
     const int ne = vol->ne;
     LevelSweep* d_ls = nullptr;
+    std::vector<LevelSweep> tab_host;
     {
         std::lock_guard<std::mutex> lk(vol->ls_mutex);
         std::vector<double> key;
@@ -631,8 +651,10 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
             }
             vol->d_ls = fresh;
             vol->ls_key.swap(key);
+            vol->ls_host.swap(ls);
         }
         d_ls = vol->d_ls;
+        tab_host = vol->ls_host;       // (a copy: another thread may rebuild the volume's table meanwhile)
     }
     RA.nonfinite = g_nonfinite_flag;
     RA.r2.fs = vol->d_fs;
@@ -664,19 +686,39 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     A.grid.tiles_y = (int)tiles_y;
     const dim3 grid((unsigned)(tiles_x * tiles_y));
     int rc = PCG_OK;
-    for (int z0 = 0; z0 < nz && rc == PCG_OK; z0 += kMaxLevelsPerLaunch) {
-        const int cnt = (nz - z0 < kMaxLevelsPerLaunch) ? nz - z0 : kMaxLevelsPerLaunch;
+    // v8: the threshold rows of a launch's levels ride in the kernel parameters when at least 16 levels fit
+    const size_t row_bytes = (size_t)(2 * ne + 3) * sizeof(LevelSweep);
+    const int tab_levels = (int)(kR3TabBytes / row_bytes);
+    const bool ct = r3 && use_const_tables() && tab_levels >= 16 && ne <= kR3PolySweeps &&
+                    vol->fs_host.size() == (size_t)ne && tab_host.size() == (size_t)nz * (2 * ne + 3);
+    const int per_launch = ct && tab_levels < kMaxLevelsPerLaunch ? tab_levels : kMaxLevelsPerLaunch;
+    std::unique_ptr<R3Args> QA;
+    if (r3) {
+        QA.reset(new R3Args);
+        memset(QA->poly, 0, sizeof(QA->poly));
+        if (ct)
+            for (int k = 0; k < ne; ++k) {
+                const FastSweep& f = vol->fs_host[k];
+                QA->poly[k][0] = f.q1; QA->poly[k][1] = f.q2; QA->poly[k][2] = f.q3; QA->poly[k][3] = f.q4;
+                QA->poly[k][4] = f.q5;
+            }
+    }
+    for (int z0 = 0; z0 < nz && rc == PCG_OK; z0 += per_launch) {
+        const int cnt = (nz - z0 < per_launch) ? nz - z0 : per_launch;
         A.nz = cnt;
         for (int k = 0; k < cnt; ++k) fill_level(&A.levels[k], levels[z0 + k], Re, a2, twoa);
         RA.r2.lp = reinterpret_cast<const LevelPair*>(d_ls) + (size_t)z0 * (2 * ne + 3);
         A.out = d_out + (size_t)z0 * (size_t)ncol;
         A.idx = d_idx ? d_idx + (size_t)z0 * (size_t)ncol * kIdxStride : nullptr;
-        if (r3)
-            rc = d_idx ? launch_r3_nf<true>(RA, nfield, vol->uniform, grid, block, smem, st)
-                       : launch_r3_nf<false>(RA, nfield, vol->uniform, grid, block, smem, st);
-        else
+        if (r3) {
+            QA->a = RA;
+            if (ct) memcpy(QA->tab, tab_host.data() + (size_t)z0 * (2 * ne + 3), (size_t)cnt * row_bytes);
+            rc = d_idx ? launch_r3_nf<true>(*QA, ct, nfield, vol->uniform, grid, block, smem, st)
+                       : launch_r3_nf<false>(*QA, ct, nfield, vol->uniform, grid, block, smem, st);
+        } else {
             rc = d_idx ? launch_fast_nf<true>(RA, nfield, vol->uniform, grid, block, smem, st)
                        : launch_fast_nf<false>(RA, nfield, vol->uniform, grid, block, smem, st);
+        }
     }
     return rc;
 }
@@ -1131,6 +1173,7 @@ static int volume_create_impl(int ne, const int* naz, const int* ng, const doubl
             VOL_TRY(g_pool.alloc((void**)&v->d_gt, gt.size() * sizeof(double2)));
             VOL_TRY(g_pool.alloc((void**)&v->d_ht, ht.size() * sizeof(GateAux)));
             VOL_TRY(cudaMemcpyAsync(v->d_fs, fs.data(), fs.size() * sizeof(FastSweep), cudaMemcpyHostToDevice, st));
+            v->fs_host = fs;
             VOL_TRY(cudaMemcpyAsync(v->d_gt, gt.data(), gt.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
             VOL_TRY(cudaMemcpyAsync(v->d_ht, ht.data(), ht.size() * sizeof(GateAux), cudaMemcpyHostToDevice, st));
             VOL_TRY(cudaStreamSynchronize(st));      // the host vectors die with this block
@@ -1550,6 +1593,37 @@ int launch_radar_pass_any(const NetArgs& a, const NetAcc& acc, int method, bool 
     }
 }
 
+template <int M, bool U>
+int launch_tile(const NetArgs& a, unsigned ntile, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(net_tile_kernel<M, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    net_tile_kernel<M, U><<<ntile, kNet2Threads, smem, st>>>(a);
+    return PCG_OK;
+}
+
+int launch_tile_any(const NetArgs& a, int method, bool uni, unsigned ntile, size_t smem, cudaStream_t st) {
+    switch (method * 2 + (uni ? 1 : 0)) {
+        case kNetMax * 2: return launch_tile<kNetMax, false>(a, ntile, smem, st);
+        case kNetMax * 2 + 1: return launch_tile<kNetMax, true>(a, ntile, smem, st);
+        case kNetNearest * 2: return launch_tile<kNetNearest, false>(a, ntile, smem, st);
+        case kNetNearest * 2 + 1: return launch_tile<kNetNearest, true>(a, ntile, smem, st);
+        case kNetExp * 2: return launch_tile<kNetExp, false>(a, ntile, smem, st);
+        case kNetExp * 2 + 1: return launch_tile<kNetExp, true>(a, ntile, smem, st);
+        case kNetQuality * 2: return launch_tile<kNetQuality, false>(a, ntile, smem, st);
+        case kNetQuality * 2 + 1: return launch_tile<kNetQuality, true>(a, ntile, smem, st);
+        default: return fail(PCG_ERR_ARG, "Unsupported composite_method code %d", method);
+    }
+}
+
+// PCG_NET=passes keeps the round-1 radar-major passes (A/B runs)
+bool use_tile_kernel() {
+    static const int choice = [] {
+        const char* e = getenv("PCG_NET");
+        return (e && strcmp(e, "passes") == 0) ? 0 : 1;
+    }();
+    return choice != 0;
+}
+
 int launch_finalize(const NetArgs& a, const NetAcc& acc, int method, cudaStream_t st) {
     const size_t nvox = (size_t)a.nz * (size_t)a.ncol;
     const unsigned blocks = (unsigned)((nvox + 255) / 256 < 148 * 32 ? (nvox + 255) / 256 : 148 * 32);
@@ -1591,7 +1665,8 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
                     const pcg_network_params* prm, const double* d_gx, const double* d_gy, long long ncol, int ny,
                     const double* levels, int nz, double fill, double* d_comp, int16_t* d_valid,
                     int16_t* d_cov, int8_t* d_blind, double* d_cr, double* d_quality,
-                    unsigned long long* d_ties, cudaStream_t st) {
+                    unsigned long long* d_ties, cudaStream_t st, double out_missing, bool* relabelled) {
+    if (relabelled) *relabelled = false;
     if (!prm) return fail(PCG_ERR_ARG, "params is NULL");
     if (nradar < 1) return fail(PCG_ERR_ARG, "radar_volumes must contain at least one volume.");
     if (nradar > 255) return fail(PCG_ERR_ARG, "at most 255 radars per composite");
@@ -1602,8 +1677,9 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
                     "blind_method must be one of 'mask', 'nearest_gate', 'lowest_sweep', 'hybrid', or "
                     "'nearest_valid'.");
     if (nz < 0) return fail(PCG_ERR_ARG, "nz must be non-negative");
-    if (ncol == 0 || nz == 0) return PCG_OK;
+    if (ncol == 0 || (nz == 0 && !d_cr)) return PCG_OK;       // (no levels: the CR plane is still wanted)
     int rc;
+    if ((rc = scratch_begin(st))) return rc;                  // a previous call on another stream may still use the scratch
     bool uni = true;
     size_t npair_total = 0, n_ls = 0;
     for (int i = 0; i < nradar; ++i) {
@@ -1635,7 +1711,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     // gate is reachable beyond reach[i] (HUGE_VAL: no culling for absurd heights or ranges)
     std::vector<double> reach(nradar);
     {
-        double zmin = levels[0];
+        double zmin = nz > 0 ? levels[0] : 0.0;
         for (int k = 1; k < nz; ++k) zmin = levels[k] < zmin ? levels[k] : zmin;
         for (int i = 0; i < nradar; ++i) {
             double rlast = 0.0;
@@ -1776,8 +1852,53 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     A.npeer = g_net_peers.n; A.peer_plane = g_net_peers.plane; A.peer_off = g_net_peers.off;
     for (int q = 0; q < g_net_peers.n; ++q) A.peer[q] = g_net_peers.ptr[q];
     A.quality_out = d_quality; A.tie_count = d_ties;
+    A.out_missing = out_missing;
+    A.ne_max = 0;
+    for (int i = 0; i < nradar; ++i) A.ne_max = vols[i]->ne > A.ne_max ? vols[i]->ne : A.ne_max;
 
-    // accumulators (one 16-byte cell per voxel) and per-radar tile lists
+    if (use_tile_kernel()) {
+        // ---- one tile-persistent launch (pcg_net2.cuh): no lists, no accumulators in HBM, no finalize ----
+        const bool nearest = prm->method == kNetNearest;
+        int chunk = nz > 0 ? nz : 1;
+        // levels per launch: the accumulators of a block live in shared memory, and how many blocks fit an SM
+        // decides how much latency the kernel hides (PCG_NET_SMEM_KB: tuning runs)
+        static const size_t smem_budget = [] {
+            const char* e = getenv("PCG_NET_SMEM_KB");
+            const long kb = e ? atol(e) : 0;
+            return (size_t)((kb >= 8 && kb <= 200) ? kb : kNet2SmemKB) * 1024;
+        }();
+        while (chunk > 1 && net2_smem_bytes(A.ne_max, chunk, nearest) > smem_budget) --chunk;
+        if (d_quality) CUDA_TRY(cudaMemsetAsync(d_quality, 0, (size_t)nz * (size_t)ncol * sizeof(double), st));
+        for (int z0 = 0; z0 < (nz > 0 ? nz : 1); z0 += chunk) {
+            NetArgs B = A;
+            B.z0 = z0;
+            B.nz = nz - z0 < chunk ? nz - z0 : chunk;
+            const size_t off = (size_t)z0 * (size_t)ncol;
+            if (d_comp) B.composite = d_comp + off;
+            if (d_valid) B.valid_count = d_valid + off;
+            if (d_cov) B.coverage = d_cov + off;
+            if (d_blind) B.blind = d_blind + off;
+            if (d_quality) B.quality_out = d_quality + off;
+            if (z0 > 0) B.cr = nullptr;
+            if (B.npeer) for (int q = 0; q < B.npeer; ++q) B.peer[q] = A.peer[q] + (size_t)z0 * (size_t)A.peer_plane;
+            const size_t smem = net2_smem_bytes(A.ne_max, B.nz, nearest);
+            if ((rc = launch_tile_any(B, prm->method, uni, (unsigned)ntile, smem, st))) return rc;
+            g_launches.fetch_add(1);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (relabelled) *relabelled = true;
+        return scratch_done(st);
+    }
+    if (nz == 0) {                                           // radar passes need at least one level: CR alone
+        NetArgs B = A;
+        B.nz = 0; B.z0 = 0;
+        if ((rc = launch_tile_any(B, prm->method, uni, (unsigned)ntile, net2_smem_bytes(A.ne_max, 0, false), st))) return rc;
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+        return scratch_done(st);
+    }
+
+    // ---- round-1 path (PCG_NET=passes): accumulators (one 16-byte cell per voxel) and per-radar tile lists
     const size_t nvox = (size_t)nz * (size_t)ncol;
     NetAcc acc;
     memset(&acc, 0, sizeof(acc));
@@ -1853,7 +1974,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     if ((rc = launch_finalize(A, acc, prm->method, st))) return rc;
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
-    return PCG_OK;
+    return scratch_done(st);
 }
 
 }  // namespace
@@ -1880,13 +2001,13 @@ extern "C" int pcg_network_compose_dev(int nradar, const pcg_volume* const* vols
     return enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
                            d_grid_x, d_grid_y, (long long)nx * ny, ny, level_heights, nz, fill, d_composite,
                            d_valid_count, d_coverage_count, d_blind_mask, d_cr, d_quality, nullptr,
-                           (cudaStream_t)stream);
+                           (cudaStream_t)stream, fill, nullptr);
 }
 
 namespace {
 int enqueue_columns(const double* d_vol, const double* d_levels, int nz, long long ncol, double fill, double min_dbz,
                     double max_dbz_cap, double threshold, double* d_cr, double* d_vil, double* d_et,
-                    unsigned char* d_topped, cudaStream_t st);
+                    unsigned char* d_topped, cudaStream_t st, int nan_as_fill = 0);
 }
 
 // ---- multi-GPU: the finished slab goes straight into every peer's grid --------------------------
@@ -1942,10 +2063,20 @@ extern "C" int pcg_network_compose_gather_dev(int nradar, const pcg_volume* cons
     const int rc = enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths,
                                    params, d_grid_x, d_grid_y, (long long)nx * ny, ny, level_heights, nz, fill,
                                    d_composite, d_valid_count, d_coverage_count, d_blind_mask, d_cr, nullptr, nullptr,
-                                   (cudaStream_t)stream);
+                                   (cudaStream_t)stream, fill, nullptr);
     g_net_peers.n = 0;
     return rc;
 }
+
+extern "C" int pcg_network_compose_ex(int nradar, const pcg_volume* const* vols, const double* radar_x,
+                                      const double* radar_y, const double* radar_height,
+                                      const double* effective_earth_radius, const double* const* beam_widths,
+                                      const pcg_network_params* params, const double* grid_x, const double* grid_y,
+                                      int nx, int ny, const double* level_heights, int nz, double fill,
+                                      double out_missing, double* composite, int16_t* valid_count,
+                                      int16_t* coverage_count, int8_t* blind_mask, double* cr, double* quality,
+                                      uint64_t* tie_voxels, const double* column_params, double* vil, double* et,
+                                      unsigned char* et_topped);
 
 extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, const double* radar_x,
                                    const double* radar_y, const double* radar_height,
@@ -1961,15 +2092,26 @@ extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, co
                                   nullptr, nullptr);
 }
 
-extern "C" int pcg_network_compose_ex(int nradar, const pcg_volume* const* vols, const double* radar_x,
-                                      const double* radar_y, const double* radar_height,
-                                      const double* effective_earth_radius, const double* const* beam_widths,
-                                      const pcg_network_params* params, const double* grid_x, const double* grid_y,
-                                      int nx, int ny, const double* level_heights, int nz, double fill,
-                                      double out_missing, double* composite, int16_t* valid_count,
-                                      int16_t* coverage_count, int8_t* blind_mask, double* cr, double* quality,
-                                      uint64_t* tie_voxels, const double* column_params, double* vil, double* et,
-                                      unsigned char* et_topped) {
+// Host-buffer network composite of rows [row_offset, row_offset + nx) of a grid of full_rows rows: grid_x / grid_y
+// and every output are the FULL host arrays; only the slab's rows are uploaded, computed and written back (each
+// level's slab is one contiguous run, so the volumes go back with one pitched copy per output).  One host thread
+// per GPU calls this for its slab: every GPU returns its rows over its own PCIe link into the same pinned arrays —
+// the device analogue of the reference's fork pool (RadarInterp.py:1816-1861).
+static int network_compose_host(int nradar, const pcg_volume* const* vols, const double* radar_x,
+                                const double* radar_y, const double* radar_height,
+                                const double* effective_earth_radius, const double* const* beam_widths,
+                                const pcg_network_params* params, const double* grid_x, const double* grid_y,
+                                int nx, int ny, const double* level_heights, int nz, double fill,
+                                double out_missing, double* composite, int16_t* valid_count,
+                                int16_t* coverage_count, int8_t* blind_mask, double* cr, double* quality,
+                                uint64_t* tie_voxels, const double* column_params, double* vil, double* et,
+                                unsigned char* et_topped, long long full_rows, long long row_offset) {
+    if (row_offset < 0 || full_rows < 0 || row_offset + nx > full_rows)
+        return fail(PCG_ERR_ARG, "slab rows [%lld, %lld) do not fit a grid of %lld rows", row_offset, row_offset + nx, full_rows);
+    const size_t row0 = (size_t)row_offset * (size_t)(ny > 0 ? ny : 0);      // first element of the slab in a plane
+    const size_t plane = (size_t)full_rows * (size_t)(ny > 0 ? ny : 0);      // elements of one full level
+    grid_x = grid_x ? grid_x + row0 : grid_x;
+    grid_y = grid_y ? grid_y + row0 : grid_y;
     if (nx < 0 || ny < 0 || nz < 0) return fail(PCG_ERR_ARG, "grid shape must be non-negative");
     const bool columns = column_params && (vil || et || et_topped);
     if (!composite && !columns) return fail(PCG_ERR_ARG, "composite is NULL");
@@ -1993,6 +2135,12 @@ extern "C" int pcg_network_compose_ex(int nradar, const pcg_volume* const* vols,
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(g_scratch[S_TMP2].ptr, 0, sizeof(unsigned long long), st));
+    // the tile kernel stores the caller's missing-value marker itself; the column products read the composite
+    // afterwards and know `fill` and NaN as "no data" — any other marker is applied after them, as before
+    const bool marker_ok = !columns || out_missing != out_missing || memcmp(&out_missing, &fill, sizeof(double)) == 0;
+    const int nan_as_fill = (columns && out_missing != out_missing) ? 1 : 0;
+    const double tile_missing = marker_ok ? out_missing : fill;
+    bool relabelled = false;
     rc = enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
                          (const double*)g_scratch[S_GX].ptr, (const double*)g_scratch[S_GY].ptr, (long long)ncol, ny,
                          level_heights, nz, fill, (double*)g_scratch[S_OUT].ptr,
@@ -2001,7 +2149,7 @@ extern "C" int pcg_network_compose_ex(int nradar, const pcg_volume* const* vols,
                          blind_mask ? (int8_t*)g_scratch[S_AUX2].ptr : nullptr,
                          cr ? (double*)g_scratch[S_AUX3].ptr : nullptr,
                          quality ? (double*)g_scratch[S_AUX4].ptr : nullptr,
-                         (unsigned long long*)g_scratch[S_TMP2].ptr, st);
+                         (unsigned long long*)g_scratch[S_TMP2].ptr, st, tile_missing, &relabelled);
     if (rc) return rc;
     if (columns && ncol) {
         // VIL / ET of the composite while it is still on the device (RadarInterp.py:2064-2119 -> derive_vil /
@@ -2013,26 +2161,58 @@ extern "C" int pcg_network_compose_ex(int nradar, const pcg_volume* const* vols,
         unsigned char* dt = (unsigned char*)(d2 + 2 * ncol);
         rc = enqueue_columns((const double*)g_scratch[S_OUT].ptr, (const double*)g_scratch[S_TMP0].ptr, nz, (long long)ncol,
                              fill, column_params[0], column_params[1], column_params[2], nullptr, vil ? d2 : nullptr,
-                             et ? d2 + ncol : nullptr, et_topped ? dt : nullptr, st);
+                             et ? d2 + ncol : nullptr, et_topped ? dt : nullptr, st, relabelled ? nan_as_fill : 0);
         if (rc) return rc;
-        if (vil) CUDA_TRY(cudaMemcpyAsync(vil, d2, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (et) CUDA_TRY(cudaMemcpyAsync(et, d2 + ncol, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (et_topped) CUDA_TRY(cudaMemcpyAsync(et_topped, dt, ncol, cudaMemcpyDeviceToHost, st));
+        if (vil) CUDA_TRY(cudaMemcpyAsync(vil + row0, d2, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (et) CUDA_TRY(cudaMemcpyAsync(et + row0, d2 + ncol, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (et_topped) CUDA_TRY(cudaMemcpyAsync(et_topped + row0, dt, ncol, cudaMemcpyDeviceToHost, st));
     }
-    if (composite) {
-        if ((rc = relabel_missing((double*)g_scratch[S_OUT].ptr, nvox, fill, out_missing, st))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(composite, g_scratch[S_OUT].ptr, nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (composite && nvox) {
+        if (!(relabelled && marker_ok) &&
+            (rc = relabel_missing((double*)g_scratch[S_OUT].ptr, nvox, fill, out_missing, st))) return rc;
+        CUDA_TRY(cudaMemcpy2DAsync(composite + row0, plane * sizeof(double), g_scratch[S_OUT].ptr, ncol * sizeof(double), ncol * sizeof(double), (size_t)nz, cudaMemcpyDeviceToHost, st));
     }
-    if (valid_count) CUDA_TRY(cudaMemcpyAsync(valid_count, g_scratch[S_AUX0].ptr, nvox * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
-    if (coverage_count) CUDA_TRY(cudaMemcpyAsync(coverage_count, g_scratch[S_AUX1].ptr, nvox * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
-    if (blind_mask) CUDA_TRY(cudaMemcpyAsync(blind_mask, g_scratch[S_AUX2].ptr, nvox * sizeof(int8_t), cudaMemcpyDeviceToHost, st));
-    if (cr) CUDA_TRY(cudaMemcpyAsync(cr, g_scratch[S_AUX3].ptr, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (quality) CUDA_TRY(cudaMemcpyAsync(quality, g_scratch[S_AUX4].ptr, nvox * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (valid_count && nvox) CUDA_TRY(cudaMemcpy2DAsync(valid_count + row0, plane * sizeof(int16_t), g_scratch[S_AUX0].ptr, ncol * sizeof(int16_t), ncol * sizeof(int16_t), (size_t)nz, cudaMemcpyDeviceToHost, st));
+    if (coverage_count && nvox) CUDA_TRY(cudaMemcpy2DAsync(coverage_count + row0, plane * sizeof(int16_t), g_scratch[S_AUX1].ptr, ncol * sizeof(int16_t), ncol * sizeof(int16_t), (size_t)nz, cudaMemcpyDeviceToHost, st));
+    if (blind_mask && nvox) CUDA_TRY(cudaMemcpy2DAsync(blind_mask + row0, plane * sizeof(int8_t), g_scratch[S_AUX2].ptr, ncol * sizeof(int8_t), ncol * sizeof(int8_t), (size_t)nz, cudaMemcpyDeviceToHost, st));
+    if (cr) CUDA_TRY(cudaMemcpyAsync(cr + row0, g_scratch[S_AUX3].ptr, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (quality && nvox) CUDA_TRY(cudaMemcpy2DAsync(quality + row0, plane * sizeof(double), g_scratch[S_AUX4].ptr, ncol * sizeof(double), ncol * sizeof(double), (size_t)nz, cudaMemcpyDeviceToHost, st));
     unsigned long long ties = 0;
     CUDA_TRY(cudaMemcpyAsync(&ties, g_scratch[S_TMP2].ptr, sizeof(ties), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (tie_voxels) *tie_voxels = ties;
     return PCG_OK;
+}
+
+extern "C" int pcg_network_compose_ex(int nradar, const pcg_volume* const* vols, const double* radar_x,
+                                      const double* radar_y, const double* radar_height,
+                                      const double* effective_earth_radius, const double* const* beam_widths,
+                                      const pcg_network_params* params, const double* grid_x, const double* grid_y,
+                                      int nx, int ny, const double* level_heights, int nz, double fill,
+                                      double out_missing, double* composite, int16_t* valid_count,
+                                      int16_t* coverage_count, int8_t* blind_mask, double* cr, double* quality,
+                                      uint64_t* tie_voxels, const double* column_params, double* vil, double* et,
+                                      unsigned char* et_topped) {
+    return network_compose_host(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
+                                grid_x, grid_y, nx, ny, level_heights, nz, fill, out_missing, composite, valid_count,
+                                coverage_count, blind_mask, cr, quality, tie_voxels, column_params, vil, et, et_topped,
+                                (long long)nx, 0);
+}
+
+extern "C" int pcg_network_compose_rows(int nradar, const pcg_volume* const* vols, const double* radar_x,
+                                        const double* radar_y, const double* radar_height,
+                                        const double* effective_earth_radius, const double* const* beam_widths,
+                                        const pcg_network_params* params, const double* grid_x, const double* grid_y,
+                                        long long full_rows, long long row_offset, int nrows, int ny,
+                                        const double* level_heights, int nz, double fill, double out_missing,
+                                        double* composite, int16_t* valid_count, int16_t* coverage_count,
+                                        int8_t* blind_mask, double* cr, uint64_t* tie_voxels,
+                                        const double* column_params, double* vil, double* et,
+                                        unsigned char* et_topped) {
+    return network_compose_host(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
+                                grid_x, grid_y, nrows, ny, level_heights, nz, fill, out_missing, composite, valid_count,
+                                coverage_count, blind_mask, cr, nullptr, tie_voxels, column_params, vil, et, et_topped,
+                                full_rows, row_offset);
 }
 
 // ---- compose_network_volume on gridded volumes, column products ---------------------------------
@@ -2093,8 +2273,9 @@ extern "C" int pcg_compose_volumes(int nradar, const double* const* volumes, con
 namespace {
 int enqueue_columns(const double* d_vol, const double* d_levels, int nz, long long ncol, double fill, double min_dbz,
                     double max_dbz_cap, double threshold, double* d_cr, double* d_vil, double* d_et,
-                    unsigned char* d_topped, cudaStream_t st) {
+                    unsigned char* d_topped, cudaStream_t st, int nan_as_fill) {
     ColumnArgs A;
+    A.nan_as_fill = nan_as_fill;
     A.vol = d_vol; A.levels = d_levels; A.nz = nz; A.ncol = ncol; A.fill = fill;
     A.min_dbz = min_dbz; A.max_dbz_cap = max_dbz_cap; A.threshold = threshold;
     A.cr = d_cr; A.vil = d_vil; A.et = d_et; A.topped = d_topped;

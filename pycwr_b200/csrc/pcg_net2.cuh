@@ -1,0 +1,428 @@
+// pcg_net2.cuh — the multi-radar merge of run_radar_network_3d as ONE tile-persistent kernel.
+//
+// Replaces, fused per output tile (pycwr/interp/RadarInterp.py):
+//   grid_single_radar_to_latlon_3d :963-1023, _compute_quality_weight_volume :603-696, _compute_observability_mask
+//   :540-600, _build_composite_weight_cache :1379-1396, compose_network_volume :1399-1487, the CR max-merge
+//   :1026-1068,2047-2063, coverage_count / blind_mask :1938-1945 and build_network_dataset's fill -> NaN :1539.
+//
+// Round 1 ran one pass per radar over that radar's tile list with the per-voxel accumulators in HBM (pcg_network.cuh):
+// a memset, a read-modify-write of a 16-byte cell per (voxel, reaching radar) and a finalize pass — about 32 GB of
+// DRAM traffic for 4.7 GB of algorithmic bytes at config C4 — plus a cull kernel and a host sync for the tile counts.
+// Here a block OWNS a tile of 128 grid columns (4 warps x (4 rows x 8 columns)) for the whole call:
+//   1. it tests every radar's reach disc against the tile's bounding box (what net_cull_kernel did, no lists in HBM),
+//   2. loops over the reaching radars IN RADAR ORDER (the sums accumulate in the reference's order, np.sum over
+//      axis 0, and exactly as in round 1: the results are bit-identical) — per (column, radar): column geometry,
+//      azimuth table in shared memory, every level through the r2-space voxel path of pcg_r3.cuh,
+//   3. keeps the tile's accumulators (sum w v, sum w as float32, two uint8 counters: 10 bytes per voxel) in shared
+//      memory, each thread touching only its own column's cells (no barriers in the radar loop),
+//   4. writes composite (with the caller's missing-value marker) / valid_count / coverage_count / blind_mask / CR
+//      once.  No memset, no accumulator traffic, no finalize pass, no relabel pass, no host synchronisation.
+// DRAM traffic is then the volumes the tiles of a grid band reach (each streamed about once, tiles run in row-band
+// order), the grids and the outputs.
+#pragma once
+#include "pcg_network.cuh"
+#include "pcg_r3.cuh"
+
+namespace pcg {
+
+constexpr int kNet2Threads = 128;
+#ifndef NET2_MINB
+#define NET2_MINB 4
+#endif
+#ifndef NET2_SMEM_KB
+#define NET2_SMEM_KB 55
+#endif
+constexpr int kNet2SmemKB = NET2_SMEM_KB;   // shared-memory budget of a block: levels per launch follow from it
+
+// dynamic shared memory of net_tile_kernel
+__host__ __device__ inline size_t net2_smem_bytes(int ne_max, int nz, bool nearest) {
+    size_t b = 512;                                                    // bbox partials, hit flags, radar list
+    b += (size_t)ne_max * kNet2Threads * sizeof(AzEntry);              // azimuth table [sweep][thread]
+    b += (size_t)nz * kNet2Threads * (2 * sizeof(float) + sizeof(unsigned short));
+    if (nearest) b += (size_t)nz * kNet2Threads * sizeof(double);
+    return (b + 15) & ~(size_t)15;
+}
+
+// observability of a voxel in the first / last gate interval of its sweep pair, or flagged by the voxel path:
+// the guard bands of pcg_network.cuh, then the NumPy-twin chain itself (out of line, rare)
+__device__ __noinline__ bool net2_obs_edge(double r2, const NetPair* np, double x, double y, const NetRadar* R,
+                                           const NetLevel* L, bool tie, unsigned long long* ties) {
+    const bool in = (r2 > np->of2_hi) & (r2 < np->ol2_lo);
+    const bool sure_out = (r2 < np->of2_lo) | (r2 > np->ol2_hi);
+    if (!tie && (in | sure_out) && (r2 > 0.0)) return in;
+    ++*ties;
+    return twin_observable(x, y, *R, *L, R->vol.sweeps, R->npairs, R->ne);
+}
+
+template <int METHOD, bool UNI>
+__global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const __grid_constant__ NetArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr unsigned T = kNet2Threads;
+    double* s_red = reinterpret_cast<double*>(smem_raw);                         // [4 x 4 warps] = 128 B
+    int* s_nlist = reinterpret_cast<int*>(smem_raw + 128);
+    unsigned char* s_list = smem_raw + 256;                                        // [256] hit flags, then the list
+    AzEntry* s_az = reinterpret_cast<AzEntry*>(smem_raw + 512);                    // [ne_max][T]
+    float* a_wv = reinterpret_cast<float*>(s_az + (size_t)p.ne_max * T);           // [nz][T]
+    float* a_w = a_wv + (size_t)p.nz * T;                                          // [nz][T]
+    unsigned short* a_cc = reinterpret_cast<unsigned short*>(a_w + (size_t)p.nz * T);   // [nz][T]: cnt | cov << 8
+    double* a_d2 = reinterpret_cast<double*>(smem_raw + ((512 + (size_t)p.ne_max * T * sizeof(AzEntry) +
+                                             (size_t)p.nz * T * 10 + 15) & ~(size_t)15));   // nearest only
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    bool active;
+    long long col;
+    net_tile_column(p, blockIdx.x, active, col);
+    const double gx = p.gx[col], gy = p.gy[col];            // inactive lanes repeat a valid column
+    // ---- 1. which radars reach this tile (bounding box against reach disc, as net_cull_kernel) ----
+    {
+        double x0 = gx, x1 = gx, y0 = gy, y1 = gy;
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+            x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+            y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        if (lane == 0) { s_red[4 * warp] = x0; s_red[4 * warp + 1] = x1; s_red[4 * warp + 2] = y0; s_red[4 * warp + 3] = y1; }
+        // NaN coordinates poison fmin / fmax silently: a tile holding one is handed to every radar
+        const bool odd = __syncthreads_or(!(gx == gx) || !(gy == gy));
+        for (int w = 0; w < (int)(T >> 5); ++w) {
+            x0 = fmin(x0, s_red[4 * w]); x1 = fmax(x1, s_red[4 * w + 1]);
+            y0 = fmin(y0, s_red[4 * w + 2]); y1 = fmax(y1, s_red[4 * w + 3]);
+        }
+        for (int ir = tid; ir < p.nradar; ir += T) {
+            const NetRadar& R = p.radars[ir];
+            const double ddx = fmax(fmax(x0 - R.x, R.x - x1), 0.0);
+            const double ddy = fmax(fmax(y0 - R.y, R.y - y1), 0.0);
+            s_list[ir] = (odd || !(ddx * ddx + ddy * ddy > R.cull2)) ? 1 : 0;
+        }
+        __syncthreads();
+        if (warp == 0) {                                      // ordered compaction: the list is in radar order
+            int base = 0;
+            for (int c = 0; c < p.nradar; c += 32) {
+                const int ir = c + lane;
+                const bool hit = ir < p.nradar && s_list[ir] != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                __syncwarp();
+                if (hit) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned char)ir;   // base + rank <= ir: in place
+                base += __popc(m);
+                __syncwarp();
+            }
+            if (lane == 0) *s_nlist = base;
+        }
+    }
+    // ---- 3. this column's accumulators ----
+    const int nz = p.nz;
+    for (int iz = 0; iz < nz; ++iz) {
+        a_wv[(size_t)iz * T + tid] = 0.f;
+        a_w[(size_t)iz * T + tid] = 0.f;
+        a_cc[(size_t)iz * T + tid] = 0;
+        if (METHOD == kNetNearest) a_d2[(size_t)iz * T + tid] = __longlong_as_double(0x7ff0000000000000LL);
+    }
+    __syncthreads();
+    const int nlist = *s_nlist;
+    float cr_best = __int_as_float(0x7fc00000);              // NaN: no echo yet
+    unsigned long long ties = 0;
+    const float fill32 = p.fill32;
+    AzEntry* my_az = s_az + tid;
+    const unsigned az_addr = (unsigned)__cvta_generic_to_shared(my_az);
+    constexpr unsigned az_pitch = T * (unsigned)sizeof(AzEntry);
+
+    // ---- 2. the reaching radars, in radar order ----
+#pragma unroll 1
+    for (int li = 0; li < nlist; ++li) {
+        const int ir = s_list[li];
+        const NetRadar& R = p.radars[ir];
+        // radar-local coordinates (RadarInterp.py:990-991) and the 2-D distance of the weight cache
+        const double x = sub(gx, R.x), y = sub(gy, R.y);
+        const double d2 = add(mul(x, x), mul(y, y));
+        if (!active || !(d2 <= R.cull2)) continue;            // beyond every gate: nothing to add (NaN: chain below)
+        const int ne = R.ne;
+        // column invariants of this radar (RadarGridC.pyx:142-146,158)
+        const double s = sqrt_rn(d2);
+        const double phi = div(s, R.Re);
+        const double cphi = cos_small(phi);
+        {
+            const double az = azimuth_from_xy(x, y);
+            const double2* __restrict__ azt = R.r2.az_t;
+            const SweepDesc* __restrict__ sw_t = R.vol.sweeps;
+#pragma unroll 1
+            for (int sw = 0; sw < ne; ++sw) {
+                const SweepDesc* d = sw_t + sw;
+                const int naz = (d->naz >= 2 && d->ng >= 2) ? d->naz : 0;
+                int g = __double2int_rd(mul(sub(az, d->az_first), d->az_inv_step)) + 1;
+                AzEntry e;
+                int rec;
+                bool done = false;
+                if (g >= 1 && g < naz) {
+                    const double2* Tt = azt + d->az_off + (unsigned)(g - 1);
+                    double2 lo = __ldg(Tt);
+                    double hi = __ldg(&Tt[1].x);
+                    if (az < lo.x) {
+                        if (g >= 2) { --g; hi = lo.x; lo = __ldg(Tt - 1); }
+                    } else if (!(az < hi)) {
+                        if (g + 1 < naz) { ++g; lo = __ldg(Tt + 1); hi = __ldg(&Tt[2].x); }
+                    }
+                    if (!(az < lo.x) && (az < hi)) {
+                        e.row = (unsigned)d->val_off + (unsigned)(g - 1) * (unsigned)d->ng;
+                        e.w = (float)sub(az, lo.x) * (float)lo.y;
+                        done = true;
+                    }
+                }
+                if (!done) az_bracket_general(d, azt, az, &e, &rec);
+                my_az[(size_t)sw * T] = e;
+            }
+        }
+        // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
+        const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? __expf(-(float)d2 * R.inv_r2inf4) : 1.f;
+        const bool lowest_sweep = p.lowest_sweep != 0, highest_sweep = p.highest_sweep != 0;
+        const int k_first = lowest_sweep ? -1 : 0;
+        const unsigned k_span = (unsigned)((highest_sweep ? ne - 1 : ne - 2) - k_first);
+        const unsigned row_bytes = (unsigned)(2 * ne + 3) * 32u;
+        const unsigned ls_off = (unsigned)(ne + 1) * 32u;
+        const unsigned pair_top = (unsigned)(ne - 1);
+        const char* lrow = reinterpret_cast<const char*>(R.r2.lp) + (size_t)p.z0 * row_bytes;
+        const NetLevel* lv = R.levels + p.z0;
+        const float4* val0 = static_cast<const float4*>(R.vol.val[0]);
+        const double2* g_t = R.r2.g_t;
+        const FastSweep* fs_t = R.r2.fs;
+        const NetPair* np_t = R.npairs;
+        const float inv2a = R.r2.inv2a;
+        const float u_inv_step = R.r2.u_inv_step, u_c0 = R.r2.u_c0, u_step = R.r2.u_step, u_r_first = R.r2.u_r_first;
+        const int u_ngm1 = R.r2.u_ngm1;
+        const unsigned u_rng_off = R.r2.u_rng_off;
+        const double src_lo = R.src_lo, src_hi = R.src_hi;
+        const float inv_decay = R.inv_decay;
+        const bool sanity = p.sanity != 0;
+        int k = -1;
+        unsigned long long slow_mask = 0ull;
+        size_t o = (size_t)col;
+        // level constants one level ahead (they gate r2, and r2 gates every other load of the level)
+        double n_a2g2 = nz > 0 ? __ldg(&lv[0].cy.a2g2) : 0.0, n_twoag = nz > 0 ? __ldg(&lv[0].cy.twoag) : 0.0;
+
+        // one voxel's contribution: range-sanity filter (RadarInterp.py:1003-1014), observability weight
+        // (:566-599 / 636-695), then the merge rule of compose_network_volume (:1448-1487)
+        auto merge = [&](int iz, float v, bool obs, float rf, const NetPair* np, size_t oo) {
+            if (sanity && v != fill32) {
+                const double vd = (double)v;
+                if (!(src_lo <= src_hi) || vd < src_lo || vd > src_hi) v = fill32;
+            }
+            const bool valid = (v != fill32) && (v == v) && (fabsf(v) != __int_as_float(0x7f800000));
+            float qw = 0.f;
+            if (obs && (METHOD == kNetQuality || p.quality_out)) {
+                const float2 bv = __ldg(reinterpret_cast<const float2*>(&np->beam_k));      // {beam_k, vert_w}
+                const float t = rf * inv_decay;
+                const float b = rf * bv.x;
+                qw = __expf(-t * t) * rcp_approx(fmaf(b, b, 1.f)) * bv.y;
+            }
+            if (p.quality_out) p.quality_out[oo] = (double)qw;
+            if (!(obs | valid)) return;
+            const size_t c = (size_t)iz * T + tid;
+            unsigned cc = a_cc[c];
+            if (obs) cc += 0x100u;
+            if (valid) {
+                cc += 1u;
+                if (METHOD == kNetMax) {
+                    if (a_w[c] == 0.f || v > a_wv[c]) a_wv[c] = v;
+                    a_w[c] = 1.f;
+                } else if (METHOD == kNetNearest) {
+                    if (d2 < a_d2[c]) { a_d2[c] = d2; a_wv[c] = v; a_w[c] = 1.f; }
+                } else {
+                    const float w = (METHOD == kNetQuality && p.quality) ? w2d * qw : w2d;
+                    a_wv[c] = fmaf(w, v, a_wv[c]);
+                    a_w[c] += w;
+                }
+            }
+            a_cc[c] = (unsigned short)cc;
+        };
+
+#pragma unroll 1
+        for (int iz = 0; iz < nz; ++iz, lrow += row_bytes, o += (size_t)p.ncol) {
+            // RadarGridC.pyx:146-149 — the reference's own operations: r2 is bit-identical
+            // (NetLevel is 56 bytes: its members are 8-byte, not 16-byte, aligned)
+            const double r2 = sub(n_a2g2, mul(n_twoag, cphi));
+            if (iz + 1 < nz) { n_a2g2 = __ldg(&lv[iz + 1].cy.a2g2); n_twoag = __ldg(&lv[iz + 1].cy.twoag); }
+            const float r2f = (float)r2;
+            const float rinv = rsqrt_approx(r2f);
+            const float rf = r2f * rinv;
+            bool slow = false;
+            // Everything a voxel of the CURRENT sweep pair needs is requested before anything is compared
+            // (uniform-table volumes: every sweep usable, one shared range table, so every speculative address
+            // is valid): the confirmation entry, the pair record, the gate band of the guessed gate, both
+            // azimuth entries, both quads and the pair polynomial are in flight together — one memory round
+            // trip per level instead of three dependent ones.  A column that leaves its pair (19 % of the
+            // voxels at config C3) walks to the new pair and asks again.
+            int4 lk;
+            double2 tg = make_double2(0.0, 0.0);
+            int gi = 1;
+            AzEntry ea, eb;
+            float4 qa4, qb4, q14;
+            float q5 = 0.f;
+            ea.row = 0u; ea.w = 0.f; eb = ea;
+            qa4 = make_float4(0.f, 0.f, 0.f, 0.f); qb4 = qa4; q14 = qa4;
+#pragma unroll 1
+            for (;;) {
+                const int4* pk = reinterpret_cast<const int4*>(lrow + (unsigned)(k + 1) * 32u);
+                const double2 cf = __ldg(reinterpret_cast<const double2*>(pk));
+                lk = __ldg(pk + 1);
+                if (UNI) {
+                    const int lo_s = max(k, 0), hi_s = min(lo_s + 1, ne - 1);
+                    gi = min(max(__float2int_rd(fmaf(rf, u_inv_step, u_c0)), 1), u_ngm1);
+                    tg = __ldg(g_t + (u_rng_off + (unsigned)(gi - 1)));
+                    ea = lds_az(az_addr + (unsigned)lo_s * az_pitch);
+                    eb = lds_az(az_addr + (unsigned)hi_s * az_pitch);
+                    qa4 = __ldg(val0 + (ea.row + (unsigned)gi));
+                    qb4 = __ldg(val0 + (eb.row + (unsigned)gi));
+                    q14 = __ldg(reinterpret_cast<const float4*>(&fs_t[lo_s].q1));
+                    q5 = __ldg(&fs_t[lo_s].q5);
+                }
+                if ((r2 < cf.x) & (r2 > cf.y)) break;
+                const char* ls = lrow + ls_off;
+#pragma unroll 1
+                for (;;) {
+                    const double2* row = reinterpret_cast<const double2*>(ls + (unsigned)(k + 1) * 32u);
+                    const double2 cur = __ldg(row);
+                    const double2 nxt = __ldg(row + 2);
+                    if ((r2 < cur.x) & (r2 > nxt.y)) break;
+                    if (r2 > cur.y) { --k; continue; }
+                    if (r2 < nxt.x) { ++k; continue; }
+                    slow = true;
+                    break;
+                }
+                if (slow) break;
+            }
+            if (slow) { slow_mask |= 1ull << iz; continue; }
+            const bool pair = (unsigned)k < pair_top;
+            const bool skip = (unsigned)(k - k_first) > k_span;
+            const int lower = max(k, 0);
+            if (skip) {                                        // blind-zone rules: nothing sampled, nothing observable
+                merge(iz, fill32, false, 0.f, np_t, o);
+                continue;
+            }
+            int ngm1 = u_ngm1;
+            float rj, idr;
+            if (UNI) {
+                if (!((r2 >= tg.x) & (r2 < tg.y))) { slow_mask |= 1ull << iz; continue; }
+                rj = fmaf((float)(gi - 1), u_step, u_r_first); idr = u_inv_step;
+            } else {
+                const int4 tab = __ldg(reinterpret_cast<const int4*>(&fs_t[lower].rng_off));
+                const unsigned rng_off = (unsigned)tab.x;
+                ngm1 = tab.y;
+                const float c0 = __int_as_float(tab.z), inv_step = __int_as_float(tab.w);
+                const int need = pair ? (kFsPolyOk | kFsShared | kFsUsable) : kFsUsable;
+                const bool usable = (__ldg(&fs_t[lower].flags) & need) == need;
+                gi = usable ? min(max(__float2int_rd(fmaf(rf, inv_step, c0)), 1), ngm1) : 1;
+                const unsigned gidx = usable ? rng_off + (unsigned)(gi - 1) : u_rng_off;
+                tg = __ldg(g_t + gidx);                        // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
+                if (!(usable & (r2 >= tg.x) & (r2 < tg.y))) { slow_mask |= 1ull << iz; continue; }
+                const int4 hv = __ldg(reinterpret_cast<const int4*>(R.r2.h_t + gidx));       // {R^2, R, 1/dR}
+                rj = __int_as_float(hv.z); idr = __int_as_float(hv.w);
+                ea = lds_az(az_addr + (unsigned)lower * az_pitch);
+                qa4 = __ldg(val0 + (ea.row + (unsigned)gi));
+                if (pair) {
+                    eb = lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
+                    qb4 = __ldg(val0 + (eb.row + (unsigned)gi));
+                    q14 = __ldg(reinterpret_cast<const float4*>(&fs_t[lower].q1));
+                    q5 = __ldg(&fs_t[lower].q5);
+                }
+            }
+            const float ea0 = fmaf(ea.w, qa4.y - qa4.x, qa4.x), ea1 = fmaf(ea.w, qa4.w - qa4.z, qa4.z);
+            const float w_r = (float)sub(r2, tg.x) * idr * rcp_approx(rf + rj);
+            float v = fmaf(w_r, ea1 - ea0, ea0);
+            bool obs = false;
+            const NetPair* np = np_t;
+            if (pair) {
+                const float u = (float)sub(r2, __hiloint2double(lk.y, lk.x)) * rcp_approx(rf + __int_as_float(lk.z)) *
+                                fmaf(__int_as_float(lk.w), rinv, inv2a);
+                float w_el = fmaf(q5, u, q14.w);
+                w_el = fmaf(w_el, u, q14.z);
+                w_el = fmaf(w_el, u, q14.y);
+                w_el = fmaf(w_el, u, q14.x);
+                w_el *= u;
+                const float eb0 = fmaf(eb.w, qb4.y - qb4.x, qb4.x), eb1 = fmaf(eb.w, qb4.w - qb4.z, qb4.z);
+                const float v1 = fmaf(w_r, eb1 - eb0, eb0);
+                v = lerp_fill(w_el, v, v1, fill32);
+                np = np_t + lower;
+                // between two sweeps and at least one gate away from both ends of their (shared) range table:
+                // observable whatever the few-ulp difference between the NumPy twin's r and this one
+                obs = (gi > 1) & (gi < ngm1);
+                if (!obs) obs = net2_obs_edge(r2, np, x, y, &R, lv + iz, false, &ties);
+            }
+            merge(iz, v, obs, rf, np, o);
+        }
+
+        // ---- the marked voxels: the reference's own chain (pcg_fast.cuh fast_voxel) ----
+        if (slow_mask) {
+            SlowArgs sa;
+            sa.s_sw = R.vol.sweeps; sa.s_pr = R.pairs; sa.my_az = my_az; sa.my_iaz = nullptr;
+            sa.rg_t = reinterpret_cast<const double2*>(R.vol.rng); sa.val = R.vol.val; sa.az_stride = T; sa.ne = ne;
+            sa.a2 = R.a2; sa.twoa = R.twoa; sa.guard = R.guard; sa.inv_twoa = R.inv_twoa; sa.fill32 = fill32;
+            sa.blind = (p.nearest_gate != 0 ? 1 : 0) | (lowest_sweep ? 2 : 0) | (highest_sweep ? 4 : 0);
+            int k6 = 0;
+#pragma unroll 1
+            while (slow_mask) {
+                const int iz = __ffsll((long long)slow_mask) - 1;
+                slow_mask &= slow_mask - 1;
+                VoxelInfo vi;
+                float tmp[1];
+                r3_slow_voxel<1, false>(&sa, &lv[iz].cy, cphi, &k6, tmp, &vi);
+                const bool is_pair = vi.bracket == kPair;
+                const int kk = vi.lower < ne - 1 ? (vi.lower < 0 ? 0 : vi.lower) : ne - 2;
+                const NetPair* np = np_t + (is_pair ? kk : 0);
+                bool obs = false;
+                if (is_pair || vi.tie || !(vi.r2 > 0.0))
+                    obs = net2_obs_edge(vi.r2, np, x, y, &R, lv + iz, vi.tie || !is_pair, &ties) && (is_pair || vi.tie);
+                merge(iz, tmp[0], obs, (float)vi.r, np, (size_t)iz * (size_t)p.ncol + (size_t)col);
+            }
+        }
+
+        if (p.cr != nullptr) {
+            // get_CR_xy on the local grid: every sweep at its fixed elevation, blind "mask"
+            // (RadarGridC.pyx:596-624), then the NaN-aware max over radars (RadarInterp.py:2047-2063)
+            const double sphi = sin_small(phi);
+            const double2* rg_t = reinterpret_cast<const double2*>(R.vol.rng);
+            for (int ie = 0; ie < ne; ++ie) {
+                const SweepDesc& d = R.vol.sweeps[ie];
+                if (d.naz < 2 || d.ng < 2) continue;
+                const double denom = sub(cphi, mul(sphi, d.tan_e));
+                if (denom == 0.0) continue;
+                const double g = div(R.a, denom);
+                double r2 = sub(add(R.a2, mul(g, g)), mul(mul(R.twoa, g), cphi));
+                if (r2 < 0.0) r2 = 0.0;
+                const double r = sqrt_rn(r2);
+                if (r != r) continue;
+                const RangeBracket rb = range_bracket(d, rg_t, r, false);
+                const float v = sample_pairs(val0, my_az[(size_t)ie * T], rb, fill32);
+                if (v == fill32 || v != v) continue;
+                if (!(cr_best >= v)) cr_best = v;             // NaN (nothing yet) or smaller
+            }
+        }
+    }
+
+    // ---- 4. the tile's outputs, once ----
+    if (active) {
+        size_t o = (size_t)col;
+        for (int iz = 0; iz < nz; ++iz, o += (size_t)p.ncol) {
+            const size_t c = (size_t)iz * T + tid;
+            const float awv = a_wv[c], aw = a_w[c];
+            const unsigned cc = a_cc[c];
+            double out = p.out_missing;
+            if (METHOD == kNetMax || METHOD == kNetNearest) {
+                if (aw != 0.f) out = (double)awv;
+            } else {
+                if (aw > 0.f) out = (double)awv / (double)aw;            // has_data = total_weight > 0
+            }
+            if (p.composite) p.composite[o] = out;
+            if (p.npeer) {
+                const size_t at = (size_t)iz * (size_t)p.peer_plane + (size_t)p.peer_off + (size_t)col;
+                for (int q = 0; q < p.npeer; ++q) p.peer[q][at] = out;
+            }
+            if (p.valid_count) p.valid_count[o] = (int16_t)(cc & 0xffu);
+            if (p.coverage) p.coverage[o] = (int16_t)(cc >> 8);
+            if (p.blind) p.blind[o] = (int8_t)((cc >> 8) == 0u);
+        }
+        if (p.cr) p.cr[col] = (double)cr_best;               // NaN where no radar has an echo
+    }
+    if (ties && p.tie_count) atomicAdd(p.tie_count, ties);
+}
+
+}  // namespace pcg

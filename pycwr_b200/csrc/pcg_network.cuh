@@ -87,6 +87,10 @@ struct NetArgs {
     double* cr;                      // [ncol] or NULL (NaN where no radar has an echo)
     double* quality_out;             // [nz][ncol] or NULL: quality weight of the LAST radar (per-radar diagnostics)
     unsigned long long* tie_count;   // voxels whose observability was decided by the twin chain
+    // tile-persistent kernel (pcg_net2.cuh)
+    double out_missing;              // value stored in empty composite cells (fill, or NaN for the dataset layout)
+    int ne_max;                      // most sweeps of any radar: rows of the shared-memory azimuth table
+    int z0;                          // first level of this launch (level chunks when the accumulators exceed shared memory)
     // multi-GPU: this rank's slab of the composite is also stored into the full grid of every peer (NVLink P2P
     // stores from the finalize kernel: the all-gather of the finished slabs, fused with producing them)
     int npeer;

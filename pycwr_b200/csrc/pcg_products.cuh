@@ -73,6 +73,8 @@ struct ColumnArgs {
     double* vil;
     double* et;
     unsigned char* topped;
+    int nan_as_fill;            // the volume already carries NaN in its empty cells (the network tile kernel stores the
+                                // dataset's marker itself): read them back as `fill`, which is what derive_et sees
 };
 
 __global__ void __launch_bounds__(256) column_kernel(const __grid_constant__ ColumnArgs p) {
@@ -85,7 +87,8 @@ __global__ void __launch_bounds__(256) column_kernel(const __grid_constant__ Col
         double vil = 0.0, prev_liq = 0.0, prev_z = 0.0;
         int top = -1;
         for (int k = 0; k < p.nz; ++k) {
-            const double v = p.vol[(size_t)k * (size_t)p.ncol + (size_t)c];
+            double v = p.vol[(size_t)k * (size_t)p.ncol + (size_t)c];
+            if (p.nan_as_fill && v != v) v = p.fill;
             const bool ok = finite_not_fill(v, p.fill);
             if (ok) { any = true; if (v > best) best = v; }
             if (p.vil) {
@@ -116,7 +119,8 @@ __global__ void __launch_bounds__(256) column_kernel(const __grid_constant__ Col
                 else {
                     const double z1 = p.levels[top + 1];
                     const double v0 = p.vol[(size_t)top * (size_t)p.ncol + (size_t)c];
-                    const double v1 = p.vol[(size_t)(top + 1) * (size_t)p.ncol + (size_t)c];
+                    double v1 = p.vol[(size_t)(top + 1) * (size_t)p.ncol + (size_t)c];
+                    if (p.nan_as_fill && v1 != v1) v1 = p.fill;
                     const bool fin1 = (v1 == v1) && (fabs(v1) != inf);
                     if (fin1 && v1 < p.threshold && v0 > p.threshold && v1 != v0)
                         et = add(z0, mul(div(sub(p.threshold, v0), sub(v1, v0)), sub(z1, z0)));

@@ -1,21 +1,26 @@
-// pcg_r3.cuh — kernel v8 of get_CAPPI_3d: the r2-space voxel path of pcg_r2.cuh with level-to-level reuse.
+// pcg_r3.cuh — kernel v8 of get_CAPPI_3d / get_CAPPI_xy / one radar of the mosaic (RadarGridC.pyx:356-593).
 //
-// Along a grid column the slant range and the elevation grow monotonically with the level, so consecutive
-// levels mostly fall between the same two sweeps AND between the same two gates (measured on config C3: 81 % keep
-// their sweep pair, 63 % their sweep pair and gate).  The reference re-derives everything per voxel
-// (RadarGridC.pyx:404-477); v7 (pcg_r2.cuh) still re-issued, per voxel, the gate-threshold gather, two 128-bit
-// quad gathers, the azimuth entries and four azimuth lerps.  Here a thread keeps, across levels,
-//   * the gate band [tg[j], tg[j+1]) of its current bracket as two doubles: `r2` inside it <=> same gate (exact,
-//     the very comparison v7 made after its gather), and
-//   * the four azimuth-interpolated samples of both sweeps at that gate pair,
-// and only the lanes that left their band redo the gathers (predicated: fewer active lanes per request, fewer
-// L1 wavefronts).  What every voxel still pays is r2, the sweep-pair confirmation, the two FP32 weights and three
-// lerps.  The quads are resolved against missing data in RANGE as well at pack time (pack_quads_kernel), so
-// the range lerp needs no fill test: a quad is either all-fill or fill-free.
-//
-// Also new against v7: azimuth table [sweep][thread] (conflict-free shared-memory reads), a straight-line
-// azimuth bracket for interior guesses, the slow path takes its arguments by value (the hot loop holds no
-// ColumnCtx, hence no local memory), merge-max as a template parameter.
+// Same decisions as v7 (pcg_r2.cuh: every comparison of the reference made on r^2 against host-built thresholds, so
+// the selected sweeps / rays / gates are the reference's by construction), rebuilt around what the ncu profiles of v7
+// showed (profiles/r01_final_cappi3d_r2.md, profiles/r02_*):
+//   * v7 was bound by the L1 data pipe (75-85 % busy), not by instruction issue: a warp-wide 128-bit load writes
+//     512 bytes back to the register file whether its 32 addresses differ or not, and v7 issued five per voxel.
+//     Two of them (the sweep-pair confirmation entry and the pair record) are the same for all lanes that share a
+//     sweep pair: here the threshold rows of a launch's levels and the pair polynomials ride in the KERNEL
+//     PARAMETERS (constant bank, up to 32 764 bytes) and are read through the constant cache (CT kernels).
+//   * the remaining loads of a level (gate band, two azimuth entries, two quads per moment) are requested TOGETHER,
+//     before anything is compared, for the sweep pair the column is in (uniform-table volumes: every speculative
+//     address is valid) — one memory round trip per level instead of three dependent ones; a column that leaves
+//     its pair walks to the new one and asks again.
+//   * the reference chain for the rare voxels that need it (guard bands, range gating ...) runs AFTER the level
+//     loop on a bit mask of marked levels: the hot loop contains no call and keeps its state in registers;
+//     loop-invariant parameters are pinned in registers (ptxas otherwise re-reads them every level).
+//   * azimuth table [sweep][thread] (conflict-free), interior azimuth brackets verified in line with one repair
+//     step, quads resolved against missing data in RANGE as well at pack time (pack_quads_kernel): a quad is either
+//     all-fill or fill-free, so only the elevation lerp tests for fill.
+// Measured and rejected on B200: carrying the gate band and the azimuth-lerped samples from level
+// to level (63 % of the voxels keep both) — fewer L1 wavefronts, but nearly every warp has a lane that left its
+// band, so the warp walks both paths and ends up slower.
 #pragma once
 #include "pcg_r2.cuh"
 
@@ -73,6 +78,21 @@ __device__ __noinline__ void r3_slow_voxel(const SlowArgs* a, const LevelConst* 
     for (int f = 0; f < NF; ++f) res[f] = tmp[f];
 }
 
+// The r2-space threshold rows of a launch's levels and the pair polynomials travel in the KERNEL PARAMETERS
+// (constant bank, up to 32 764 bytes since CUDA 12.1) when they fit: a warp mostly shares its sweep pair, so the
+// 32-byte confirmation / pair record of a voxel is one constant-cache broadcast instead of two 128-bit loads per
+// LANE through the L1 data pipe — which, at 512 bytes of register write-back per warp-wide 128-bit load, was the
+// limiter of v7 (l1tex data-pipe 75-85 % busy, measured; profiles/r02_*).  Rows that do not fit (many sweeps) stay
+// in global memory (CT = false).
+constexpr int kR3TabBytes = 27 * 1024;
+constexpr int kR3PolySweeps = 16;
+struct R3Args {
+    R2Args a;
+    float poly[kR3PolySweeps][8];                   // q1 .. q5 of pair (k, k+1), padded to 32 bytes
+    double tab[kR3TabBytes / 8];                    // rows of this launch's levels (CT kernels), as 8-byte words
+};
+static_assert(sizeof(R3Args) <= 32764, "kernel parameters are limited to 32764 bytes");
+
 #ifndef R3_MINB
 #define R3_MINB 4
 #endif
@@ -110,8 +130,9 @@ __device__ __forceinline__ float lds_f(unsigned addr) {
     return v;
 }
 
-template <int NF, bool EMIT, bool UNI, bool MERGE>
-__global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_constant__ R2Args P) {
+template <int NF, bool EMIT, bool UNI, bool MERGE, bool CT>
+__global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_constant__ R3Args Q) {
+    const R2Args& P = Q.a;
     const FastArgs& p = P.base;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ne = p.vol.ne;
@@ -170,14 +191,21 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
 #pragma unroll 1
         for (int sw = 0; sw < ne; ++sw) {
             const AzDesc d = s_ad[sw];
-            const int g = __double2int_rd(mul(sub(az, d.az_first), d.az_inv_step)) + 1;
+            int g = __double2int_rd(mul(sub(az, d.az_first), d.az_inv_step)) + 1;
             AzEntry e;
             int rec;
             bool done = false;
+            // interior brackets in line: entries g-1 and g must both exist (1 <= g <= naz-1).  Jittered tables
+            // put the arithmetic guess off by one for a few lanes of almost every warp: one repair step in line.
             if (g >= 1 && g < d.naz) {
                 const double2* Tt = azt + d.az_off + (unsigned)(g - 1);
-                const double2 lo = __ldg(Tt);
-                const double hi = __ldg(&Tt[1].x);
+                double2 lo = __ldg(Tt);
+                double hi = __ldg(&Tt[1].x);
+                if (az < lo.x) {
+                    if (g >= 2) { --g; hi = lo.x; lo = __ldg(Tt - 1); }
+                } else if (!(az < hi)) {
+                    if (g + 1 < d.naz) { ++g; lo = __ldg(Tt + 1); hi = __ldg(&Tt[2].x); }
+                }
                 if (!(az < lo.x) && (az < hi)) {
                     e.row = d.val_off + (unsigned)(g - 1) * (unsigned)d.ng;
                     e.w = (float)sub(az, lo.x) * (float)lo.y;
@@ -214,145 +242,181 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
         R3_PIN(az_addr); R3_PIN(az_pitch); R3_PIN(fs_addr);
         if (UNI) { R3_PIN(u_inv_step); R3_PIN(u_c0); R3_PIN(u_step); R3_PIN(u_r_first); R3_PIN(u_ngm1); R3_PIN(u_rng_off); }
     }
-    const char* lrow = reinterpret_cast<const char*>(P.r2.lp);   // this level's row (block-uniform)
+    const char* lrow = reinterpret_cast<const char*>(P.r2.lp);   // this level's row (block-uniform), global copy
+    unsigned tab_off = 0;                                          // the same row inside Q.tab (CT)
+    // one 16-byte half of a 32-byte record of this level's row
+    auto row16 = [&](unsigned byte_off) -> int4 {
+        if (CT) {                                                  // two 64-bit constant-bank loads
+            const unsigned w = (tab_off + byte_off) >> 3;
+            const double a = Q.tab[w], b = Q.tab[w + 1];
+            return make_int4(__double2loint(a), __double2hiint(a), __double2loint(b), __double2hiint(b));
+        }
+        return __ldg(reinterpret_cast<const int4*>(lrow + byte_off));
+    };
+    auto as_d2 = [](const int4& v) -> double2 {
+        return make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z));
+    };
     int k = -1, k6 = 0;
-    // the cached bracket: gate band in r2 space (empty = nothing cached), R[j], 1 / dR, the azimuth-lerped samples
-    double c_lo = __longlong_as_double(0x7ff0000000000000LL), c_hi = 0.0;
-    float c_rj = 0.f, c_idr = UNI ? u_inv_step : 0.f;
-    int c_gi = 0;
-    float ca0[NF], ca1[NF], cb0[NF], cb1[NF];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) { ca0[f] = ca1[f] = cb0[f] = cb1[f] = fill32; }
     char* out_b = reinterpret_cast<char*>(p.out + col);
     const size_t lvl_bytes = (size_t)ncol * sizeof(double);
     // levels whose voxel needs the reference chain are only MARKED here and resolved after the loop: the hot
     // loop then contains no call, so its state stays in registers (kMaxLevelsPerLaunch <= 64)
     unsigned long long slow_mask = 0ull;
+#ifndef R3_NOSPEC
+    constexpr bool SPEC = UNI;      // uniform-table volumes: every speculative address below is valid
+#else
+    constexpr bool SPEC = false;
+#endif
 
 #pragma unroll 1
-    for (int iz = 0; iz < p.nz; ++iz, lrow += row_bytes, out_b += lvl_bytes) {
+    for (int iz = 0; iz < p.nz; ++iz, lrow += row_bytes, tab_off += row_bytes, out_b += lvl_bytes) {
         float res[NF];
         int st_state = kEmpty, st_lower = -1, st_upper = -1, r_iaz0 = -1, r_ir0 = -1, r_fl0 = -1, r_iaz1 = -1, r_ir1 = -1,
             r_fl1 = -1;
         // RadarGridC.pyx:146-149 — the reference's own operations: r2 is bit-identical
         const double r2 = sub(p.levels[iz].a2g2, mul(p.levels[iz].twoag, cphi));
+        const float r2f = (float)r2;
+        const float rinv = rsqrt_approx(r2f);
+        const float rf = r2f * rinv;
         bool slow = false;
-        {
-            const double2 cf = __ldg(reinterpret_cast<const double2*>(lrow + (unsigned)(k + 1) * 32u));
-            if (!((r2 < cf.x) & (r2 > cf.y))) {
-                // the column left its sweep pair: walk the per-sweep bands (pcg_r2.cuh), drop the cached bracket
-                const char* ls = lrow + ls_off;
-                c_lo = __longlong_as_double(0x7ff0000000000000LL);
+        // SPEC: everything a voxel of the CURRENT sweep pair needs is requested before anything is compared —
+        // confirmation entry, pair record, the gate band of the guessed gate, both azimuth entries, the quads —
+        // so a level costs one memory round trip instead of three dependent ones; a column that leaves its pair
+        // (19 % of the voxels at config C3) walks to the new pair and asks again.
+        int4 lk;
+        double2 tg = make_double2(0.0, 0.0);
+        int gi = 1;
+        AzEntry ea, eb;
+        float4 qa4[NF], qb4[NF];
+        ea.row = 0u; ea.w = 0.f; eb = ea;
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) { qa4[fi] = make_float4(0.f, 0.f, 0.f, 0.f); qb4[fi] = qa4[fi]; }
 #pragma unroll 1
-                for (;;) {
-                    const double2* row = reinterpret_cast<const double2*>(ls + (unsigned)(k + 1) * 32u);
-                    const double2 cur = __ldg(row);
-                    const double2 nxt = __ldg(row + 2);
-                    if ((r2 < cur.x) & (r2 > nxt.y)) break;
-                    if (r2 > cur.y) { --k; continue; }
-                    if (r2 < nxt.x) { ++k; continue; }
-                    slow = true;
-                    break;
+        for (;;) {
+            const unsigned pk = (unsigned)(k + 1) * 32u;
+            const double2 cf = as_d2(row16(pk));
+            lk = row16(pk + 16u);                                 // {rho2, rho, b1} of pair k: used if k is confirmed
+            if (SPEC) {
+                const int lo_s = max(k, 0), hi_s = min(lo_s + 1, ne - 1);
+                gi = min(max(__float2int_rd(fmaf(rf, u_inv_step, u_c0)), 1), u_ngm1);
+                tg = __ldg(g_t + (u_rng_off + (unsigned)(gi - 1)));
+                ea = lds_az(az_addr + (unsigned)lo_s * az_pitch);
+                eb = lds_az(az_addr + (unsigned)hi_s * az_pitch);
+#pragma unroll
+                for (int fi = 0; fi < NF; ++fi) {
+                    const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
+                    qa4[fi] = __ldg(v + (ea.row + (unsigned)gi));
+                    qb4[fi] = __ldg(v + (eb.row + (unsigned)gi));
                 }
             }
-        }
-        if (!slow) {
-            const bool pair = (unsigned)k < pair_top;
-            const bool skip = (unsigned)(k - k_first) > k_span;
-            const int lower = max(k, 0);
-            if (EMIT) {
-                st_state = skip ? (pair ? kPair : (k < 0 ? kSkipLow : kSkipHigh)) : (pair ? kPair : kSingle);
-                st_lower = lower; st_upper = lower + (pair ? 1 : 0);
+            if ((r2 < cf.x) & (r2 > cf.y)) break;
+            // the column left its sweep pair: walk the per-sweep bands (pcg_r2.cuh)
+#pragma unroll 1
+            for (;;) {
+                const unsigned ro = ls_off + (unsigned)(k + 1) * 32u;
+                const double2 cur = as_d2(row16(ro));
+                const double2 nxt = as_d2(row16(ro + 32u));
+                if ((r2 < cur.x) & (r2 > nxt.y)) break;
+                if (r2 > cur.y) { --k; continue; }
+                if (r2 < nxt.x) { ++k; continue; }
+                slow = true;
+                break;
             }
-            if (skip) {
-#pragma unroll
-                for (int f = 0; f < NF; ++f) res[f] = fill32;
-            } else {
-                const float r2f = (float)r2;
-                const float rinv = rsqrt_approx(r2f);
-                const float rf = r2f * rinv;
-                if (!((r2 >= c_lo) & (r2 < c_hi))) {
-                    // ---- new gate (or new sweep pair): bracket, gather, azimuth lerps ----
-                    const FastSweep* f = s_fs + lower;
-                    unsigned rng_off = u_rng_off;
-                    int ngm1 = u_ngm1;
-                    float inv_step = u_inv_step, c0 = u_c0;
-                    bool usable = true;
-                    if (!UNI) {
-                        const int4 tab = *reinterpret_cast<const int4*>(&f->rng_off);
-                        rng_off = (unsigned)tab.x; ngm1 = tab.y; c0 = __int_as_float(tab.z); inv_step = __int_as_float(tab.w);
-                        const int need = pair ? (kFsPolyOk | kFsShared | kFsUsable) : kFsUsable;
-                        usable = (f->flags & need) == need;
-                    }
-                    const int gi = usable ? min(max(__float2int_rd(fmaf(rf, inv_step, c0)), 1), ngm1) : 1;
-                    const unsigned gidx = usable ? rng_off + (unsigned)(gi - 1) : u_rng_off;
-                    const double2 tg = __ldg(g_t + gidx);        // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
-                    if (usable & (r2 >= tg.x) & (r2 < tg.y)) {
-                        c_lo = tg.x; c_hi = tg.y;
-                        if (UNI) {
-                            c_rj = fmaf((float)(gi - 1), u_step, u_r_first);
-                        } else {
-                            const int4 hv = __ldg(reinterpret_cast<const int4*>(P.r2.h_t + gidx));   // {R^2, R, 1/dR}
-                            c_rj = __int_as_float(hv.z); c_idr = __int_as_float(hv.w);
-                        }
-                        if (EMIT) c_gi = gi;
-                        const AzEntry ea = lds_az(az_addr + (unsigned)lower * az_pitch);
-#pragma unroll
-                        for (int fi = 0; fi < NF; ++fi) {
-                            const float4 q = __ldg((fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi])) + (ea.row + (unsigned)gi));
-                            ca0[fi] = fmaf(ea.w, q.y - q.x, q.x);
-                            ca1[fi] = fmaf(ea.w, q.w - q.z, q.z);
-                        }
-                        if (pair) {
-                            const AzEntry eb = lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
-#pragma unroll
-                            for (int fi = 0; fi < NF; ++fi) {
-                                const float4 q = __ldg((fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi])) + (eb.row + (unsigned)gi));
-                                cb0[fi] = fmaf(eb.w, q.y - q.x, q.x);
-                                cb1[fi] = fmaf(eb.w, q.w - q.z, q.z);
-                            }
-                        }
-                    } else {
-                        slow = true;
-                    }
-                }
-                if (!slow) {
-                    // ---- every voxel: the two weights and three lerps (RadarGridC.pyx:297-299,469-476) ----
-                    // tg[j] is R[j]^2 to within two ulps: w_r = (r^2 - R[j]^2) / ((r + R[j]) dR)
-                    const float w_r = (float)sub(r2, c_lo) * c_idr * rcp_approx(rf + c_rj);
-                    if (pair) {
-                        const int4 lk = __ldg(reinterpret_cast<const int4*>(lrow + (unsigned)(k + 1) * 32u) + 1);   // {rho2, rho, b1}
-                        const float u = (float)sub(r2, __hiloint2double(lk.y, lk.x)) * rcp_approx(rf + __int_as_float(lk.z)) *
-                                        fmaf(__int_as_float(lk.w), rinv, inv2a);
-                        const unsigned fa = fs_addr + (unsigned)lower * (unsigned)sizeof(FastSweep);
-                        const float4 qa = lds_f4(fa);                 // q1 .. q4
-                        float w_el = fmaf(lds_f(fa + 16u), u, qa.w);  // q5
-                        w_el = fmaf(w_el, u, qa.z);
-                        w_el = fmaf(w_el, u, qa.y);
-                        w_el = fmaf(w_el, u, qa.x);
-                        w_el *= u;
-#pragma unroll
-                        for (int fi = 0; fi < NF; ++fi) {
-                            const float v0 = fmaf(w_r, ca1[fi] - ca0[fi], ca0[fi]);
-                            const float v1 = fmaf(w_r, cb1[fi] - cb0[fi], cb0[fi]);
-                            res[fi] = lerp_fill(w_el, v0, v1, fill32);
-                        }
-                    } else {
-#pragma unroll
-                        for (int fi = 0; fi < NF; ++fi) res[fi] = fmaf(w_r, ca1[fi] - ca0[fi], ca0[fi]);
-                    }
-                    if (EMIT) {
-                        const int ra = my_iaz[(size_t)lower * T];
-                        r_ir0 = c_gi; r_iaz0 = ra & 0x3fffffff; r_fl0 = (ra >> 30) & 1;
-                        if (pair) {
-                            const int rb2 = my_iaz[(size_t)(lower + 1) * T];
-                            r_ir1 = c_gi; r_iaz1 = rb2 & 0x3fffffff; r_fl1 = (rb2 >> 30) & 1;
-                        }
-                    }
-                }
-            }
+            if (slow) break;
         }
         if (slow) { slow_mask |= 1ull << iz; continue; }
+        const bool pair = (unsigned)k < pair_top;
+        const bool skip = (unsigned)(k - k_first) > k_span;
+        const int lower = max(k, 0);
+        if (EMIT) {
+            st_state = skip ? (pair ? kPair : (k < 0 ? kSkipLow : kSkipHigh)) : (pair ? kPair : kSingle);
+            st_lower = lower; st_upper = lower + (pair ? 1 : 0);
+        }
+        if (skip) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) res[f] = fill32;
+        } else {
+            float rj, idr;
+            if (SPEC) {
+                if (!((r2 >= tg.x) & (r2 < tg.y))) { slow_mask |= 1ull << iz; continue; }
+                rj = fmaf((float)(gi - 1), u_step, u_r_first); idr = u_inv_step;
+            } else {
+                // ---- bracket, then gather (volumes with ragged / irregular / degenerate tables) ----
+                const FastSweep* f = s_fs + lower;
+                unsigned rng_off = u_rng_off;
+                int ngm1 = u_ngm1;
+                float inv_step = u_inv_step, c0 = u_c0;
+                bool usable = true;
+                if (!UNI) {
+                    const int4 tab = *reinterpret_cast<const int4*>(&f->rng_off);
+                    rng_off = (unsigned)tab.x; ngm1 = tab.y; c0 = __int_as_float(tab.z); inv_step = __int_as_float(tab.w);
+                    const int need = pair ? (kFsPolyOk | kFsShared | kFsUsable) : kFsUsable;
+                    usable = (f->flags & need) == need;
+                }
+                gi = usable ? min(max(__float2int_rd(fmaf(rf, inv_step, c0)), 1), ngm1) : 1;
+                const unsigned gidx = usable ? rng_off + (unsigned)(gi - 1) : u_rng_off;
+                tg = __ldg(g_t + gidx);                          // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
+                if (!(usable & (r2 >= tg.x) & (r2 < tg.y))) { slow_mask |= 1ull << iz; continue; }
+                if (UNI) {
+                    rj = fmaf((float)(gi - 1), u_step, u_r_first); idr = u_inv_step;
+                } else {
+                    const int4 hv = __ldg(reinterpret_cast<const int4*>(P.r2.h_t + gidx));   // {R^2, R, 1/dR}
+                    rj = __int_as_float(hv.z); idr = __int_as_float(hv.w);
+                }
+                ea = lds_az(az_addr + (unsigned)lower * az_pitch);
+                if (pair) eb = lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
+#pragma unroll
+                for (int fi = 0; fi < NF; ++fi) {
+                    const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
+                    qa4[fi] = __ldg(v + (ea.row + (unsigned)gi));
+                    if (pair) qb4[fi] = __ldg(v + (eb.row + (unsigned)gi));
+                }
+            }
+            // ---- the two weights and the lerps (RadarGridC.pyx:297-299,469-476) ----
+            // tg[j] is R[j]^2 to within two ulps: w_r = (r^2 - R[j]^2) / ((r + R[j]) dR)
+            const float w_r = (float)sub(r2, tg.x) * idr * rcp_approx(rf + rj);
+            if (pair) {
+                const float u = (float)sub(r2, __hiloint2double(lk.y, lk.x)) * rcp_approx(rf + __int_as_float(lk.z)) *
+                                fmaf(__int_as_float(lk.w), rinv, inv2a);
+                float4 qa;                                    // q1 .. q4
+                float q5;
+                if (CT) {
+                    qa = *reinterpret_cast<const float4*>(&Q.poly[lower][0]);
+                    q5 = Q.poly[lower][4];
+                } else {
+                    const unsigned fa = fs_addr + (unsigned)lower * (unsigned)sizeof(FastSweep);
+                    qa = lds_f4(fa);
+                    q5 = lds_f(fa + 16u);
+                }
+                float w_el = fmaf(q5, u, qa.w);
+                w_el = fmaf(w_el, u, qa.z);
+                w_el = fmaf(w_el, u, qa.y);
+                w_el = fmaf(w_el, u, qa.x);
+                w_el *= u;
+#pragma unroll
+                for (int fi = 0; fi < NF; ++fi) {
+                    const float ea0 = fmaf(ea.w, qa4[fi].y - qa4[fi].x, qa4[fi].x), ea1 = fmaf(ea.w, qa4[fi].w - qa4[fi].z, qa4[fi].z);
+                    const float eb0 = fmaf(eb.w, qb4[fi].y - qb4[fi].x, qb4[fi].x), eb1 = fmaf(eb.w, qb4[fi].w - qb4[fi].z, qb4[fi].z);
+                    const float v0 = fmaf(w_r, ea1 - ea0, ea0);
+                    const float v1 = fmaf(w_r, eb1 - eb0, eb0);
+                    res[fi] = lerp_fill(w_el, v0, v1, fill32);
+                }
+            } else {
+#pragma unroll
+                for (int fi = 0; fi < NF; ++fi) {
+                    const float ea0 = fmaf(ea.w, qa4[fi].y - qa4[fi].x, qa4[fi].x), ea1 = fmaf(ea.w, qa4[fi].w - qa4[fi].z, qa4[fi].z);
+                    res[fi] = fmaf(w_r, ea1 - ea0, ea0);
+                }
+            }
+            if (EMIT) {
+                const int ra = my_iaz[(size_t)lower * T];
+                r_ir0 = gi; r_iaz0 = ra & 0x3fffffff; r_fl0 = (ra >> 30) & 1;
+                if (pair) {
+                    const int rb2 = my_iaz[(size_t)(lower + 1) * T];
+                    r_ir1 = gi; r_iaz1 = rb2 & 0x3fffffff; r_fl1 = (rb2 >> 30) & 1;
+                }
+            }
+        }
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             double* dst = reinterpret_cast<double*>(out_b) + (size_t)f * (size_t)p.field_stride;

@@ -280,7 +280,7 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
                     quality_weight_terms=("range", "beam", "vertical"), range_decay_m=230000.0,
                     beam_radius_ref_m=3000.0, vertical_gap_ref_deg=0.5, beam_widths=None, effective_earth_radius=None,
                     sanity_filter=True, outputs=("valid_count", "coverage_count", "blind_mask", "CR"), rows=None,
-                    allow_empty=False, missing=None, column_products=None, composite=True):
+                    allow_empty=False, missing=None, column_products=None, composite=True, devices=None):
     """All radars of one field merged in one fused kernel launch.
 
     ``volumes``: packed :class:`DeviceVolume` per radar (field 0 is used).  ``rows=(r0, r1)``
@@ -293,8 +293,24 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
     of ``build_network_dataset``, applied on the device).  ``column_products=(vil_min_dbz, vil_max_dbz_cap,
     et_threshold_dbz)`` adds ``VIL`` / ``ET`` / ``ET_TOPPED`` of the composite, computed before it leaves the
     device; ``composite=False`` then skips returning the volume itself.
+
+    ``devices=[d0, d1, ...]`` (with :class:`~pycwr_b200.runtime.HostVolume` volumes): ONE call over several GPUs of
+    the box — the grid's rows are split into slabs balanced by the (column, radar) pairs they hold, one host thread
+    per GPU packs the radars reaching its slab, composites it and returns its rows over that GPU's own PCIe link into
+    the shared pinned result arrays (no device-to-device exchange: the consumer of the product is the host).  The
+    device analogue of the reference's fork pool (RadarInterp.py:1816-1861); results equal the single-GPU call's
+    bit for bit.
     """
     method = _check_method(method)
+    if devices is not None:
+        if rows is not None:
+            raise ValueError("rows= and devices= are two ways of sharding: give one")
+        return _network_compose_devices(
+            list(devices), volumes, radar_sites_xy, radar_heights, grid_x, grid_y, level_heights, fillvalue, method,
+            influence_radius_m, blind_method, quality_weight_terms, range_decay_m, beam_radius_ref_m,
+            vertical_gap_ref_deg, beam_widths, effective_earth_radius, sanity_filter, outputs, missing,
+            column_products, composite)
+    volumes = [v.on() if hasattr(v, "on") else v for v in volumes]
     gx = _f64_2d(grid_x, "grid_x")
     gy = _f64_2d(grid_y, "grid_y")
     if gy.shape != gx.shape:
@@ -398,6 +414,139 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
             ctypes.byref(ties), None if cpar is None else cpar.ctypes.data_as(_lib.c_double_p),
             ptr("VIL"), ptr("ET"), ptr("ET_TOPPED")))
     res["tie_voxels"] = int(ties.value)
+    return res
+
+
+def _network_compose_devices(devices, volumes, radar_sites_xy, radar_heights, grid_x, grid_y, level_heights, fillvalue,
+                             method, influence_radius_m, blind_method, quality_weight_terms, range_decay_m,
+                             beam_radius_ref_m, vertical_gap_ref_deg, beam_widths, effective_earth_radius,
+                             sanity_filter, outputs, missing, column_products, composite):
+    """``network_compose`` over several GPUs of one box: row slabs, one host thread per GPU, every slab written by
+    its own GPU into the shared pinned result (``pcg_network_compose_rows``)."""
+    import threading
+
+    from . import sharding
+    if not devices:
+        raise ValueError("devices must name at least one GPU")
+    n = len(volumes)
+    if n == 0:
+        raise ValueError("radar_volumes must contain at least one volume.")
+    if any(not hasattr(v, "on") for v in volumes):
+        raise ValueError("devices= needs HostVolume objects (each GPU packs the radars its slab needs)")
+    gx = _f64_2d(grid_x, "grid_x")
+    gy = _f64_2d(grid_y, "grid_y")
+    if gy.shape != gx.shape:
+        raise ValueError("grid_x and grid_y must have the same shape.")
+    levels = np.ascontiguousarray(np.asarray(level_heights, dtype=np.float64).ravel())
+    sites = np.ascontiguousarray(np.asarray(radar_sites_xy, dtype=np.float64).reshape(n, 2))
+    rh = np.ascontiguousarray(np.asarray(radar_heights, dtype=np.float64).ravel())
+    if rh.size != n:
+        raise ValueError("radar_heights must have one entry per radar.")
+    if effective_earth_radius is None or np.isscalar(effective_earth_radius):
+        radii = [effective_earth_radius] * n
+    else:
+        radii = list(effective_earth_radius)
+        if len(radii) != n:
+            raise ValueError("effective_earth_radius must be None, a scalar, or a sequence matching the radar count.")
+    re_all = np.array([G._resolve_effective_earth_radius(r) for r in radii], dtype=np.float64)
+    prm = _lib.NetworkParams(
+        _lib.NET_METHODS[method], G._resolve_blind_code(blind_method),
+        sum(_lib.QUALITY_TERMS[t] for t in set(quality_weight_terms or []) if t in _lib.QUALITY_TERMS),
+        1 if sanity_filter else 0, float(influence_radius_m), float(range_decay_m), float(beam_radius_ref_m),
+        float(vertical_gap_ref_deg))
+    nz, (nx, ny) = int(levels.size), gx.shape
+    shape = (nz, nx, ny)
+    want = set(outputs or ())
+    miss = float(fillvalue if missing is None else missing)
+    res = {}
+    if composite or column_products is None:
+        res["composite"] = pinned_empty(shape, np.float64)
+    cpar = None
+    if column_products is not None:
+        cpar = np.ascontiguousarray(column_products, dtype=np.float64).ravel()
+        if cpar.size != 3:
+            raise ValueError("column_products must be (vil_min_dbz, vil_max_dbz_cap, et_threshold_dbz)")
+        res["VIL"] = pinned_empty((nx, ny), np.float64)
+        res["ET"] = pinned_empty((nx, ny), np.float64)
+        res["ET_TOPPED"] = pinned_empty((nx, ny), np.uint8)
+    if "valid_count" in want:
+        res["valid_count"] = pinned_empty(shape, np.int16)
+    if "coverage_count" in want or "blind_mask" in want:
+        res["coverage_count"] = pinned_empty(shape, np.int16)
+        res["blind_mask"] = pinned_empty(shape, np.int8)
+    if "CR" in want:
+        res["CR"] = pinned_empty((nx, ny), np.float64)
+    reach = [sharding.radar_reach_m(v.vol_range) for v in volumes]
+    bounds = sharding.slab_bounds_weighted(sharding.row_costs(gx, gy, sites, reach), len(devices))
+    ties = [0] * len(devices)
+    errors = []
+
+    def ptr(key):
+        return _lib.as_ptr(res[key]) if key in res else None
+
+    def slab(di):
+        try:
+            r0, r1 = bounds[di]
+            if r1 <= r0:
+                return
+            idx = sharding.radars_reaching(gx[r0:r1], gy[r0:r1], sites, reach)
+            if not idx or nx * ny == 0:
+                for key, val in (("composite", miss), ("valid_count", 0), ("coverage_count", 0), ("blind_mask", 1),
+                                 ("CR", np.nan), ("VIL", np.nan), ("ET", np.nan), ("ET_TOPPED", 0)):
+                    if key in res:
+                        res[key][..., r0:r1, :] = val
+                return
+            _lib.set_device(devices[di])
+            dvs = [volumes[i].on(devices[di]) for i in idx]
+            m = len(idx)
+            keep = []
+            bwp = None
+            if beam_widths is not None:
+                ptrs = []
+                for i, dv in zip(idx, dvs):
+                    bw = beam_widths[i]
+                    if bw is None:
+                        ptrs.append(None)
+                        continue
+                    b = np.asarray(bw, dtype=np.float64).ravel()
+                    if b.size < dv.ne:
+                        b = np.concatenate([b, np.full(dv.ne - b.size, float(b[-1]))])
+                    b = np.ascontiguousarray(b[:dv.ne])
+                    keep.append(b)
+                    ptrs.append(b.ctypes.data_as(_lib.c_double_p))
+                bwp = (_lib.c_double_p * m)(*ptrs)
+            rx = np.ascontiguousarray(sites[idx, 0])
+            ry = np.ascontiguousarray(sites[idx, 1])
+            hh = np.ascontiguousarray(rh[idx])
+            rr = np.ascontiguousarray(re_all[idx])
+            handles = (ctypes.c_void_p * m)(*[v.handle for v in dvs])
+            t = ctypes.c_uint64(0)
+            dp = _lib.c_double_p
+            _lib.check(_lib.load().pcg_network_compose_rows(
+                m, handles, rx.ctypes.data_as(dp), ry.ctypes.data_as(dp), hh.ctypes.data_as(dp), rr.ctypes.data_as(dp),
+                bwp, ctypes.byref(prm), _lib.as_ptr(gx), _lib.as_ptr(gy), nx, r0, r1 - r0, ny,
+                levels.ctypes.data_as(dp), nz, float(fillvalue), miss, ptr("composite"), ptr("valid_count"),
+                ptr("coverage_count"), ptr("blind_mask"), ptr("CR"), ctypes.byref(t),
+                None if cpar is None else cpar.ctypes.data_as(dp), ptr("VIL"), ptr("ET"), ptr("ET_TOPPED")))
+            ties[di] = int(t.value)
+        except BaseException as exc:                # noqa: BLE001 - re-raised by the caller's thread below
+            errors.append(exc)
+
+    prev = _lib.current_device()
+    if len(devices) == 1:
+        slab(0)
+    else:
+        threads = [threading.Thread(target=slab, args=(di,), name="pycwr-b200-gpu%d" % devices[di])
+                   for di in range(len(devices))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    _lib.set_device(prev)
+    if errors:
+        raise errors[0]
+    res["tie_voxels"] = int(sum(ties))
+    res["slab_rows"] = [b[1] - b[0] for b in bounds]
     return res
 
 

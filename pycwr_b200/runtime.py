@@ -194,6 +194,40 @@ class DeviceVolume:
         return n.value
 
 
+class HostVolume:
+    """One radar volume held on the HOST in the reference's ``PRD.vol`` form, uploaded on demand to whichever GPU a
+    product needs it on (``on(device)``, one :class:`DeviceVolume` per device, kept until ``close``).  What the
+    multi-GPU network product takes: each GPU packs only the radars that reach its slab of the grid."""
+
+    def __init__(self, vol_azimuth, vol_range, fix_elevation, vol_value, fillvalue=-999.0, value_dtype="f32"):
+        self.vol_azimuth, self.vol_range, self.vol_value = list(vol_azimuth), list(vol_range), vol_value
+        self.fix_elevation = np.ascontiguousarray(fix_elevation, dtype=np.float64)
+        self.fillvalue, self.value_dtype = float(fillvalue), value_dtype
+        self.ne = int(self.fix_elevation.shape[0])
+        self.last_gate = np.array([r[-1] if len(r) else np.nan for r in self.vol_range], dtype=np.float64)
+        self._dev = {}
+        self._lock = threading.Lock()
+
+    def on(self, device=None):
+        """The packed volume on ``device`` (default: the calling thread's current device)."""
+        device = _lib.current_device() if device is None else int(device)
+        with self._lock:
+            dv = self._dev.get(device)
+        if dv is None:
+            _lib.set_device(device)
+            dv = DeviceVolume(self.vol_azimuth, self.vol_range, self.fix_elevation, self.vol_value,
+                              fillvalue=self.fillvalue, value_dtype=self.value_dtype)
+            with self._lock:
+                self._dev[device] = dv
+        return dv
+
+    def close(self):
+        with self._lock:
+            vols, self._dev = list(self._dev.values()), {}
+        for dv in vols:
+            dv.close()
+
+
 class _PinnedPool:
     """Recycles page-locked host blocks: pinning is slow (~ms per 10 MB), reuse is free."""
 
