@@ -15,6 +15,7 @@
 #include <map>
 #include <memory>
 #include <unordered_map>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -1681,7 +1682,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     int rc;
     if ((rc = scratch_begin(st))) return rc;                  // a previous call on another stream may still use the scratch
     bool uni = true;
-    size_t npair_total = 0, n_ls = 0;
+    size_t npair_total = 0, n_ls = 0, nsweep_total = 0;
     for (int i = 0; i < nradar; ++i) {
         if ((rc = check_volume(vols[i]))) return rc;
         if (!(re[i] > 0.0)) return fail(PCG_ERR_ARG, "effective_earth_radius must be positive");
@@ -1694,6 +1695,7 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
                         vols[i]->fill);
         uni = uni && vols[i]->uniform;
         npair_total += (size_t)(vols[i]->ne - 1);
+        nsweep_total += (size_t)vols[i]->ne;
         n_ls += (size_t)nz * (2 * vols[i]->ne + 3);
     }
     const size_t bytes_radars = sizeof(NetRadar) * (size_t)nradar;
@@ -1703,7 +1705,8 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     const size_t bytes_ls = sizeof(LevelSweep) * n_ls, bytes_lp = 0;
     const size_t off_pairs = bytes_radars, off_levels = off_pairs + bytes_pairs, off_spairs = off_levels + bytes_levels;
     const size_t off_ls = (off_spairs + bytes_spairs + 31) & ~(size_t)31, off_lp = off_ls + bytes_ls;
-    const size_t total = off_lp + bytes_lp;
+    const size_t off_pq = (off_lp + bytes_lp + 31) & ~(size_t)31;
+    const size_t total = off_pq + sizeof(NetPairQ) * nsweep_total;
     if ((rc = g_scratch[S_NET].ensure(total + 64))) return rc;
     char* d_base = (char*)g_scratch[S_NET].ptr;
 
@@ -1743,7 +1746,8 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
         NetLevel* nlevels = reinterpret_cast<NetLevel*>(blob.data() + off_levels);
         PairDesc* spairs = reinterpret_cast<PairDesc*>(blob.data() + off_spairs);
         LevelSweep* ls_all = reinterpret_cast<LevelSweep*>(blob.data() + off_ls);
-        size_t poff = 0, lsoff = 0;
+        NetPairQ* pq_all = reinterpret_cast<NetPairQ*>(blob.data() + off_pq);
+        size_t poff = 0, lsoff = 0, qoff = 0;
         std::vector<unsigned char> slow;
         for (int i = 0; i < nradar; ++i) {
             const pcg_volume* v = vols[i];
@@ -1785,6 +1789,15 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
                 R.src_lo = mn - tol;
                 R.src_hi = mx + tol;
             }
+            if (R.src_lo <= R.src_hi) {
+                float lo = (float)R.src_lo, hi = (float)R.src_hi;
+                if ((double)lo < R.src_lo) lo = nextafterf(lo, HUGE_VALF);
+                if ((double)hi > R.src_hi) hi = nextafterf(hi, -HUGE_VALF);
+                R.src_lo_f = lo; R.src_hi_f = hi;
+            } else {
+                R.src_lo_f = HUGE_VALF; R.src_hi_f = -HUGE_VALF;
+            }
+            R.pq = reinterpret_cast<const NetPairQ*>(d_base + off_pq) + qoff;
             R.inv_decay = (prm->quality_terms & kTermRange) ? (float)(1.0 / prm->range_decay_m) : 0.f;
             R.inv_r2inf4 = (float)(4.0 / (prm->influence_radius_m * prm->influence_radius_m));
             R.cull2 = reach[i] < HUGE_VAL ? reach[i] * reach[i] : HUGE_VAL;
@@ -1810,6 +1823,15 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
                 sp.c_lo = s_lo; sp.c_hi = s_hi; sp.c_mid = s_mid;
                 spairs[poff + k] = sp;
             }
+            for (int k = 0; k < ne; ++k) {          // (entry ne - 1 is only ever loaded speculatively)
+                NetPairQ& q = pq_all[qoff + k];
+                const FastSweep& f = v->fs_host[k];
+                q.q1 = f.q1; q.q2 = f.q2; q.q3 = f.q3; q.q4 = f.q4; q.q5 = f.q5;
+                q.beam_k = k + 1 < ne ? npairs[poff + k].beam_k : 0.f;
+                q.vert_w = k + 1 < ne ? npairs[poff + k].vert_w : 1.f;
+                q.pad = 0.f;
+            }
+            qoff += (size_t)ne;
             poff += (size_t)(ne - 1);
             for (int k = 0; k < nz; ++k) {
                 NetLevel& L = nlevels[(size_t)i * nz + k];
@@ -1856,7 +1878,8 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
     A.ne_max = 0;
     for (int i = 0; i < nradar; ++i) A.ne_max = vols[i]->ne > A.ne_max ? vols[i]->ne : A.ne_max;
 
-    if (use_tile_kernel()) {
+    // (the per-radar quality diagnostics are written by the radar-major passes only)
+    if (use_tile_kernel() && !d_quality) {
         // ---- one tile-persistent launch (pcg_net2.cuh): no lists, no accumulators in HBM, no finalize ----
         const bool nearest = prm->method == kNetNearest;
         int chunk = nz > 0 ? nz : 1;
@@ -1868,7 +1891,6 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
             return (size_t)((kb >= 8 && kb <= 200) ? kb : kNet2SmemKB) * 1024;
         }();
         while (chunk > 1 && net2_smem_bytes(A.ne_max, chunk, nearest) > smem_budget) --chunk;
-        if (d_quality) CUDA_TRY(cudaMemsetAsync(d_quality, 0, (size_t)nz * (size_t)ncol * sizeof(double), st));
         for (int z0 = 0; z0 < (nz > 0 ? nz : 1); z0 += chunk) {
             NetArgs B = A;
             B.z0 = z0;
@@ -1878,7 +1900,6 @@ int enqueue_network(int nradar, const pcg_volume* const* vols, const double* rad
             if (d_valid) B.valid_count = d_valid + off;
             if (d_cov) B.coverage = d_cov + off;
             if (d_blind) B.blind = d_blind + off;
-            if (d_quality) B.quality_out = d_quality + off;
             if (z0 > 0) B.cr = nullptr;
             if (B.npeer) for (int q = 0; q < B.npeer; ++q) B.peer[q] = A.peer[q] + (size_t)z0 * (size_t)A.peer_plane;
             const size_t smem = net2_smem_bytes(A.ne_max, B.nz, nearest);
@@ -2097,6 +2118,34 @@ extern "C" int pcg_network_compose(int nradar, const pcg_volume* const* vols, co
 // level's slab is one contiguous run, so the volumes go back with one pitched copy per output).  One host thread
 // per GPU calls this for its slab: every GPU returns its rows over its own PCIe link into the same pinned arrays —
 // the device analogue of the reference's fork pool (RadarInterp.py:1816-1861).
+// PCG_TRACE=1: the host-buffer network call reports where its time goes (stderr, one line per call; the stream is
+// synchronised after each stage, so the stages no longer overlap — a diagnostic, not a timing mode)
+struct StageTrace {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    char line[512];
+    int len;
+    explicit StageTrace(cudaStream_t s) : on(false), st(s), len(0) {
+        static const bool enabled = [] { const char* e = getenv("PCG_TRACE"); return e && *e && *e != '0'; }();
+        on = enabled;
+        line[0] = 0;
+        if (on) t0 = std::chrono::steady_clock::now();
+    }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        len += snprintf(line + len, sizeof(line) - (size_t)len, " %s %.2f ms", what,
+                        std::chrono::duration<double, std::milli>(t1 - t0).count());
+        if (len > (int)sizeof(line) - 1) len = (int)sizeof(line) - 1;
+        t0 = t1;
+    }
+    void flush(const char* who, int device) {
+        if (on) fprintf(stderr, "[pcg trace] %s dev %d:%s\n", who, device, line);
+    }
+};
+
 static int network_compose_host(int nradar, const pcg_volume* const* vols, const double* radar_x,
                                 const double* radar_y, const double* radar_height,
                                 const double* effective_earth_radius, const double* const* beam_widths,
@@ -2132,9 +2181,12 @@ static int network_compose_host(int nradar, const pcg_volume* const* vols, const
     if (cr && (rc = g_scratch[S_AUX3].ensure(ncol * sizeof(double)))) return rc;
     if (quality && (rc = g_scratch[S_AUX4].ensure(nvox * sizeof(double)))) return rc;
     if ((rc = g_scratch[S_TMP2].ensure(sizeof(unsigned long long)))) return rc;
+    StageTrace trace(st);
+    trace.mark("scratch");
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(g_scratch[S_TMP2].ptr, 0, sizeof(unsigned long long), st));
+    trace.mark("grid H2D");
     // the tile kernel stores the caller's missing-value marker itself; the column products read the composite
     // afterwards and know `fill` and NaN as "no data" — any other marker is applied after them, as before
     const bool marker_ok = !columns || out_missing != out_missing || memcmp(&out_missing, &fill, sizeof(double)) == 0;
@@ -2151,6 +2203,7 @@ static int network_compose_host(int nradar, const pcg_volume* const* vols, const
                          quality ? (double*)g_scratch[S_AUX4].ptr : nullptr,
                          (unsigned long long*)g_scratch[S_TMP2].ptr, st, tile_missing, &relabelled);
     if (rc) return rc;
+    trace.mark("tables + kernels");
     if (columns && ncol) {
         // VIL / ET of the composite while it is still on the device (RadarInterp.py:2064-2119 -> derive_vil /
         // derive_et, RadarProduct.py:33-85): no second trip of the volume over PCIe
@@ -2167,11 +2220,13 @@ static int network_compose_host(int nradar, const pcg_volume* const* vols, const
         if (et) CUDA_TRY(cudaMemcpyAsync(et + row0, d2 + ncol, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (et_topped) CUDA_TRY(cudaMemcpyAsync(et_topped + row0, dt, ncol, cudaMemcpyDeviceToHost, st));
     }
+    trace.mark("column products + D2H");
     if (composite && nvox) {
         if (!(relabelled && marker_ok) &&
             (rc = relabel_missing((double*)g_scratch[S_OUT].ptr, nvox, fill, out_missing, st))) return rc;
         CUDA_TRY(cudaMemcpy2DAsync(composite + row0, plane * sizeof(double), g_scratch[S_OUT].ptr, ncol * sizeof(double), ncol * sizeof(double), (size_t)nz, cudaMemcpyDeviceToHost, st));
     }
+    trace.mark("composite D2H");
     if (valid_count && nvox) CUDA_TRY(cudaMemcpy2DAsync(valid_count + row0, plane * sizeof(int16_t), g_scratch[S_AUX0].ptr, ncol * sizeof(int16_t), ncol * sizeof(int16_t), (size_t)nz, cudaMemcpyDeviceToHost, st));
     if (coverage_count && nvox) CUDA_TRY(cudaMemcpy2DAsync(coverage_count + row0, plane * sizeof(int16_t), g_scratch[S_AUX1].ptr, ncol * sizeof(int16_t), ncol * sizeof(int16_t), (size_t)nz, cudaMemcpyDeviceToHost, st));
     if (blind_mask && nvox) CUDA_TRY(cudaMemcpy2DAsync(blind_mask + row0, plane * sizeof(int8_t), g_scratch[S_AUX2].ptr, ncol * sizeof(int8_t), ncol * sizeof(int8_t), (size_t)nz, cudaMemcpyDeviceToHost, st));
@@ -2180,6 +2235,12 @@ static int network_compose_host(int nradar, const pcg_volume* const* vols, const
     unsigned long long ties = 0;
     CUDA_TRY(cudaMemcpyAsync(&ties, g_scratch[S_TMP2].ptr, sizeof(ties), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    trace.mark("counts / masks / CR D2H");
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        trace.flush("network_compose_host", dev);
+    }
     if (tie_voxels) *tie_voxels = ties;
     return PCG_OK;
 }

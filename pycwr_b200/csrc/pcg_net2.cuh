@@ -26,6 +26,34 @@
 namespace pcg {
 
 constexpr int kNet2Threads = 128;
+#ifndef NET2_PANEL
+#define NET2_PANEL 8
+#endif
+// Tiles are numbered in PANELS of NET2_PANEL tiles across y, x fastest inside a panel, so that the ~600 blocks
+// resident at any time cover a compact ~300 x 256-column patch of the grid instead of a 25-row band across all of it:
+// they then gather from the same three or four radar volumes (L2-resident together) rather than from every radar the
+// band crosses.  NET2_PANEL = 0: row-band order.
+__device__ __forceinline__ void net2_tile_column(const NetArgs& p, int tile, bool& active, long long& col) {
+    const int pyl = p.py_log2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int ly = lane & ((1 << pyl) - 1), lx = lane >> pyl;
+    int by, bx;
+    if (NET2_PANEL > 0) {
+        const int tiles_x = (p.nx + (32 >> pyl) - 1) / (32 >> pyl);
+        const int per_panel = NET2_PANEL * tiles_x;
+        const int panel = tile / per_panel, r = tile - panel * per_panel;
+        const int width = min(NET2_PANEL, p.tiles_y - panel * NET2_PANEL);
+        bx = r / width;
+        by = panel * NET2_PANEL + (r - bx * width);
+    } else {
+        by = tile % p.tiles_y; bx = tile / p.tiles_y;
+    }
+    int iy = ((by * nwarp + warp) << pyl) + ly;
+    int ix = bx * (32 >> pyl) + lx;
+    active = (ix < p.nx) & (iy < p.ny);
+    ix = min(ix, p.nx - 1); iy = min(iy, p.ny - 1);
+    col = (long long)ix * p.ny + iy;
+}
 #ifndef NET2_MINB
 #define NET2_MINB 4
 #endif
@@ -54,6 +82,23 @@ __device__ __noinline__ bool net2_obs_edge(double r2, const NetPair* np, double 
     return twin_observable(x, y, *R, *L, R->vol.sweeps, R->npairs, R->ne);
 }
 
+__device__ __forceinline__ float2 lds_f2(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f2(unsigned addr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned addr, unsigned v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+
 template <int METHOD, bool UNI>
 __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const __grid_constant__ NetArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -62,16 +107,15 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
     int* s_nlist = reinterpret_cast<int*>(smem_raw + 128);
     unsigned char* s_list = smem_raw + 256;                                        // [256] hit flags, then the list
     AzEntry* s_az = reinterpret_cast<AzEntry*>(smem_raw + 512);                    // [ne_max][T]
-    float* a_wv = reinterpret_cast<float*>(s_az + (size_t)p.ne_max * T);           // [nz][T]
-    float* a_w = a_wv + (size_t)p.nz * T;                                          // [nz][T]
-    unsigned short* a_cc = reinterpret_cast<unsigned short*>(a_w + (size_t)p.nz * T);   // [nz][T]: cnt | cov << 8
+    float2* a_acc = reinterpret_cast<float2*>(s_az + (size_t)p.ne_max * T);        // [nz][T]: {sum w v, sum w}
+    unsigned short* a_cc = reinterpret_cast<unsigned short*>(a_acc + (size_t)p.nz * T);   // [nz][T]: cnt | cov << 8
     double* a_d2 = reinterpret_cast<double*>(smem_raw + ((512 + (size_t)p.ne_max * T * sizeof(AzEntry) +
                                              (size_t)p.nz * T * 10 + 15) & ~(size_t)15));   // nearest only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     bool active;
     long long col;
-    net_tile_column(p, blockIdx.x, active, col);
+    net2_tile_column(p, blockIdx.x, active, col);
     const double gx = p.gx[col], gy = p.gy[col];            // inactive lanes repeat a valid column
     // ---- 1. which radars reach this tile (bounding box against reach disc, as net_cull_kernel) ----
     {
@@ -113,8 +157,7 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
     // ---- 3. this column's accumulators ----
     const int nz = p.nz;
     for (int iz = 0; iz < nz; ++iz) {
-        a_wv[(size_t)iz * T + tid] = 0.f;
-        a_w[(size_t)iz * T + tid] = 0.f;
+        a_acc[(size_t)iz * T + tid] = make_float2(0.f, 0.f);
         a_cc[(size_t)iz * T + tid] = 0;
         if (METHOD == kNetNearest) a_d2[(size_t)iz * T + tid] = __longlong_as_double(0x7ff0000000000000LL);
     }
@@ -126,6 +169,13 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
     AzEntry* my_az = s_az + tid;
     const unsigned az_addr = (unsigned)__cvta_generic_to_shared(my_az);
     constexpr unsigned az_pitch = T * (unsigned)sizeof(AzEntry);
+    const unsigned acc_addr = (unsigned)__cvta_generic_to_shared(a_acc + tid);
+    const unsigned cc_addr = (unsigned)__cvta_generic_to_shared(a_cc + tid);
+#ifndef NET2_NOSPEC
+    constexpr bool SPEC = UNI;      // uniform-table volumes: every speculative address of the level loop is valid
+#else
+    constexpr bool SPEC = false;
+#endif
 
     // ---- 2. the reaching radars, in radar order ----
 #pragma unroll 1
@@ -185,58 +235,61 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
         const float4* val0 = static_cast<const float4*>(R.vol.val[0]);
         const double2* g_t = R.r2.g_t;
         const FastSweep* fs_t = R.r2.fs;
+        const NetPairQ* pq_t = R.pq;
         const NetPair* np_t = R.npairs;
         const float inv2a = R.r2.inv2a;
         const float u_inv_step = R.r2.u_inv_step, u_c0 = R.r2.u_c0, u_step = R.r2.u_step, u_r_first = R.r2.u_r_first;
         const int u_ngm1 = R.r2.u_ngm1;
         const unsigned u_rng_off = R.r2.u_rng_off;
-        const double src_lo = R.src_lo, src_hi = R.src_hi;
+        const float src_lo_f = R.src_lo_f, src_hi_f = R.src_hi_f;
         const float inv_decay = R.inv_decay;
         const bool sanity = p.sanity != 0;
         int k = -1;
         unsigned long long slow_mask = 0ull;
-        size_t o = (size_t)col;
         // level constants one level ahead (they gate r2, and r2 gates every other load of the level)
         double n_a2g2 = nz > 0 ? __ldg(&lv[0].cy.a2g2) : 0.0, n_twoag = nz > 0 ? __ldg(&lv[0].cy.twoag) : 0.0;
 
-        // one voxel's contribution: range-sanity filter (RadarInterp.py:1003-1014), observability weight
+        // one voxel's contribution: range-sanity filter (RadarInterp.py:1003-1014, on the float value against the
+        // float-rounded window: the same decisions as the reference's double comparison), observability weight
         // (:566-599 / 636-695), then the merge rule of compose_network_volume (:1448-1487)
-        auto merge = [&](int iz, float v, bool obs, float rf, const NetPair* np, size_t oo) {
-            if (sanity && v != fill32) {
-                const double vd = (double)v;
-                if (!(src_lo <= src_hi) || vd < src_lo || vd > src_hi) v = fill32;
-            }
-            const bool valid = (v != fill32) && (v == v) && (fabsf(v) != __int_as_float(0x7f800000));
-            float qw = 0.f;
-            if (obs && (METHOD == kNetQuality || p.quality_out)) {
-                const float2 bv = __ldg(reinterpret_cast<const float2*>(&np->beam_k));      // {beam_k, vert_w}
-                const float t = rf * inv_decay;
-                const float b = rf * bv.x;
-                qw = __expf(-t * t) * rcp_approx(fmaf(b, b, 1.f)) * bv.y;
-            }
-            if (p.quality_out) p.quality_out[oo] = (double)qw;
+        auto merge = [&](int iz, float v, bool obs, float rf, float beam_k, float vert_w) {
+            bool valid = (v != fill32) & (fabsf(v) < __int_as_float(0x7f800000));        // finite and not fill
+            if (sanity) valid = valid & (v >= src_lo_f) & (v <= src_hi_f);
             if (!(obs | valid)) return;
-            const size_t c = (size_t)iz * T + tid;
-            unsigned cc = a_cc[c];
+            const unsigned cc_a = cc_addr + (unsigned)iz * (T * 2u);
+            unsigned cc = lds_u16(cc_a);
             if (obs) cc += 0x100u;
             if (valid) {
                 cc += 1u;
+                const unsigned ac = acc_addr + (unsigned)iz * (T * 8u);
+                float2 a = lds_f2(ac);
                 if (METHOD == kNetMax) {
-                    if (a_w[c] == 0.f || v > a_wv[c]) a_wv[c] = v;
-                    a_w[c] = 1.f;
+                    if (a.y == 0.f || v > a.x) a.x = v;
+                    a.y = 1.f;
                 } else if (METHOD == kNetNearest) {
-                    if (d2 < a_d2[c]) { a_d2[c] = d2; a_wv[c] = v; a_w[c] = 1.f; }
+                    const size_t c = (size_t)iz * T + tid;
+                    if (d2 < a_d2[c]) { a_d2[c] = d2; a.x = v; a.y = 1.f; }
                 } else {
-                    const float w = (METHOD == kNetQuality && p.quality) ? w2d * qw : w2d;
-                    a_wv[c] = fmaf(w, v, a_wv[c]);
-                    a_w[c] += w;
+                    float w = w2d;
+                    if (METHOD == kNetQuality && p.quality) {
+                        float qw = 0.f;
+                        if (obs) {
+                            const float t = rf * inv_decay;
+                            const float b = rf * beam_k;
+                            qw = __expf(-t * t) * rcp_approx(fmaf(b, b, 1.f)) * vert_w;
+                        }
+                        w *= qw;
+                    }
+                    a.x = fmaf(w, v, a.x);
+                    a.y += w;
                 }
+                sts_f2(ac, a);
             }
-            a_cc[c] = (unsigned short)cc;
+            sts_u16(cc_a, cc);
         };
 
 #pragma unroll 1
-        for (int iz = 0; iz < nz; ++iz, lrow += row_bytes, o += (size_t)p.ncol) {
+        for (int iz = 0; iz < nz; ++iz, lrow += row_bytes) {
             // RadarGridC.pyx:146-149 — the reference's own operations: r2 is bit-identical
             // (NetLevel is 56 bytes: its members are 8-byte, not 16-byte, aligned)
             const double r2 = sub(n_a2g2, mul(n_twoag, cphi));
@@ -251,29 +304,36 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
             // azimuth entries, both quads and the pair polynomial are in flight together — one memory round
             // trip per level instead of three dependent ones.  A column that leaves its pair (19 % of the
             // voxels at config C3) walks to the new pair and asks again.
-            int4 lk;
+            int4 lk = make_int4(0, 0, 0, 0);
             double2 tg = make_double2(0.0, 0.0);
             int gi = 1;
             AzEntry ea, eb;
-            float4 qa4, qb4, q14;
-            float q5 = 0.f;
+            float4 qa4, qb4, q14, q58;           // q14 = {q1 .. q4}, q58 = {q5, beam_k, vert_w, -} of the pair
             ea.row = 0u; ea.w = 0.f; eb = ea;
-            qa4 = make_float4(0.f, 0.f, 0.f, 0.f); qb4 = qa4; q14 = qa4;
+            qa4 = make_float4(0.f, 0.f, 0.f, 0.f); qb4 = qa4; q14 = qa4; q58 = qa4;
 #pragma unroll 1
             for (;;) {
                 const int4* pk = reinterpret_cast<const int4*>(lrow + (unsigned)(k + 1) * 32u);
                 const double2 cf = __ldg(reinterpret_cast<const double2*>(pk));
-                lk = __ldg(pk + 1);
-                if (UNI) {
-                    const int lo_s = max(k, 0), hi_s = min(lo_s + 1, ne - 1);
+                if (SPEC) {
+                    // what the GUESSED pair needs: a column below the lowest / above the highest sweep samples one
+                    // sweep, so the second quad, the pair record and the pair polynomial are not even asked for
+                    // (62 % of the sampled voxels at config C4: a third of the L1 wavefronts of the level)
+                    const int lo_s = max(k, 0);
                     gi = min(max(__float2int_rd(fmaf(rf, u_inv_step, u_c0)), 1), u_ngm1);
-                    tg = __ldg(g_t + (u_rng_off + (unsigned)(gi - 1)));
+                    tg = ldg_vol(g_t + (u_rng_off + (unsigned)(gi - 1)));
                     ea = lds_az(az_addr + (unsigned)lo_s * az_pitch);
-                    eb = lds_az(az_addr + (unsigned)hi_s * az_pitch);
-                    qa4 = __ldg(val0 + (ea.row + (unsigned)gi));
-                    qb4 = __ldg(val0 + (eb.row + (unsigned)gi));
-                    q14 = __ldg(reinterpret_cast<const float4*>(&fs_t[lo_s].q1));
-                    q5 = __ldg(&fs_t[lo_s].q5);
+                    qa4 = ldg_vol(val0 + (ea.row + (unsigned)gi));
+                    if ((unsigned)k < pair_top) {
+                        lk = __ldg(pk + 1);
+                        eb = lds_az(az_addr + (unsigned)(lo_s + 1) * az_pitch);
+                        qb4 = ldg_vol(val0 + (eb.row + (unsigned)gi));
+                        const float4* pq = reinterpret_cast<const float4*>(pq_t + lo_s);
+                        q14 = __ldg(pq);
+                        q58 = __ldg(pq + 1);
+                    }
+                } else {
+                    lk = __ldg(pk + 1);
                 }
                 if ((r2 < cf.x) & (r2 > cf.y)) break;
                 const char* ls = lrow + ls_off;
@@ -295,45 +355,54 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
             const bool skip = (unsigned)(k - k_first) > k_span;
             const int lower = max(k, 0);
             if (skip) {                                        // blind-zone rules: nothing sampled, nothing observable
-                merge(iz, fill32, false, 0.f, np_t, o);
-                continue;
+                continue;                                      // (nothing valid, nothing observable: no contribution)
             }
             int ngm1 = u_ngm1;
             float rj, idr;
-            if (UNI) {
+            if (SPEC) {
                 if (!((r2 >= tg.x) & (r2 < tg.y))) { slow_mask |= 1ull << iz; continue; }
                 rj = fmaf((float)(gi - 1), u_step, u_r_first); idr = u_inv_step;
             } else {
-                const int4 tab = __ldg(reinterpret_cast<const int4*>(&fs_t[lower].rng_off));
-                const unsigned rng_off = (unsigned)tab.x;
-                ngm1 = tab.y;
-                const float c0 = __int_as_float(tab.z), inv_step = __int_as_float(tab.w);
-                const int need = pair ? (kFsPolyOk | kFsShared | kFsUsable) : kFsUsable;
-                const bool usable = (__ldg(&fs_t[lower].flags) & need) == need;
+                // ---- bracket, then gather ----
+                unsigned rng_off = u_rng_off;
+                float inv_step = u_inv_step, c0 = u_c0;
+                bool usable = true;
+                if (!UNI) {
+                    const int4 tab = __ldg(reinterpret_cast<const int4*>(&fs_t[lower].rng_off));
+                    rng_off = (unsigned)tab.x;
+                    ngm1 = tab.y;
+                    c0 = __int_as_float(tab.z); inv_step = __int_as_float(tab.w);
+                    const int need = pair ? (kFsPolyOk | kFsShared | kFsUsable) : kFsUsable;
+                    usable = (__ldg(&fs_t[lower].flags) & need) == need;
+                }
                 gi = usable ? min(max(__float2int_rd(fmaf(rf, inv_step, c0)), 1), ngm1) : 1;
                 const unsigned gidx = usable ? rng_off + (unsigned)(gi - 1) : u_rng_off;
-                tg = __ldg(g_t + gidx);                        // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
+                tg = ldg_vol(g_t + gidx);                        // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
                 if (!(usable & (r2 >= tg.x) & (r2 < tg.y))) { slow_mask |= 1ull << iz; continue; }
-                const int4 hv = __ldg(reinterpret_cast<const int4*>(R.r2.h_t + gidx));       // {R^2, R, 1/dR}
-                rj = __int_as_float(hv.z); idr = __int_as_float(hv.w);
+                if (UNI) {
+                    rj = fmaf((float)(gi - 1), u_step, u_r_first); idr = u_inv_step;
+                } else {
+                    const int4 hv = __ldg(reinterpret_cast<const int4*>(R.r2.h_t + gidx));   // {R^2, R, 1/dR}
+                    rj = __int_as_float(hv.z); idr = __int_as_float(hv.w);
+                }
                 ea = lds_az(az_addr + (unsigned)lower * az_pitch);
-                qa4 = __ldg(val0 + (ea.row + (unsigned)gi));
+                qa4 = ldg_vol(val0 + (ea.row + (unsigned)gi));
                 if (pair) {
                     eb = lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
-                    qb4 = __ldg(val0 + (eb.row + (unsigned)gi));
-                    q14 = __ldg(reinterpret_cast<const float4*>(&fs_t[lower].q1));
-                    q5 = __ldg(&fs_t[lower].q5);
+                    qb4 = ldg_vol(val0 + (eb.row + (unsigned)gi));
+                    const float4* pq = reinterpret_cast<const float4*>(pq_t + lower);
+                    q14 = __ldg(pq);
+                    q58 = __ldg(pq + 1);
                 }
             }
             const float ea0 = fmaf(ea.w, qa4.y - qa4.x, qa4.x), ea1 = fmaf(ea.w, qa4.w - qa4.z, qa4.z);
             const float w_r = (float)sub(r2, tg.x) * idr * rcp_approx(rf + rj);
             float v = fmaf(w_r, ea1 - ea0, ea0);
             bool obs = false;
-            const NetPair* np = np_t;
             if (pair) {
                 const float u = (float)sub(r2, __hiloint2double(lk.y, lk.x)) * rcp_approx(rf + __int_as_float(lk.z)) *
                                 fmaf(__int_as_float(lk.w), rinv, inv2a);
-                float w_el = fmaf(q5, u, q14.w);
+                float w_el = fmaf(q58.x, u, q14.w);
                 w_el = fmaf(w_el, u, q14.z);
                 w_el = fmaf(w_el, u, q14.y);
                 w_el = fmaf(w_el, u, q14.x);
@@ -341,13 +410,12 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                 const float eb0 = fmaf(eb.w, qb4.y - qb4.x, qb4.x), eb1 = fmaf(eb.w, qb4.w - qb4.z, qb4.z);
                 const float v1 = fmaf(w_r, eb1 - eb0, eb0);
                 v = lerp_fill(w_el, v, v1, fill32);
-                np = np_t + lower;
                 // between two sweeps and at least one gate away from both ends of their (shared) range table:
                 // observable whatever the few-ulp difference between the NumPy twin's r and this one
                 obs = (gi > 1) & (gi < ngm1);
-                if (!obs) obs = net2_obs_edge(r2, np, x, y, &R, lv + iz, false, &ties);
+                if (!obs) obs = net2_obs_edge(r2, np_t + lower, x, y, &R, lv + iz, false, &ties);
             }
-            merge(iz, v, obs, rf, np, o);
+            merge(iz, v, obs, rf, q58.y, q58.z);
         }
 
         // ---- the marked voxels: the reference's own chain (pcg_fast.cuh fast_voxel) ----
@@ -371,7 +439,8 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                 bool obs = false;
                 if (is_pair || vi.tie || !(vi.r2 > 0.0))
                     obs = net2_obs_edge(vi.r2, np, x, y, &R, lv + iz, vi.tie || !is_pair, &ties) && (is_pair || vi.tie);
-                merge(iz, tmp[0], obs, (float)vi.r, np, (size_t)iz * (size_t)p.ncol + (size_t)col);
+                const NetPairQ* pq = pq_t + (is_pair ? kk : 0);
+                merge(iz, tmp[0], obs, (float)vi.r, pq->beam_k, pq->vert_w);
             }
         }
 
@@ -403,7 +472,8 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
         size_t o = (size_t)col;
         for (int iz = 0; iz < nz; ++iz, o += (size_t)p.ncol) {
             const size_t c = (size_t)iz * T + tid;
-            const float awv = a_wv[c], aw = a_w[c];
+            const float2 acc = a_acc[c];
+            const float awv = acc.x, aw = acc.y;
             const unsigned cc = a_cc[c];
             double out = p.out_missing;
             if (METHOD == kNetMax || METHOD == kNetNearest) {

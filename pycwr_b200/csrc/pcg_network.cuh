@@ -42,6 +42,12 @@ struct NetPair {                     // sweep pair (k, k+1) of one radar
     float vert_w;                    // 1 / (1 + (gap_half / vertical_gap_ref)^2)             (1: term off)
 };
 
+struct NetPairQ {                    // per (radar, sweep k): what a sampled voxel of pair (k, k+1) reads besides its
+    float q1, q2, q3, q4, q5;        // level row — the elevation-weight polynomial (FastSweep) and the quality terms
+    float beam_k, vert_w;            // of NetPair, side by side: two 128-bit loads (tile-persistent kernel)
+    float pad;
+};
+
 struct NetLevel {                    // per (radar, level) constants, host-evaluated
     LevelConst cy;                   // the gridding chain (RadarGridC.pyx:145-146)
     double a2g2_np, twoag_np, g2_np; // the NumPy twin: a**2 + g**2, 2*a*g, g**2 (transforms.py:213-218)
@@ -61,7 +67,12 @@ struct NetRadar {
     float inv_decay;                 // 1 / range_decay_m   (0: term off)
     float inv_r2inf4;                // 4 / influence_radius^2
     int ne;
+    // the range-sanity window for FLOAT values: for a float v, (double)v < src_lo <=> v < src_lo_f (the smallest
+    // float >= src_lo) and (double)v > src_hi <=> v > src_hi_f (the largest float <= src_hi); no valid source
+    // value: +inf / -inf, which no finite v passes
+    float src_lo_f, src_hi_f;
     int pad;
+    const NetPairQ* pq;              // [ne]
 };
 
 constexpr int kNetMaxPeers = 16;

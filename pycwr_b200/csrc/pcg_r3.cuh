@@ -112,6 +112,39 @@ __device__ __forceinline__ const T* r3_pin(const T* v, int z) {
 #define R3_PIN(x)
 #endif
 
+// Gathers from the packed volume ask L2 to fetch the whole 128-byte line (PCG_LTC = 256: two lines) on a miss
+// instead of the one 32-byte sector: the neighbouring gates are wanted by the neighbouring lanes and levels anyway,
+// and it is the number of exposed DRAM round trips, not the DRAM bytes (6 % of peak), that the gridding kernels wait on.
+#ifndef PCG_LTC
+#define PCG_LTC 128
+#endif
+__device__ __forceinline__ float4 ldg_vol(const float4* p) {
+#if PCG_LTC == 128
+    float4 v;
+    asm volatile("ld.global.nc.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#elif PCG_LTC == 256
+    float4 v;
+    asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ double2 ldg_vol(const double2* p) {
+#if PCG_LTC == 128
+    double2 v;
+    asm volatile("ld.global.nc.L2::128B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#elif PCG_LTC == 256
+    double2 v;
+    asm volatile("ld.global.nc.L2::256B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // shared-memory reads of the level loop through 32-bit shared addresses held in registers (the compiler would
 // otherwise rebuild the carve-up offsets from `ne` at every use)
 __device__ __forceinline__ AzEntry lds_az(unsigned addr) {
@@ -262,10 +295,10 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
     // levels whose voxel needs the reference chain are only MARKED here and resolved after the loop: the hot
     // loop then contains no call, so its state stays in registers (kMaxLevelsPerLaunch <= 64)
     unsigned long long slow_mask = 0ull;
-#ifndef R3_NOSPEC
+#ifdef R3_SPEC
     constexpr bool SPEC = UNI;      // uniform-table volumes: every speculative address below is valid
 #else
-    constexpr bool SPEC = false;
+    constexpr bool SPEC = false;    // measured on B200, config C3: 0.386 ms with, 0.344 ms without
 #endif
 
 #pragma unroll 1
@@ -299,14 +332,14 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
             if (SPEC) {
                 const int lo_s = max(k, 0), hi_s = min(lo_s + 1, ne - 1);
                 gi = min(max(__float2int_rd(fmaf(rf, u_inv_step, u_c0)), 1), u_ngm1);
-                tg = __ldg(g_t + (u_rng_off + (unsigned)(gi - 1)));
+                tg = ldg_vol(g_t + (u_rng_off + (unsigned)(gi - 1)));
                 ea = lds_az(az_addr + (unsigned)lo_s * az_pitch);
                 eb = lds_az(az_addr + (unsigned)hi_s * az_pitch);
 #pragma unroll
                 for (int fi = 0; fi < NF; ++fi) {
                     const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
-                    qa4[fi] = __ldg(v + (ea.row + (unsigned)gi));
-                    qb4[fi] = __ldg(v + (eb.row + (unsigned)gi));
+                    qa4[fi] = ldg_vol(v + (ea.row + (unsigned)gi));
+                    qb4[fi] = ldg_vol(v + (eb.row + (unsigned)gi));
                 }
             }
             if ((r2 < cf.x) & (r2 > cf.y)) break;
@@ -355,7 +388,7 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
                 }
                 gi = usable ? min(max(__float2int_rd(fmaf(rf, inv_step, c0)), 1), ngm1) : 1;
                 const unsigned gidx = usable ? rng_off + (unsigned)(gi - 1) : u_rng_off;
-                tg = __ldg(g_t + gidx);                          // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
+                tg = ldg_vol(g_t + gidx);                          // r in [R[gi-1], R[gi])  <=>  tg.x <= r2 < tg.y
                 if (!(usable & (r2 >= tg.x) & (r2 < tg.y))) { slow_mask |= 1ull << iz; continue; }
                 if (UNI) {
                     rj = fmaf((float)(gi - 1), u_step, u_r_first); idr = u_inv_step;
@@ -368,8 +401,8 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
 #pragma unroll
                 for (int fi = 0; fi < NF; ++fi) {
                     const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
-                    qa4[fi] = __ldg(v + (ea.row + (unsigned)gi));
-                    if (pair) qb4[fi] = __ldg(v + (eb.row + (unsigned)gi));
+                    qa4[fi] = ldg_vol(v + (ea.row + (unsigned)gi));
+                    if (pair) qb4[fi] = ldg_vol(v + (eb.row + (unsigned)gi));
                 }
             }
             // ---- the two weights and the lerps (RadarGridC.pyx:297-299,469-476) ----
