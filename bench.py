@@ -338,6 +338,64 @@ def _fused_gather(torch, dist, dev, rank, world, lib, launch_args, nlat, r0, ste
         lib.pcg_peer_free(full)
 
 
+def gpu_numa_cpus(torch, index):
+    """CPUs local to GPU `index` (sysfs local_cpulist of its PCI function), or None when the box does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        text = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        return cpus or None
+    except Exception:                                   # noqa: BLE001 - no sysfs entry / no permission: run unbound
+        return None
+
+
+def network_e2e_devices(args, devices):
+    """The network product end to end as ONE host call over `devices` (interp.network_compose(devices=...)): host
+    grids in; composite (NaN in its empty cells), coverage, blind mask, CR, VIL, ET and the topped flag out, every
+    slab returned by its own GPU into the shared pinned arrays.  Volumes are packed per device on the first call."""
+    from pycwr_b200 import interp, synth
+    from pycwr_b200.runtime import HostVolume
+    cfg = synth.network_config(style="stress", scale=args.network_scale, nradar=args.network_radars)
+    hvs = [HostVolume(v["vol_azimuth"], v["vol_range"], v["fix_elevation"], v["vol_value"]["dBZ"], fillvalue=FILL)
+           for v in cfg["volumes"]]
+    sites = np.stack([cfg["radar_x"], cfg["radar_y"]], axis=1)
+    heights = [v["radar_height"] for v in cfg["volumes"]]
+    bws = [v["beam_widths"] for v in cfg["volumes"]]
+    from pycwr_b200.runtime import pinned_copy
+    gx, gy, lv = pinned_copy(cfg["GridX"]), pinned_copy(cfg["GridY"]), cfg["levels"]      # inputs in pinned host memory
+    call = lambda: interp.network_compose(                                                      # noqa: E731
+        hvs, sites, heights, gx, gy, lv, fillvalue=FILL, beam_widths=bws, missing=float("nan"),
+        outputs=("coverage_count", "blind_mask", "CR"), column_products=(18.0, 56.0, 18.0), devices=devices)
+    try:
+        res = call()
+        res = call()
+        reps, ts = 3, []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            res = call()
+            ts.append(time.perf_counter() - t0)
+        dt = float(np.mean(ts))
+        out_bytes = sum(int(np.asarray(a).nbytes) for k, a in res.items() if hasattr(a, "nbytes"))
+        slab_rows = list(res["slab_rows"])
+        del res
+    finally:
+        for h in hvs:
+            h.close()
+    voxels = int(lv.size) * gx.size
+    return {"value": voxels / dt, "unit": UNIT, "ms_per_call": dt * 1e3, "ms_best": float(min(ts)) * 1e3,
+            "n_gpus": len(devices), "slab_rows": slab_rows,
+            "h2d_bytes_per_step": int(gx.nbytes + gy.nbytes), "d2h_bytes_per_step": out_bytes,
+            "api": "pycwr_b200.interp.network_compose(devices=[0..N-1]): one host call, one thread per GPU, every "
+                   "slab copied to the shared pinned result by its own GPU (no device-to-device exchange)"}
+
+
 def bench_network(args, torch, dist, dev, rank, world):
     """Fused network kernel on this rank's row slab (inputs resident in HBM), then the NCCL gather
     of the finished composite slabs.  Returns the `network` object of the JSON line (rank 0)."""
@@ -459,8 +517,10 @@ def bench_network(args, torch, dist, dev, rank, world):
         import time
 
         from pycwr_b200 import interp
+        from pycwr_b200.runtime import pinned_copy
+        gx_p, gy_p = pinned_copy(gx_h), pinned_copy(gy_h)                                       # inputs in pinned host memory
         call = lambda: interp.network_compose(                                                  # noqa: E731
-            vols, sites[mine], heights, gx_h, gy_h, levels, fillvalue=FILL, beam_widths=bws, missing=float("nan"),
+            vols, sites[mine], heights, gx_p, gy_p, levels, fillvalue=FILL, beam_widths=bws, missing=float("nan"),
             outputs=("coverage_count", "blind_mask", "CR"), column_products=(18.0, 56.0, 18.0))
         res = call()
         res = call()
@@ -476,6 +536,22 @@ def bench_network(args, torch, dist, dev, rank, world):
         del res
     for v in vols:
         v.close()
+    if world > 1:
+        # the host-facing product over all GPUs of the box: one call from rank 0's process, one thread per GPU; the
+        # other ranks have released their buffers and wait on a gloo barrier (no NCCL kernel spinning on their GPUs)
+        torch.cuda.empty_cache()
+        sync = dist.new_group(backend="gloo")
+        dist.barrier(group=sync)
+        if rank == 0:
+            try:
+                os.sched_setaffinity(0, range(os.cpu_count() or 1))    # the threads serve GPUs on every socket
+            except Exception:                                          # noqa: BLE001
+                pass
+            try:
+                e2e = network_e2e_devices(args, list(range(world)))
+            except Exception as exc:                                   # noqa: BLE001 - reported, the device numbers stand
+                e2e = {"error": repr(exc)[:300]}
+        dist.barrier(group=sync)
     if rank != 0:
         return None
     peak, _ = read_peaks()
@@ -639,6 +715,16 @@ def run_product(args):
         raise RuntimeError("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
     _lib.check(_lib.load().pcg_set_device(local))
+    numa = None
+    if world > 1:
+        # one process per GPU: keep it (and the pinned buffers it allocates) on the CPUs next to that GPU
+        cpus = gpu_numa_cpus(torch, local)
+        if cpus:
+            try:
+                os.sched_setaffinity(0, cpus)
+                numa = "%d CPUs local to GPU %d" % (len(cpus), local)
+            except Exception:                                          # noqa: BLE001
+                numa = None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -808,6 +894,7 @@ def run_product(args):
                    "value_storage": dv.value_dtype, "blind_method": cfg["blind_method"],
                    "l2": "256 MB flush write between timed steps (excluded from step time)",
                    "parallelism": "1 radar volume per GPU, no collective" if world > 1 else "single GPU",
+                   "cpu_binding": numa,
                    "wall_s_timed_region": wall},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "api": "pycwr_b200.RadarGridC.%s (host buffers in, host array out)"

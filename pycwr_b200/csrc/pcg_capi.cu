@@ -2172,69 +2172,118 @@ static int network_compose_host(int nradar, const pcg_volume* const* vols, const
     std::lock_guard<std::mutex> lock(g_mutex);
     cudaStream_t st;
     if ((rc = lib_stream(&st))) return rc;
-    if ((rc = g_scratch[S_GX].ensure(ncol * sizeof(double)))) return rc;
-    if ((rc = g_scratch[S_GY].ensure(ncol * sizeof(double)))) return rc;
-    if ((rc = g_scratch[S_OUT].ensure((nvox ? nvox : 1) * sizeof(double)))) return rc;
-    if (valid_count && (rc = g_scratch[S_AUX0].ensure(nvox * sizeof(int16_t)))) return rc;
-    if (coverage_count && (rc = g_scratch[S_AUX1].ensure(nvox * sizeof(int16_t)))) return rc;
-    if (blind_mask && (rc = g_scratch[S_AUX2].ensure(nvox * sizeof(int8_t)))) return rc;
-    if (cr && (rc = g_scratch[S_AUX3].ensure(ncol * sizeof(double)))) return rc;
-    if (quality && (rc = g_scratch[S_AUX4].ensure(nvox * sizeof(double)))) return rc;
-    if ((rc = g_scratch[S_TMP2].ensure(sizeof(unsigned long long)))) return rc;
     StageTrace trace(st);
-    trace.mark("scratch");
-    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GX].ptr, grid_x, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(g_scratch[S_GY].ptr, grid_y, ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    // The slab is taken in ROW CHUNKS through two sets of device buffers: while chunk c's results cross PCIe on the
+    // copy stream, chunk c + 1's grid rows are uploaded and its kernels run on the compute stream (tiles are
+    // independent, so chunking by rows repeats no work; the radar tables are built once and cached).  The call is
+    // then bound by the result's trip over PCIe alone instead of upload + kernels + download one after the other.
+    // PCG_TRACE, the per-radar quality output and small slabs use one chunk.
+    int nchunk = 1;
+    if (!trace.on && !quality && use_tile_kernel() && nz > 0 && nx >= 256) {
+        nchunk = nx / 128;
+        if (nchunk > 6) nchunk = 6;
+    }
+    if (const char* e = getenv("PCG_NET_CHUNKS")) {          // tests: force a chunk count on small grids
+        const int want = atoi(e);
+        if (want >= 1 && !quality && use_tile_kernel() && nz > 0) nchunk = want < nx ? want : (nx > 0 ? nx : 1);
+    }
+    const int rows_cap = (nx + nchunk - 1) / nchunk;
+    const size_t ccol = (size_t)rows_cap * (size_t)ny, cvox = (size_t)nz * ccol;     // capacity of one buffer set
+    const int nset = nchunk > 1 ? 2 : 1;
+    if ((rc = g_scratch[S_GX].ensure(nset * ccol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_GY].ensure(nset * ccol * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_OUT].ensure(nset * (cvox ? cvox : 1) * sizeof(double)))) return rc;
+    if (valid_count && (rc = g_scratch[S_AUX0].ensure(nset * cvox * sizeof(int16_t)))) return rc;
+    if (coverage_count && (rc = g_scratch[S_AUX1].ensure(nset * cvox * sizeof(int16_t)))) return rc;
+    if (blind_mask && (rc = g_scratch[S_AUX2].ensure(nset * cvox * sizeof(int8_t)))) return rc;
+    if (cr && (rc = g_scratch[S_AUX3].ensure(nset * ccol * sizeof(double)))) return rc;
+    if (quality && (rc = g_scratch[S_AUX4].ensure(cvox * sizeof(double)))) return rc;
+    if ((rc = g_scratch[S_TMP2].ensure(sizeof(unsigned long long)))) return rc;
+    const size_t col_bytes = 2 * ccol * sizeof(double) + ((ccol + 7) & ~(size_t)7);     // VIL, ET, topped of one set
+    if (columns && ncol) {
+        if ((rc = g_scratch[S_TMP0].ensure((size_t)(nz ? nz : 1) * sizeof(double)))) return rc;
+        if ((rc = g_scratch[S_ACC0].ensure(nset * col_bytes))) return rc;
+        if (nz) CUDA_TRY(cudaMemcpyAsync(g_scratch[S_TMP0].ptr, level_heights, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaMemsetAsync(g_scratch[S_TMP2].ptr, 0, sizeof(unsigned long long), st));
-    trace.mark("grid H2D");
+    trace.mark("scratch");
+    NetStreams* ns = nullptr;
+    cudaStream_t cp = st;                      // copy-out stream (the compute stream itself when there is one chunk)
+    if (nchunk > 1) {
+        if ((rc = net_streams(&ns))) return rc;
+        cp = ns->side[0];
+    }
     // the tile kernel stores the caller's missing-value marker itself; the column products read the composite
     // afterwards and know `fill` and NaN as "no data" — any other marker is applied after them, as before
     const bool marker_ok = !columns || out_missing != out_missing || memcmp(&out_missing, &fill, sizeof(double)) == 0;
     const int nan_as_fill = (columns && out_missing != out_missing) ? 1 : 0;
     const double tile_missing = marker_ok ? out_missing : fill;
-    bool relabelled = false;
-    rc = enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
-                         (const double*)g_scratch[S_GX].ptr, (const double*)g_scratch[S_GY].ptr, (long long)ncol, ny,
-                         level_heights, nz, fill, (double*)g_scratch[S_OUT].ptr,
-                         valid_count ? (int16_t*)g_scratch[S_AUX0].ptr : nullptr,
-                         coverage_count ? (int16_t*)g_scratch[S_AUX1].ptr : nullptr,
-                         blind_mask ? (int8_t*)g_scratch[S_AUX2].ptr : nullptr,
-                         cr ? (double*)g_scratch[S_AUX3].ptr : nullptr,
-                         quality ? (double*)g_scratch[S_AUX4].ptr : nullptr,
-                         (unsigned long long*)g_scratch[S_TMP2].ptr, st, tile_missing, &relabelled);
-    if (rc) return rc;
-    trace.mark("tables + kernels");
-    if (columns && ncol) {
-        // VIL / ET of the composite while it is still on the device (RadarInterp.py:2064-2119 -> derive_vil /
-        // derive_et, RadarProduct.py:33-85): no second trip of the volume over PCIe
-        if ((rc = g_scratch[S_TMP0].ensure((size_t)(nz ? nz : 1) * sizeof(double)))) return rc;
-        if ((rc = g_scratch[S_ACC0].ensure(2 * ncol * sizeof(double) + ncol))) return rc;
-        if (nz) CUDA_TRY(cudaMemcpyAsync(g_scratch[S_TMP0].ptr, level_heights, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, st));
-        double* d2 = (double*)g_scratch[S_ACC0].ptr;
-        unsigned char* dt = (unsigned char*)(d2 + 2 * ncol);
-        rc = enqueue_columns((const double*)g_scratch[S_OUT].ptr, (const double*)g_scratch[S_TMP0].ptr, nz, (long long)ncol,
-                             fill, column_params[0], column_params[1], column_params[2], nullptr, vil ? d2 : nullptr,
-                             et ? d2 + ncol : nullptr, et_topped ? dt : nullptr, st, relabelled ? nan_as_fill : 0);
+    for (int c = 0; c < nchunk; ++c) {
+        const int b = c & 1;
+        const int r_lo = (int)(((long long)nx * c) / nchunk), r_hi = (int)(((long long)nx * (c + 1)) / nchunk);
+        const int rows = r_hi - r_lo;
+        const size_t kcol = (size_t)rows * (size_t)ny, kvox = (size_t)nz * kcol;     // this chunk
+        const size_t h0 = row0 + (size_t)r_lo * (size_t)ny;                          // its first element in a host plane
+        double* d_gx = (double*)g_scratch[S_GX].ptr + b * ccol;
+        double* d_gy = (double*)g_scratch[S_GY].ptr + b * ccol;
+        double* d_out = (double*)g_scratch[S_OUT].ptr + b * cvox;
+        int16_t* d_valid = valid_count ? (int16_t*)g_scratch[S_AUX0].ptr + b * cvox : nullptr;
+        int16_t* d_cov = coverage_count ? (int16_t*)g_scratch[S_AUX1].ptr + b * cvox : nullptr;
+        int8_t* d_blind = blind_mask ? (int8_t*)g_scratch[S_AUX2].ptr + b * cvox : nullptr;
+        double* d_cr = cr ? (double*)g_scratch[S_AUX3].ptr + b * ccol : nullptr;
+        // this buffer set is free again once the copies of chunk c - 2 have left it
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(st, ns->ev_side[2 + b], 0));
+        CUDA_TRY(cudaMemcpyAsync(d_gx, grid_x + (size_t)r_lo * (size_t)ny, kcol * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_gy, grid_y + (size_t)r_lo * (size_t)ny, kcol * sizeof(double), cudaMemcpyHostToDevice, st));
+        trace.mark("grid H2D");
+        bool relabelled = false;
+        rc = enqueue_network(nradar, vols, radar_x, radar_y, radar_height, effective_earth_radius, beam_widths, params,
+                             d_gx, d_gy, (long long)kcol, ny, level_heights, nz, fill, d_out, d_valid, d_cov, d_blind, d_cr,
+                             quality ? (double*)g_scratch[S_AUX4].ptr : nullptr,
+                             (unsigned long long*)g_scratch[S_TMP2].ptr, st, tile_missing, &relabelled);
         if (rc) return rc;
-        if (vil) CUDA_TRY(cudaMemcpyAsync(vil + row0, d2, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (et) CUDA_TRY(cudaMemcpyAsync(et + row0, d2 + ncol, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (et_topped) CUDA_TRY(cudaMemcpyAsync(et_topped + row0, dt, ncol, cudaMemcpyDeviceToHost, st));
+        trace.mark("tables + kernels");
+        double* d2 = nullptr;
+        unsigned char* dt = nullptr;
+        if (columns && kcol) {
+            // VIL / ET of the composite while it is still on the device (RadarInterp.py:2064-2119 -> derive_vil /
+            // derive_et, RadarProduct.py:33-85): no second trip of the volume over PCIe
+            d2 = (double*)((char*)g_scratch[S_ACC0].ptr + b * col_bytes);
+            dt = (unsigned char*)(d2 + 2 * ccol);
+            rc = enqueue_columns(d_out, (const double*)g_scratch[S_TMP0].ptr, nz, (long long)kcol, fill, column_params[0],
+                                 column_params[1], column_params[2], nullptr, vil ? d2 : nullptr, et ? d2 + ccol : nullptr,
+                                 et_topped ? dt : nullptr, st, relabelled ? nan_as_fill : 0);
+            if (rc) return rc;
+        }
+        if (composite && kvox && !(relabelled && marker_ok) &&
+            (rc = relabel_missing(d_out, kvox, fill, out_missing, st))) return rc;
+        if (nchunk > 1) {
+            CUDA_TRY(cudaEventRecord(ns->ev_side[b], st));
+            CUDA_TRY(cudaStreamWaitEvent(cp, ns->ev_side[b], 0));
+        }
+        if (d2) {
+            if (vil) CUDA_TRY(cudaMemcpyAsync(vil + h0, d2, kcol * sizeof(double), cudaMemcpyDeviceToHost, cp));
+            if (et) CUDA_TRY(cudaMemcpyAsync(et + h0, d2 + ccol, kcol * sizeof(double), cudaMemcpyDeviceToHost, cp));
+            if (et_topped) CUDA_TRY(cudaMemcpyAsync(et_topped + h0, dt, kcol, cudaMemcpyDeviceToHost, cp));
+        }
+        trace.mark("column products + D2H");
+        if (composite && kvox)
+            CUDA_TRY(cudaMemcpy2DAsync(composite + h0, plane * sizeof(double), d_out, kcol * sizeof(double), kcol * sizeof(double), (size_t)nz, cudaMemcpyDeviceToHost, cp));
+        trace.mark("composite D2H");
+        if (valid_count && kvox) CUDA_TRY(cudaMemcpy2DAsync(valid_count + h0, plane * sizeof(int16_t), d_valid, kcol * sizeof(int16_t), kcol * sizeof(int16_t), (size_t)nz, cudaMemcpyDeviceToHost, cp));
+        if (coverage_count && kvox) CUDA_TRY(cudaMemcpy2DAsync(coverage_count + h0, plane * sizeof(int16_t), d_cov, kcol * sizeof(int16_t), kcol * sizeof(int16_t), (size_t)nz, cudaMemcpyDeviceToHost, cp));
+        if (blind_mask && kvox) CUDA_TRY(cudaMemcpy2DAsync(blind_mask + h0, plane * sizeof(int8_t), d_blind, kcol * sizeof(int8_t), kcol * sizeof(int8_t), (size_t)nz, cudaMemcpyDeviceToHost, cp));
+        if (cr && kcol) CUDA_TRY(cudaMemcpyAsync(cr + h0, d_cr, kcol * sizeof(double), cudaMemcpyDeviceToHost, cp));
+        if (quality && kvox) CUDA_TRY(cudaMemcpy2DAsync(quality + h0, plane * sizeof(double), g_scratch[S_AUX4].ptr, kcol * sizeof(double), kcol * sizeof(double), (size_t)nz, cudaMemcpyDeviceToHost, cp));
+        if (nchunk > 1) CUDA_TRY(cudaEventRecord(ns->ev_side[2 + b], cp));
     }
-    trace.mark("column products + D2H");
-    if (composite && nvox) {
-        if (!(relabelled && marker_ok) &&
-            (rc = relabel_missing((double*)g_scratch[S_OUT].ptr, nvox, fill, out_missing, st))) return rc;
-        CUDA_TRY(cudaMemcpy2DAsync(composite + row0, plane * sizeof(double), g_scratch[S_OUT].ptr, ncol * sizeof(double), ncol * sizeof(double), (size_t)nz, cudaMemcpyDeviceToHost, st));
-    }
-    trace.mark("composite D2H");
-    if (valid_count && nvox) CUDA_TRY(cudaMemcpy2DAsync(valid_count + row0, plane * sizeof(int16_t), g_scratch[S_AUX0].ptr, ncol * sizeof(int16_t), ncol * sizeof(int16_t), (size_t)nz, cudaMemcpyDeviceToHost, st));
-    if (coverage_count && nvox) CUDA_TRY(cudaMemcpy2DAsync(coverage_count + row0, plane * sizeof(int16_t), g_scratch[S_AUX1].ptr, ncol * sizeof(int16_t), ncol * sizeof(int16_t), (size_t)nz, cudaMemcpyDeviceToHost, st));
-    if (blind_mask && nvox) CUDA_TRY(cudaMemcpy2DAsync(blind_mask + row0, plane * sizeof(int8_t), g_scratch[S_AUX2].ptr, ncol * sizeof(int8_t), ncol * sizeof(int8_t), (size_t)nz, cudaMemcpyDeviceToHost, st));
-    if (cr) CUDA_TRY(cudaMemcpyAsync(cr + row0, g_scratch[S_AUX3].ptr, ncol * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (quality && nvox) CUDA_TRY(cudaMemcpy2DAsync(quality + row0, plane * sizeof(double), g_scratch[S_AUX4].ptr, ncol * sizeof(double), ncol * sizeof(double), (size_t)nz, cudaMemcpyDeviceToHost, st));
     unsigned long long ties = 0;
     CUDA_TRY(cudaMemcpyAsync(&ties, g_scratch[S_TMP2].ptr, sizeof(ties), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (cp != st) {
+        CUDA_TRY(cudaStreamSynchronize(cp));
+        // later calls on the library stream must also see the copy stream drained (it is, here) — nothing to record
+    }
     trace.mark("counts / masks / CR D2H");
     {
         int dev = 0;

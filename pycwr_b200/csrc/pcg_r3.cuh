@@ -112,11 +112,11 @@ __device__ __forceinline__ const T* r3_pin(const T* v, int z) {
 #define R3_PIN(x)
 #endif
 
-// Gathers from the packed volume ask L2 to fetch the whole 128-byte line (PCG_LTC = 256: two lines) on a miss
-// instead of the one 32-byte sector: the neighbouring gates are wanted by the neighbouring lanes and levels anyway,
-// and it is the number of exposed DRAM round trips, not the DRAM bytes (6 % of peak), that the gridding kernels wait on.
+// Gathers from the packed volume can ask L2 to fetch the whole 128-byte line (PCG_LTC = 128) or two lines (256) on a
+// miss instead of the one 32-byte sector.  Measured on B200 and left OFF: no change for the network kernel
+// (11.73 / 11.73 / 11.70 ms for 0 / 128 / 256), 128 slower on config C3 (0.366 vs 0.343 ms), 256 the same as 0.
 #ifndef PCG_LTC
-#define PCG_LTC 128
+#define PCG_LTC 0
 #endif
 __device__ __forceinline__ float4 ldg_vol(const float4* p) {
 #if PCG_LTC == 128

@@ -386,16 +386,21 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
         cpar = np.ascontiguousarray(column_products, dtype=np.float64).ravel()
         if cpar.size != 3:
             raise ValueError("column_products must be (vil_min_dbz, vil_max_dbz_cap, et_threshold_dbz)")
-        res["VIL"] = np.full((nx, ny), np.nan)
-        res["ET"] = np.full((nx, ny), np.nan)
-        res["ET_TOPPED"] = np.zeros((nx, ny), dtype=np.uint8)
+        # (page-locked like the volumes: the library overwrites every cell when the grid is not empty)
+        res["VIL"] = pinned_empty((nx, ny), np.float64)
+        res["ET"] = pinned_empty((nx, ny), np.float64)
+        res["ET_TOPPED"] = pinned_empty((nx, ny), np.uint8)
+        if nx * ny == 0 or nz == 0:
+            res["VIL"][...] = np.nan
+            res["ET"][...] = np.nan
+            res["ET_TOPPED"][...] = 0
     if "valid_count" in want:
         res["valid_count"] = pinned_empty(shape, np.int16)
     if "coverage_count" in want or "blind_mask" in want:
         res["coverage_count"] = pinned_empty(shape, np.int16)
         res["blind_mask"] = pinned_empty(shape, np.int8)
     if "CR" in want:
-        res["CR"] = np.empty((nx, ny), dtype=np.float64)
+        res["CR"] = pinned_empty((nx, ny), np.float64)
     if "quality" in want:
         res["quality"] = pinned_empty(shape, np.float64)
     ties = ctypes.c_uint64(0)
@@ -477,7 +482,12 @@ def _network_compose_devices(devices, volumes, radar_sites_xy, radar_heights, gr
     if "CR" in want:
         res["CR"] = pinned_empty((nx, ny), np.float64)
     reach = [sharding.radar_reach_m(v.vol_range) for v in volumes]
-    bounds = sharding.slab_bounds_weighted(sharding.row_costs(gx, gy, sites, reach), len(devices))
+    if len(devices) == 1:
+        bounds = [(0, nx)]          # (the kernel culls radars per tile: nothing to balance or to drop here)
+    else:
+        # the cost estimate only balances the slabs: every 8th column of the grid is enough for it
+        sub = slice(None, None, 8) if ny >= 64 else slice(None)
+        bounds = sharding.slab_bounds_weighted(sharding.row_costs(gx[:, sub], gy[:, sub], sites, reach), len(devices))
     ties = [0] * len(devices)
     errors = []
 
@@ -489,7 +499,7 @@ def _network_compose_devices(devices, volumes, radar_sites_xy, radar_heights, gr
             r0, r1 = bounds[di]
             if r1 <= r0:
                 return
-            idx = sharding.radars_reaching(gx[r0:r1], gy[r0:r1], sites, reach)
+            idx = list(range(n)) if len(devices) == 1 else sharding.radars_reaching(gx[r0:r1], gy[r0:r1], sites, reach)
             if not idx or nx * ny == 0:
                 for key, val in (("composite", miss), ("valid_count", 0), ("coverage_count", 0), ("blind_mask", 1),
                                  ("CR", np.nan), ("VIL", np.nan), ("ET", np.nan), ("ET_TOPPED", 0)):
