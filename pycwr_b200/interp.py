@@ -422,6 +422,9 @@ def network_compose(volumes, radar_sites_xy, radar_heights, grid_x, grid_y, leve
     return res
 
 
+_DEVICE_SHARES = {}      # device list -> share of the grid's cost each device takes (measured, see below)
+
+
 def _network_compose_devices(devices, volumes, radar_sites_xy, radar_heights, grid_x, grid_y, level_heights, fillvalue,
                              method, influence_radius_m, blind_method, quality_weight_terms, range_decay_m,
                              beam_radius_ref_m, vertical_gap_ref_deg, beam_widths, effective_earth_radius,
@@ -482,20 +485,35 @@ def _network_compose_devices(devices, volumes, radar_sites_xy, radar_heights, gr
     if "CR" in want:
         res["CR"] = pinned_empty((nx, ny), np.float64)
     reach = [sharding.radar_reach_m(v.vol_range) for v in volumes]
+    costs = None
     if len(devices) == 1:
         bounds = [(0, nx)]          # (the kernel culls radars per tile: nothing to balance or to drop here)
     else:
-        # the cost estimate only balances the slabs: every 8th column of the grid is enough for it
-        sub = slice(None, None, 8) if ny >= 64 else slice(None)
-        bounds = sharding.slab_bounds_weighted(sharding.row_costs(gx[:, sub], gy[:, sub], sites, reach), len(devices))
+        # The cost estimate only balances the slabs: 17 columns of the grid are enough for it (a contiguous copy —
+        # reductions over a strided view of the 72 MB arrays cost 18 ms).  The shares of the devices start equal and
+        # follow the rates measured on the previous call with the same device list: on the GPU boxes of this pool the
+        # device-to-host path of GPUs 0-3 is about half as fast as that of GPUs 4-7 when all eight return results
+        # (profiles/r02_host_link.md), and a slab is done when its rows are back in host memory.
+        cols = np.unique(np.linspace(0, ny - 1, min(ny, 17)).astype(np.int64)) if ny else np.zeros(0, np.int64)
+        costs = sharding.row_costs(np.take(gx, cols, axis=1), np.take(gy, cols, axis=1), sites, reach)
+        shares = _DEVICE_SHARES.get(tuple(devices))
+        if shares is None or len(shares) != len(devices):
+            shares = np.full(len(devices), 1.0 / len(devices))
+        bounds = sharding.slab_bounds_shares(costs, shares)
+    elapsed = [0.0] * len(devices)
     ties = [0] * len(devices)
     errors = []
+    import os
+    import time
+    trace = [None] * len(devices) if os.environ.get("PCG_PYTRACE") else None      # per-thread timeline (diagnostic)
+    t_call = time.perf_counter()
 
     def ptr(key):
         return _lib.as_ptr(res[key]) if key in res else None
 
     def slab(di):
         try:
+            t_in = time.perf_counter()
             r0, r1 = bounds[di]
             if r1 <= r0:
                 return
@@ -532,6 +550,7 @@ def _network_compose_devices(devices, volumes, radar_sites_xy, radar_heights, gr
             handles = (ctypes.c_void_p * m)(*[v.handle for v in dvs])
             t = ctypes.c_uint64(0)
             dp = _lib.c_double_p
+            t_prep = time.perf_counter()
             _lib.check(_lib.load().pcg_network_compose_rows(
                 m, handles, rx.ctypes.data_as(dp), ry.ctypes.data_as(dp), hh.ctypes.data_as(dp), rr.ctypes.data_as(dp),
                 bwp, ctypes.byref(prm), _lib.as_ptr(gx), _lib.as_ptr(gy), nx, r0, r1 - r0, ny,
@@ -539,6 +558,10 @@ def _network_compose_devices(devices, volumes, radar_sites_xy, radar_heights, gr
                 ptr("coverage_count"), ptr("blind_mask"), ptr("CR"), ctypes.byref(t),
                 None if cpar is None else cpar.ctypes.data_as(dp), ptr("VIL"), ptr("ET"), ptr("ET_TOPPED")))
             ties[di] = int(t.value)
+            t_out = time.perf_counter()
+            elapsed[di] = t_out - t_in
+            if trace is not None:
+                trace[di] = (1e3 * (t_in - t_call), 1e3 * (t_prep - t_in), 1e3 * (t_out - t_prep), r1 - r0, m)
         except BaseException as exc:                # noqa: BLE001 - re-raised by the caller's thread below
             errors.append(exc)
 
@@ -555,6 +578,20 @@ def _network_compose_devices(devices, volumes, radar_sites_xy, radar_heights, gr
     _lib.set_device(prev)
     if errors:
         raise errors[0]
+    if costs is not None and len(set(devices)) == len(devices):
+        # next call's shares: the cost each device got through per second, damped (the rates depend on who else is
+        # copying at the same time) and floored so that no device is starved by one slow call
+        done = np.array([float(costs[b[0]:b[1]].sum()) for b in bounds])
+        secs = np.array(elapsed)
+        if np.all(secs > 0.0) and np.all(done > 0.0):
+            rate = done / secs
+            new = 0.5 * shares / shares.sum() + 0.5 * rate / rate.sum()
+            new = np.maximum(new, 0.25 / len(devices))
+            _DEVICE_SHARES[tuple(devices)] = new / new.sum()
+    if trace is not None:
+        print("[pcg pytrace] alloc+bounds %.2f ms; per device (start, prep, call ms, rows, radars): %s; total %.2f ms" % (
+            1e3 * 0, ["%.1f/%.1f/%.1f/%d/%d" % t if t else "-" for t in trace], 1e3 * (time.perf_counter() - t_call)),
+            flush=True)
     res["tie_voxels"] = int(sum(ties))
     res["slab_rows"] = [b[1] - b[0] for b in bounds]
     return res

@@ -64,6 +64,28 @@ def slab_bounds_weighted(costs, world):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def slab_bounds_shares(costs, shares):
+    """Contiguous row slabs whose total costs are in the proportions ``shares`` (one entry per rank, any positive
+    scale): rank r owns rows [b[r][0], b[r][1]).  ``slab_bounds_weighted`` is the equal-shares case."""
+    costs = np.asarray(costs, dtype=np.float64)
+    shares = np.asarray(shares, dtype=np.float64)
+    world = int(shares.size)
+    if world < 1 or not np.all(shares > 0.0):
+        raise ValueError("shares must hold one positive entry per rank")
+    n = costs.size
+    total = float(costs.sum())
+    if n == 0 or not total > 0.0:
+        return slab_bounds(n, world)
+    cum = np.concatenate([[0.0], np.cumsum(costs)])
+    targets = total * np.cumsum(shares) / float(shares.sum())
+    cuts = [0]
+    for r in range(world - 1):
+        cut = int(np.searchsorted(cum, targets[r], side="left"))
+        cuts.append(min(max(cut, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def radar_reach_m(vol_range, margin=1.002, extra_m=1000.0):
     """Ground distance beyond which no gate of the radar can be reached (slant range >= 0.999 x
     ground distance for |z|, |h| << Re; the kernel applies the same cull per block)."""

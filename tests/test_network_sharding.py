@@ -108,3 +108,18 @@ def test_two_rank_gloo_sharded_network_equals_unsharded(tmp_path):
         assert np.array_equal(r0[key], g[ref], equal_nan=True), key      # gathered == reference's unsharded result
         assert np.array_equal(r0[key], r1[key], equal_nan=True), key     # every rank holds the same full grid
         assert r0[key].dtype == g[ref].dtype, key
+
+
+def test_slab_bounds_follow_the_given_shares():
+    """``slab_bounds_shares``: contiguous slabs whose costs are in the requested proportions (what the multi-GPU
+    product uses to give the GPUs with the faster host link more rows); equal shares = ``slab_bounds_weighted``."""
+    rng = np.random.default_rng(5)
+    costs = rng.uniform(0.5, 3.0, 2000)
+    assert S.slab_bounds_shares(costs, [1, 1, 1, 1]) == S.slab_bounds_weighted(costs, 4)
+    b = S.slab_bounds_shares(costs, [1, 2, 1, 4])
+    assert b[0][0] == 0 and b[-1][1] == costs.size and all(b[i][1] == b[i + 1][0] for i in range(3))
+    got = np.array([costs[x:y].sum() for x, y in b]) / costs.sum()
+    assert np.allclose(got, np.array([1, 2, 1, 4]) / 8.0, atol=2e-3)
+    assert S.slab_bounds_shares(np.zeros(0), [1, 1]) == [(0, 0), (0, 0)]
+    with pytest.raises(ValueError):
+        S.slab_bounds_shares(costs, [1, 0])
