@@ -338,6 +338,14 @@ def _fused_gather(torch, dist, dev, rank, world, lib, launch_args, nlat, r0, ste
         lib.pcg_peer_free(full)
 
 
+def _static_traffic(key):
+    """DRAM bytes per launch of the dominant kernel of workload `key`, from the committed ncu capture."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key, {}).get("bytes")
+    except Exception:                                   # noqa: BLE001
+        return None
+
+
 def gpu_numa_cpus(torch, index):
     """CPUs local to GPU `index` (sysfs local_cpulist of its PCI function), or None when the box does not say."""
     try:
@@ -385,15 +393,75 @@ def network_e2e_devices(args, devices):
         out_bytes = sum(int(np.asarray(a).nbytes) for k, a in res.items() if hasattr(a, "nbytes"))
         slab_rows = list(res["slab_rows"])
         del res
+        one_gpu_ms = None
+        if len(devices) > 1:
+            # the SAME composite unsharded on one GPU of this box, in this run (inputs resident, device-timed like
+            # the sharded `ms_per_step`): what the strong-scaling numbers of this line are measured against
+            one_gpu_ms = _network_one_gpu_ms(devices[0], hvs, sites, heights, bws, cfg)
     finally:
         for h in hvs:
             h.close()
     voxels = int(lv.size) * gx.size
     return {"value": voxels / dt, "unit": UNIT, "ms_per_call": dt * 1e3, "ms_best": float(min(ts)) * 1e3,
-            "n_gpus": len(devices), "slab_rows": slab_rows,
+            "n_gpus": len(devices), "slab_rows": slab_rows, "one_gpu_kernel_ms_same_run": one_gpu_ms,
             "h2d_bytes_per_step": int(gx.nbytes + gy.nbytes), "d2h_bytes_per_step": out_bytes,
             "api": "pycwr_b200.interp.network_compose(devices=[0..N-1]): one host call, one thread per GPU, every "
                    "slab copied to the shared pinned result by its own GPU (no device-to-device exchange)"}
+
+
+def _network_one_gpu_ms(device, hvs, sites, heights, bws, cfg, steps=3):
+    """Device time of the unsharded C4 composite on `device` (pcg_network_compose_dev, full grid, L2 flushed)."""
+    import ctypes
+
+    import torch
+
+    from pycwr_b200 import _lib
+    _lib.set_device(device)
+    dev = torch.device("cuda", device)
+    with torch.cuda.device(dev):
+        dvs = [h.on(device) for h in hvs]
+        gx = torch.from_numpy(np.ascontiguousarray(cfg["GridX"])).to(dev)
+        gy = torch.from_numpy(np.ascontiguousarray(cfg["GridY"])).to(dev)
+        levels = cfg["levels"]
+        nz, (nlat, nlon) = int(levels.size), cfg["GridX"].shape
+        comp = torch.empty((nz, nlat, nlon), dtype=torch.float64, device=dev)
+        cov = torch.empty((nz, nlat, nlon), dtype=torch.int16, device=dev)
+        blind = torch.empty((nz, nlat, nlon), dtype=torch.int8, device=dev)
+        cr = torch.empty((nlat, nlon), dtype=torch.float64, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        n = len(dvs)
+        lib = _lib.load()
+        prm = _lib.NetworkParams(_lib.NET_METHODS["quality_weighted"], 3, 7, 1, 300000.0, 230000.0, 3000.0, 0.5)
+        handles = (ctypes.c_void_p * n)(*[v.handle for v in dvs])
+        dp = _lib.c_double_p
+        rx, ry = np.ascontiguousarray(sites[:, 0]), np.ascontiguousarray(sites[:, 1])
+        rh = np.ascontiguousarray(np.array(heights, dtype=np.float64))
+        re = np.full(n, 8494666.6666666661)
+        keep = [np.ascontiguousarray(b) for b in bws]
+        bwp = (_lib.c_double_p * n)(*[b.ctypes.data_as(dp) for b in keep])
+
+        def launch():
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.pcg_network_compose_dev(
+                n, handles, rx.ctypes.data_as(dp), ry.ctypes.data_as(dp), rh.ctypes.data_as(dp), re.ctypes.data_as(dp),
+                bwp, ctypes.byref(prm), gx.data_ptr(), gy.data_ptr(), nlat, nlon, levels.ctypes.data_as(dp), nz, FILL,
+                comp.data_ptr(), None, cov.data_ptr(), blind.data_ptr(), cr.data_ptr(), None, st))
+
+        for _ in range(3):
+            launch()
+            flush.zero_()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            launch()
+            b.record()
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        del comp, cov, blind, cr, flush, gx, gy
+        torch.cuda.empty_cache()
+    return ms
 
 
 def bench_network(args, torch, dist, dev, rank, world):
@@ -573,6 +641,10 @@ def bench_network(args, torch, dist, dev, rank, world):
         "valid_fraction_rank0": valid_frac, "e2e": e2e,
         "roofline": {"bound": "hbm", "achieved": balg / kern_s / 1e9, "peak": peak * world, "unit": "GB/s",
                      "frac": balg / kern_s / 1e9 / (peak * world), "algorithmic_bytes": int(balg),
+                     "traffic": _static_traffic("C4_network_32r_3000x3000x30") if world == 1 and args.network_scale == 1.0
+                     and args.network_radars == 32 else None,
+                     "traffic_source": "profiles/traffic.json (one `ncu --set full` capture of this kernel on this workload; "
+                                       "static, not measured in this run)",
                      "kernel": "pcg::net_tile_kernel<3,1> (one launch per level chunk)" if os.environ.get("PCG_NET") != "passes"
                      else "pcg::net_radar_kernel<3,1> x radars + net_cull_kernel + net_finalize_kernel<3>"},
     }
