@@ -177,6 +177,22 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
     constexpr bool SPEC = false;
 #endif
 
+    // The 2-D weights exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389) of a column are taken RELATIVE to its nearest
+    // reaching radar: exp(-4 (d^2 - d_min^2) / R_inf^2).  Numerator and denominator of the weighted mean scale by
+    // the same factor, so the quotient is the reference's; but the float32 sums no longer underflow where every
+    // reaching radar is far compared with the influence radius (the reference accumulates in float64: a voxel seen
+    // only from 4.7 influence radii away has a value there and had none here).
+    double d2_min = 0.0;
+    if (METHOD == kNetExp || METHOD == kNetQuality) {
+        d2_min = __longlong_as_double(0x7ff0000000000000LL);
+        for (int li = 0; li < nlist; ++li) {
+            const NetRadar& R = p.radars[s_list[li]];
+            const double x = sub(gx, R.x), y = sub(gy, R.y);
+            const double d2 = add(mul(x, x), mul(y, y));
+            if ((d2 <= R.cull2) & (d2 < d2_min)) d2_min = d2;
+        }
+    }
+
     // ---- 2. the reaching radars, in radar order ----
 #pragma unroll 1
     for (int li = 0; li < nlist; ++li) {
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
             }
         }
         // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
-        const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? __expf(-(float)d2 * R.inv_r2inf4) : 1.f;
+        const float w2d = (METHOD == kNetExp || METHOD == kNetQuality) ? __expf(-(float)sub(d2, d2_min) * R.inv_r2inf4) : 1.f;
         const bool lowest_sweep = p.lowest_sweep != 0, highest_sweep = p.highest_sweep != 0;
         const int k_first = lowest_sweep ? -1 : 0;
         const unsigned k_span = (unsigned)((highest_sweep ? ne - 1 : ne - 2) - k_first);
