@@ -23,6 +23,8 @@ There is no CPU fallback: every function that grids or merges calls the CUDA lib
 import ctypes
 import json
 
+import threading
+
 import numpy as np
 
 from . import RadarGridC as G
@@ -206,14 +208,16 @@ def _prd_volume(prd, field_name, fillvalue, range_mode, max_range_km):
     return vol_azimuth, vol_range, np.asarray(fix_elevation, dtype=np.float64), vol_value, float(radar_height), range_mode
 
 
-def _prd_device_volume(prd, field_name, fillvalue, range_mode, max_range_km):
+def _prd_device_volume(prd, field_name, fillvalue, range_mode, max_range_km, device=None):
     """(DeviceVolume, radar height, range mode used, owned): the PRD's cached device volume when it offers one
-    (``get_device_volume``: packed by the GPU from the raw sweeps), else a fresh upload of ``prd.vol``."""
+    (``get_device_volume``: packed by the GPU from the raw sweeps), else a fresh upload of ``prd.vol`` — on the
+    calling thread's current device (``device``: the same index, for the PRD's per-device cache)."""
     if hasattr(prd, "get_device_volume"):
         if hasattr(prd, "_resolve_field_range_mode"):
             range_mode = prd._resolve_field_range_mode(field_name, range_mode=range_mode)
+        kw = {} if device is None else {"device": device}
         dv = prd.get_device_volume(field_name=field_name, fillvalue=fillvalue, range_mode=range_mode,
-                                   max_range_km=max_range_km)
+                                   max_range_km=max_range_km, **kw)
         return dv, float(prd.radar_height), range_mode, False
     va, vr, fe, vv, h, used = _prd_volume(prd, field_name, fillvalue, range_mode, max_range_km)
     return DeviceVolume(va, vr, fe, vv, fillvalue=fillvalue, value_dtype="f32"), h, used, True
@@ -616,6 +620,11 @@ class SimpleDataset(dict):
         if isinstance(value, tuple):
             value = SimpleVariable(value[0], np.asarray(value[1]))
         super().__setitem__(name, value)
+
+    @property
+    def data_vars(self):
+        """The variable names (xarray: a mapping whose iteration yields them)."""
+        return list(self.keys())
 
 
 class _Coords(dict):
@@ -1109,6 +1118,59 @@ def _network_field_unfused(radars, field, source_names, mode, o, levels, want_ob
     return res
 
 
+def _resolve_devices(parallel, max_workers):
+    """The reference's ``parallel`` / ``max_workers`` (RadarInterp.py:1816-1824: a fork pool over radars) mapped to the
+    GPUs of the box: a device list for ``network_compose(devices=...)`` or None for the current device.
+    ``PYCWR_B200_DEVICES="0,1,..."`` overrides the choice (tests, pinning a job to a subset of the GPUs)."""
+    import os
+    env = os.environ.get("PYCWR_B200_DEVICES")
+    if env:
+        return [int(tok) for tok in env.split(",") if tok.strip() != ""] or None
+    if not parallel:
+        return None
+    count = _lib.device_count()
+    if max_workers is not None:
+        count = min(count, max(1, int(max_workers)))
+    return list(range(count)) if count > 1 else None
+
+
+class _PrdVolumes(object):
+    """One PRD's field as ``network_compose(devices=...)`` wants its volumes: packed on whichever GPU asks for it
+    (``on(device)``; the PRD's own per-device cache when it has one), closed afterwards if it was uploaded here."""
+
+    def __init__(self, prd, field_name, fillvalue, mode, max_range_km, first_device):
+        self._args = (prd, field_name, fillvalue, mode, max_range_km)
+        self._dev, self._owned = {}, []
+        self._lock = threading.Lock()
+        first = self.on(first_device)
+        self.ne, self.network_ready = first.ne, first.network_ready
+        self.last_gate = np.asarray(first.last_gate, dtype=np.float64)
+        self.vol_range = [np.array([g]) for g in self.last_gate]          # what the reach of the radar is read from
+
+    def on(self, device=None):
+        device = _lib.current_device() if device is None else int(device)
+        with self._lock:                                   # (two slabs of one device may ask at the same time)
+            dv = self._dev.get(device)
+            if dv is None:
+                prev = _lib.current_device()
+                _lib.set_device(device)
+                try:
+                    prd, field_name, fillvalue, mode, max_range_km = self._args
+                    dv, self.height, _, mine = _prd_device_volume(prd, field_name, fillvalue, mode, max_range_km,
+                                                                  device=device)
+                finally:
+                    _lib.set_device(prev)
+                self._dev[device] = dv
+                if mine:
+                    self._owned.append(dv)
+        return dv
+
+    def close(self):
+        for dv in self._owned:
+            dv.close()
+        self._dev, self._owned = {}, []
+
+
 def _network_field(radars, field, source_names, mode, o, levels, is_ref, cpar):
     """Composite one field on ``levels``; ``cpar`` = VIL / ET parameters when the column products are wanted too.
     Returns the result dict (``composite`` with NaN in its empty cells, coverage / blind / CR for the reflectivity
@@ -1122,11 +1184,17 @@ def _network_field(radars, field, source_names, mode, o, levels, is_ref, cpar):
     if "qc" in o["terms"] and o["qc_weight_field"] and any(r.qc_applied for r in radars):
         fused = False
     present, vols, owned, heights, bws, radii, actual, by_sweep = [], [], [], [], [], [], {}, {}
+    devices = o.get("devices") if o.get("rows") is None else None
     if fused:
         for radar in radars:
             try:
-                dv, h, _, mine = _prd_device_volume(radar.prd, source_names[radar.radar_id], o["fillvalue"], mode,
-                                                    o["max_range_km"])
+                if devices:
+                    dv = _PrdVolumes(radar.prd, source_names[radar.radar_id], o["fillvalue"], mode, o["max_range_km"],
+                                     devices[0])
+                    h, mine = dv.height, True
+                else:
+                    dv, h, _, mine = _prd_device_volume(radar.prd, source_names[radar.radar_id], o["fillvalue"], mode,
+                                                        o["max_range_km"])
             except KeyError:
                 actual[radar.radar_id] = None
                 by_sweep[radar.radar_id] = None
@@ -1149,7 +1217,7 @@ def _network_field(radars, field, source_names, mode, o, levels, is_ref, cpar):
                 beam_radius_ref_m=o["beam_radius_ref_m"], vertical_gap_ref_deg=o["vertical_gap_ref_deg"],
                 beam_widths=bws, effective_earth_radius=radii, rows=o.get("rows"),
                 outputs=(("coverage_count", "blind_mask") + (("CR",) if want_cr else ())) if is_ref else (),
-                missing=np.nan, column_products=cpar)
+                missing=np.nan, column_products=cpar, devices=devices or None)
             res["actual"], res["by_sweep"] = actual, by_sweep
             return res
     finally:
@@ -1372,8 +1440,10 @@ def run_radar_network_3d(
 
     What differs is where the work runs: the selected volumes are read on the host (``read_auto``), packed to the
     device, and every field is composited by the fused network kernels in one call (``network_compose``) instead
-    of the fork pool of per-radar NumPy workers (:1816-1861) — ``parallel`` / ``max_workers`` are accepted and have
-    nothing to fan out.  Plot options are accepted and recorded but no figure is drawn (presentation is out of
+    of the fork pool of per-radar NumPy workers (:1816-1861).  ``parallel`` / ``max_workers`` keep their meaning one
+    level down: with ``parallel`` true and more than one GPU in the box the composite fans out over
+    ``min(max_workers, GPUs)`` devices (``network_compose(devices=...)``: row slabs, one host thread per GPU, every
+    slab returned by its own GPU), otherwise it runs on the current device.  Plot options are accepted and recorded but no figure is drawn (presentation is out of
     scope): ``plot_files`` is ``{}``.
     """
     from datetime import datetime
@@ -1506,6 +1576,7 @@ def run_radar_network_3d(
         "effective_earth_radius": effective_earth_radius, "qc_weight_field": qc_weight_field,
         "blockage_config": blockage_config, "coverage_policy": coverage_policy, "vil_min_dbz": vil_min_dbz,
         "vil_max_dbz_cap": vil_max_dbz_cap, "et_threshold_dbz": et_threshold_dbz,
+        "devices": _resolve_devices(parallel, max_workers),
     }
     dataset, actual_by_field, source_by_field = _network_dataset(
         radars, o, field_names, field_range_mode, level_heights, product_level_heights, output_products, lon, lat)

@@ -105,13 +105,17 @@ class ArrayPRD(object):
         return self.vol
 
     def get_device_volume(self, field_name="dBZ", fillvalue=FILL, range_mode=None, max_range_km=None,
-                          value_dtype="f32"):
+                          value_dtype="f32", device=None):
         """The device form of ``get_vol_data``: the sweeps go to the GPU as stored (scan order,
-        NaN) and are sorted / clipped / fill-marked by the pack kernels; cached per key like ``_vol_cache``."""
+        NaN) and are sorted / clipped / fill-marked by the pack kernels; cached per key like ``_vol_cache``.
+        ``device``: the GPU the calling thread has selected (``_lib.set_device``), part of the cache key — the
+        multi-GPU network product asks for the same field on several devices."""
+        from . import _lib
         range_mode = self._resolve_field_range_mode(field_name, range_mode=range_mode)
         max_range_km = None if max_range_km is None else float(max_range_km)
         sweeps = self._sweeps_of(field_name, range_mode)
-        key = (field_name, float(fillvalue), range_mode, max_range_km, value_dtype)
+        device = _lib.current_device() if device is None else int(device)
+        key = (field_name, float(fillvalue), range_mode, max_range_km, value_dtype, device)
         if key not in self._dev_cache:
             from .runtime import DeviceVolume
             self._dev_cache[key] = DeviceVolume.from_sweeps(sweeps, self.fix_elevation,

@@ -386,3 +386,30 @@ def test_qc_hook_and_attrs(tmp_path):
     assert np.allclose(ds["dBZ"].values, 30.0, atol=1e-3)       # max(25 corrected, 30 original)
     with pytest.raises(ValueError, match="moments required"):
         _run(_sub(tmp_path, "x"), prds, use_qc=True, qc_fallback="raise")
+
+
+@pytest.mark.gpu
+def test_run_radar_network_3d_fans_out_over_devices(tmp_path, monkeypatch):
+    """``parallel`` / ``max_workers`` one level down: the composite of every field goes through
+    ``network_compose(devices=...)``.  On a one-GPU box the device list is forced to ``0,0`` (two slabs, two host
+    threads on the same GPU): the dataset must equal the single-device run variable by variable."""
+    def make():
+        return {"Z9001": FakePRD("Z9001", lon=120.0, lat=30.0, values={"dBZ": 10.0, "ZDR": 1.0}),
+                "Z9002": FakePRD("Z9002", lon=120.05, lat=30.02, values={"dBZ": 30.0, "ZDR": 3.0})}
+    kw = dict(field_names=["dBZ", "ZDR"], lon_min=119.98, lon_max=120.08, lat_min=29.97, lat_max=30.05,
+              level_heights=np.array([150.0, 400.0, 900.0]), composite_method="quality_weighted")
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    monkeypatch.delenv("PYCWR_B200_DEVICES", raising=False)
+    one, _, _ = _run(tmp_path / "a", make(), **kw)
+    monkeypatch.setenv("PYCWR_B200_DEVICES", "0,0")
+    many, _, _ = _run(tmp_path / "b", make(), **kw)
+    assert sorted(one.data_vars) == sorted(many.data_vars)
+    for name in one.data_vars:
+        a, b = np.asarray(one[name].values), np.asarray(many[name].values)
+        assert a.shape == b.shape and a.dtype == b.dtype, name
+        assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f"), name
+    assert np.isfinite(np.asarray(one["dBZ"].values)).any()
+    assert I._resolve_devices(False, None) == [0, 0]                       # the override wins
+    monkeypatch.delenv("PYCWR_B200_DEVICES")
+    assert I._resolve_devices(False, 8) is None and I._resolve_devices(True, 1) is None
