@@ -67,7 +67,9 @@ __host__ __device__ inline size_t net2_smem_bytes(int ne_max, int nz, bool neare
     size_t b = 512;                                                    // bbox partials, hit flags, radar list
     b += (size_t)ne_max * kNet2Threads * sizeof(AzEntry);              // azimuth table [sweep][thread]
     b += (size_t)nz * kNet2Threads * (2 * sizeof(float) + sizeof(unsigned short));
+    b = (b + 15) & ~(size_t)15;
     if (nearest) b += (size_t)nz * kNet2Threads * sizeof(double);
+    b += (size_t)(kNet2Threads / 32) * ne_max * (sizeof(AzDesc) + sizeof(double));   // per-warp sweep descriptors
     return (b + 15) & ~(size_t)15;
 }
 
@@ -99,6 +101,17 @@ __device__ __forceinline__ void sts_u16(unsigned addr, unsigned v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
 }
 
+// one sweep's CR sample by the reference chain (RadarGridC.pyx:596-624 through range_bracket / sample_pairs): the
+// exact square root, the bracket verified against the range table itself (rare: the r2-space guess was not confirmed;
+// volumes without one shared regular range table)
+__device__ __noinline__ float net2_cr_exact(const SweepDesc* d, const double2* rg_t, const float4* val0,
+                                            const AzEntry* az, double r2, float fill32) {
+    const double r = sqrt_rn(r2);
+    if (r != r) return fill32;
+    const RangeBracket rb = range_bracket(*d, rg_t, r, false);
+    return sample_pairs(val0, *az, rb, fill32);
+}
+
 template <int METHOD, bool UNI>
 __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const __grid_constant__ NetArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -112,6 +125,17 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
     double* a_d2 = reinterpret_cast<double*>(smem_raw + ((512 + (size_t)p.ne_max * T * sizeof(AzEntry) +
                                              (size_t)p.nz * T * 10 + 15) & ~(size_t)15));   // nearest only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // per-warp copies of the current radar's sweep descriptors (what the azimuth brackets and the CR pass read):
+    // fetched by one lane per sweep in ONE round trip instead of one dependent L2 access per sweep and loop
+    AzDesc* w_ad;
+    double* w_tan;
+    {
+        const size_t acc_end = ((512 + (size_t)p.ne_max * T * sizeof(AzEntry) + (size_t)p.nz * T * 10 + 15) & ~(size_t)15) +
+                               (METHOD == kNetNearest ? (size_t)p.nz * T * sizeof(double) : 0);
+        unsigned char* base = smem_raw + acc_end + (size_t)warp * p.ne_max * (sizeof(AzDesc) + sizeof(double));
+        w_ad = reinterpret_cast<AzDesc*>(base);
+        w_tan = reinterpret_cast<double*>(base + (size_t)p.ne_max * sizeof(AzDesc));
+    }
 
     bool active;
     long long col;
@@ -193,49 +217,91 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
         }
     }
 
+    // Dead work: in the quality-weighted composite a radar that does not OBSERVE a voxel has weight zero there, so its
+    // sample can only show in valid_count.  When the caller does not ask for valid_count (run_radar_network_3d
+    // never does: `composite, _ = compose_network_volume(...)`, RadarInterp.py:1957,1990) the voxels a radar merely
+    // fills in from its lowest sweep ('lowest_sweep' / 'hybrid' blind methods: 62 % of the sampled voxels at config
+    // C4) are not sampled at all — composite, coverage_count, blind_mask and CR are bit for bit what they would be.
+    const bool dead_unobserved = (METHOD == kNetQuality) && p.quality != 0 && p.valid_count == nullptr;
+
     // ---- 2. the reaching radars, in radar order ----
 #pragma unroll 1
     for (int li = 0; li < nlist; ++li) {
         const int ir = s_list[li];
         const NetRadar& R = p.radars[ir];
+        const int ne = R.ne;
+        {
+            // this radar's sweep descriptors for the warp (every lane takes part, whether its column is in reach or not)
+            __syncwarp();
+            const SweepDesc* __restrict__ sw_t = R.vol.sweeps;
+            for (int sw = lane; sw < ne; sw += 32) {
+                const SweepDesc* d = sw_t + sw;
+                AzDesc a;
+                a.az_first = d->az_first; a.az_inv_step = d->az_inv_step; a.az_off = d->az_off;
+                a.naz = (d->naz >= 2 && d->ng >= 2) ? d->naz : 0;                  // 0: degenerate, general path
+                a.val_off = (unsigned)d->val_off; a.ng = d->ng;
+                w_ad[sw] = a;
+                w_tan[sw] = d->tan_e;
+            }
+            __syncwarp();
+        }
         // radar-local coordinates (RadarInterp.py:990-991) and the 2-D distance of the weight cache
         const double x = sub(gx, R.x), y = sub(gy, R.y);
         const double d2 = add(mul(x, x), mul(y, y));
         if (!active || !(d2 <= R.cull2)) continue;            // beyond every gate: nothing to add (NaN: chain below)
-        const int ne = R.ne;
         // column invariants of this radar (RadarGridC.pyx:142-146,158)
         const double s = sqrt_rn(d2);
         const double phi = div(s, R.Re);
         const double cphi = cos_small(phi);
         {
+            // the column's azimuth bracket of every sweep (RadarGridC.pyx:282-289), three sweeps at a time: the table
+            // entries the three guesses point at are requested together
             const double az = azimuth_from_xy(x, y);
             const double2* __restrict__ azt = R.r2.az_t;
-            const SweepDesc* __restrict__ sw_t = R.vol.sweeps;
 #pragma unroll 1
-            for (int sw = 0; sw < ne; ++sw) {
-                const SweepDesc* d = sw_t + sw;
-                const int naz = (d->naz >= 2 && d->ng >= 2) ? d->naz : 0;
-                int g = __double2int_rd(mul(sub(az, d->az_first), d->az_inv_step)) + 1;
-                AzEntry e;
-                int rec;
-                bool done = false;
-                if (g >= 1 && g < naz) {
-                    const double2* Tt = azt + d->az_off + (unsigned)(g - 1);
-                    double2 lo = __ldg(Tt);
-                    double hi = __ldg(&Tt[1].x);
-                    if (az < lo.x) {
-                        if (g >= 2) { --g; hi = lo.x; lo = __ldg(Tt - 1); }
-                    } else if (!(az < hi)) {
-                        if (g + 1 < naz) { ++g; lo = __ldg(Tt + 1); hi = __ldg(&Tt[2].x); }
-                    }
-                    if (!(az < lo.x) && (az < hi)) {
-                        e.row = (unsigned)d->val_off + (unsigned)(g - 1) * (unsigned)d->ng;
-                        e.w = (float)sub(az, lo.x) * (float)lo.y;
-                        done = true;
+            for (int sw0 = 0; sw0 < ne; sw0 += 3) {
+                AzDesc d[3];
+                int g[3];
+                double2 lo[3];
+                double hi[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int sw = min(sw0 + j, ne - 1);
+                    d[j] = w_ad[sw];
+                    g[j] = __double2int_rd(mul(sub(az, d[j].az_first), d[j].az_inv_step)) + 1;
+                    lo[j] = make_double2(0.0, 0.0); hi[j] = 0.0;
+                    if (g[j] >= 1 && g[j] < d[j].naz) {
+                        const double2* Tt = azt + d[j].az_off + (unsigned)(g[j] - 1);
+                        lo[j] = __ldg(Tt);
+                        hi[j] = __ldg(&Tt[1].x);
                     }
                 }
-                if (!done) az_bracket_general(d, azt, az, &e, &rec);
-                my_az[(size_t)sw * T] = e;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int sw = sw0 + j;
+                    if (sw >= ne) break;
+                    AzEntry e;
+                    int rec;
+                    bool done = false;
+                    int gg = g[j];
+                    if (gg >= 1 && gg < d[j].naz) {
+                        const double2* Tt = azt + d[j].az_off + (unsigned)(gg - 1);
+                        double2 l = lo[j];
+                        double h = hi[j];
+                        if (az < l.x) {
+                            if (gg >= 2) { --gg; h = l.x; l = __ldg(Tt - 1); }
+                        } else if (!(az < h)) {
+                            if (gg + 1 < d[j].naz) { ++gg; l = __ldg(Tt + 1); h = __ldg(&Tt[2].x); }
+                        }
+                        if (!(az < l.x) && (az < h)) {
+                            e.row = d[j].val_off + (unsigned)(gg - 1) * (unsigned)d[j].ng;
+                            e.w = (float)sub(az, l.x) * (float)l.y;
+                            done = true;
+                        }
+                    }
+                    if (!done) az_bracket_general(R.vol.sweeps + sw, azt, az, &e, &rec);
+                    my_az[(size_t)sw * T] = e;
+                }
             }
         }
         // exp(-4 d^2 / R_inf^2) (RadarInterp.py:1389)
@@ -337,9 +403,11 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                     // (62 % of the sampled voxels at config C4: a third of the L1 wavefronts of the level)
                     const int lo_s = max(k, 0);
                     gi = min(max(__float2int_rd(fmaf(rf, u_inv_step, u_c0)), 1), u_ngm1);
-                    tg = ldg_vol(g_t + (u_rng_off + (unsigned)(gi - 1)));
-                    ea = lds_az(az_addr + (unsigned)lo_s * az_pitch);
-                    qa4 = ldg_vol(val0 + (ea.row + (unsigned)gi));
+                    if (!dead_unobserved || (unsigned)k < pair_top) {
+                        tg = ldg_vol(g_t + (u_rng_off + (unsigned)(gi - 1)));
+                        ea = lds_az(az_addr + (unsigned)lo_s * az_pitch);
+                        qa4 = ldg_vol(val0 + (ea.row + (unsigned)gi));
+                    }
                     if ((unsigned)k < pair_top) {
                         lk = __ldg(pk + 1);
                         eb = lds_az(az_addr + (unsigned)(lo_s + 1) * az_pitch);
@@ -373,6 +441,7 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
             if (skip) {                                        // blind-zone rules: nothing sampled, nothing observable
                 continue;                                      // (nothing valid, nothing observable: no contribution)
             }
+            if (dead_unobserved && !pair) continue;            // one-sweep fill-in with weight zero: nothing to add
             int ngm1 = u_ngm1;
             float rj, idr;
             if (SPEC) {
@@ -464,21 +533,70 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
             // get_CR_xy on the local grid: every sweep at its fixed elevation, blind "mask"
             // (RadarGridC.pyx:596-624), then the NaN-aware max over radars (RadarInterp.py:2047-2063)
             const double sphi = sin_small(phi);
-            const double2* rg_t = reinterpret_cast<const double2*>(R.vol.rng);
-            for (int ie = 0; ie < ne; ++ie) {
-                const SweepDesc& d = R.vol.sweeps[ie];
-                if (d.naz < 2 || d.ng < 2) continue;
-                const double denom = sub(cphi, mul(sphi, d.tan_e));
-                if (denom == 0.0) continue;
-                const double g = div(R.a, denom);
-                double r2 = sub(add(R.a2, mul(g, g)), mul(mul(R.twoa, g), cphi));
-                if (r2 < 0.0) r2 = 0.0;
-                const double r = sqrt_rn(r2);
-                if (r != r) continue;
-                const RangeBracket rb = range_bracket(d, rg_t, r, false);
-                const float v = sample_pairs(val0, my_az[(size_t)ie * T], rb, fill32);
-                if (v == fill32 || v != v) continue;
-                if (!(cr_best >= v)) cr_best = v;             // NaN (nothing yet) or smaller
+            if (UNI) {
+                // Uniform-table volumes, three sweeps at a time: the geometry chain of the reference in FP64 up to
+                // r2 (bit-identical), the gate bracket in r2 space like the level loop (r >= R[j] <=> r2 >= tg[j]:
+                // no FP64 square root, one band load), and the three bands and three quads requested together.
+                // A guess the band does not confirm takes the reference chain (net2_cr_exact).
+                const double2 ends = __ldg(reinterpret_cast<const double2*>(&fs_t[0].tg_first));   // {tg_first, tg_gt_last}
+#pragma unroll 1
+                for (int ie0 = 0; ie0 < ne; ie0 += 3) {
+                    double r2v[3];
+                    float rfv[3];
+                    int giv[3];
+                    bool okv[3];
+                    double2 tgv[3];
+                    float4 qv[3];
+                    AzEntry ev[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int ie = min(ie0 + j, ne - 1);
+                        const double denom = sub(cphi, mul(sphi, w_tan[ie]));
+                        const double g = div(R.a, denom);
+                        double r2 = sub(add(R.a2, mul(g, g)), mul(mul(R.twoa, g), cphi));
+                        if (r2 < 0.0) r2 = 0.0;
+                        // r in [R[0], R[ng-1]] (RadarGridC.pyx:275-280, blind "mask"); a NaN fails both tests
+                        okv[j] = (ie0 + j < ne) & (denom != 0.0) & (r2 >= ends.x) & (r2 < ends.y);
+                        r2v[j] = r2;
+                        const float f = okv[j] ? (float)r2 : 1.f;
+                        rfv[j] = f * rsqrt_approx(f);
+                        giv[j] = min(max(__float2int_rd(fmaf(rfv[j], u_inv_step, u_c0)), 1), u_ngm1);
+                        tgv[j] = ldg_vol(g_t + (u_rng_off + (unsigned)(giv[j] - 1)));
+                        ev[j] = lds_az(az_addr + (unsigned)ie * az_pitch);
+                        qv[j] = ldg_vol(val0 + (ev[j].row + (unsigned)giv[j]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        if (!okv[j]) continue;
+                        float v;
+                        if ((r2v[j] >= tgv[j].x) & (r2v[j] < tgv[j].y)) {
+                            const float rj = fmaf((float)(giv[j] - 1), u_step, u_r_first);
+                            const float w_r = (float)sub(r2v[j], tgv[j].x) * u_inv_step * rcp_approx(rfv[j] + rj);
+                            const float er0 = fmaf(ev[j].w, qv[j].y - qv[j].x, qv[j].x);
+                            const float er1 = fmaf(ev[j].w, qv[j].w - qv[j].z, qv[j].z);
+                            v = lerp_fill(w_r, er0, er1, fill32);
+                        } else {
+                            v = net2_cr_exact(R.vol.sweeps + (ie0 + j), reinterpret_cast<const double2*>(R.vol.rng), val0,
+                                              my_az + (size_t)(ie0 + j) * T, r2v[j], fill32);
+                        }
+                        if (v == fill32 || v != v) continue;
+                        if (!(cr_best >= v)) cr_best = v;     // NaN (nothing yet) or smaller
+                    }
+                }
+            } else {
+                const double2* rg_t = reinterpret_cast<const double2*>(R.vol.rng);
+                for (int ie = 0; ie < ne; ++ie) {
+                    const SweepDesc& d = R.vol.sweeps[ie];
+                    if (d.naz < 2 || d.ng < 2) continue;
+                    const double denom = sub(cphi, mul(sphi, d.tan_e));
+                    if (denom == 0.0) continue;
+                    const double g = div(R.a, denom);
+                    double r2 = sub(add(R.a2, mul(g, g)), mul(mul(R.twoa, g), cphi));
+                    if (r2 < 0.0) r2 = 0.0;
+                    const float v = net2_cr_exact(&d, rg_t, val0, my_az + (size_t)ie * T, r2, fill32);
+                    if (v == fill32 || v != v) continue;
+                    if (!(cr_best >= v)) cr_best = v;         // NaN (nothing yet) or smaller
+                }
             }
         }
     }
