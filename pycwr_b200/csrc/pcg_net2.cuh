@@ -70,6 +70,8 @@ __host__ __device__ inline size_t net2_smem_bytes(int ne_max, int nz, bool neare
     b = (b + 15) & ~(size_t)15;
     if (nearest) b += (size_t)nz * kNet2Threads * sizeof(double);
     b += (size_t)(kNet2Threads / 32) * ne_max * (sizeof(AzDesc) + sizeof(double));   // per-warp sweep descriptors
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)(kNet2Threads / 32) * nz * 2 * sizeof(double2);       // per-warp level constants + lowest-sweep band
     return (b + 15) & ~(size_t)15;
 }
 
@@ -129,12 +131,16 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
     // fetched by one lane per sweep in ONE round trip instead of one dependent L2 access per sweep and loop
     AzDesc* w_ad;
     double* w_tan;
+    double2* w_lev;                 // [nz][2]: {a2g2, twoag}, {t_lo, t_hi} of the "below the lowest sweep" record
     {
         const size_t acc_end = ((512 + (size_t)p.ne_max * T * sizeof(AzEntry) + (size_t)p.nz * T * 10 + 15) & ~(size_t)15) +
                                (METHOD == kNetNearest ? (size_t)p.nz * T * sizeof(double) : 0);
-        unsigned char* base = smem_raw + acc_end + (size_t)warp * p.ne_max * (sizeof(AzDesc) + sizeof(double));
+        const size_t desc = (size_t)p.ne_max * (sizeof(AzDesc) + sizeof(double));
+        unsigned char* base = smem_raw + acc_end + (size_t)warp * desc;
         w_ad = reinterpret_cast<AzDesc*>(base);
         w_tan = reinterpret_cast<double*>(base + (size_t)p.ne_max * sizeof(AzDesc));
+        const size_t lev0 = (acc_end + (T >> 5) * desc + 15) & ~(size_t)15;
+        w_lev = reinterpret_cast<double2*>(smem_raw + lev0) + (size_t)warp * p.nz * 2;
     }
 
     bool active;
@@ -243,6 +249,15 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                 w_ad[sw] = a;
                 w_tan[sw] = d->tan_e;
             }
+            // ... and its level constants with the confirmation band of "below the lowest sweep" (record 0 of a
+            // level's row): a column climbing towards the lowest beam is then recognised without a global access
+            const unsigned rb = (unsigned)(2 * ne + 3) * 32u;
+            const char* rows = reinterpret_cast<const char*>(R.r2.lp) + (size_t)p.z0 * rb;
+            const NetLevel* lvl = R.levels + p.z0;
+            for (int iz = lane; iz < p.nz; iz += 32) {
+                w_lev[2 * iz] = make_double2(__ldg(&lvl[iz].cy.a2g2), __ldg(&lvl[iz].cy.twoag));
+                w_lev[2 * iz + 1] = __ldg(reinterpret_cast<const double2*>(rows + (size_t)iz * rb));
+            }
             __syncwarp();
         }
         // radar-local coordinates (RadarInterp.py:990-991) and the 2-D distance of the weight cache
@@ -328,8 +343,6 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
         const bool sanity = p.sanity != 0;
         int k = -1;
         unsigned long long slow_mask = 0ull;
-        // level constants one level ahead (they gate r2, and r2 gates every other load of the level)
-        double n_a2g2 = nz > 0 ? __ldg(&lv[0].cy.a2g2) : 0.0, n_twoag = nz > 0 ? __ldg(&lv[0].cy.twoag) : 0.0;
 
         // one voxel's contribution: range-sanity filter (RadarInterp.py:1003-1014, on the float value against the
         // float-rounded window: the same decisions as the reference's double comparison), observability weight
@@ -374,8 +387,14 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
         for (int iz = 0; iz < nz; ++iz, lrow += row_bytes) {
             // RadarGridC.pyx:146-149 — the reference's own operations: r2 is bit-identical
             // (NetLevel is 56 bytes: its members are 8-byte, not 16-byte, aligned)
-            const double r2 = sub(n_a2g2, mul(n_twoag, cphi));
-            if (iz + 1 < nz) { n_a2g2 = __ldg(&lv[iz + 1].cy.a2g2); n_twoag = __ldg(&lv[iz + 1].cy.twoag); }
+            const double2 lc = w_lev[2 * iz];
+            const double r2 = sub(lc.x, mul(lc.y, cphi));
+            if (dead_unobserved && k == -1) {
+                // still certainly below the lowest sweep (the confirmation test of pair -1, from the warp's copy):
+                // a one-sweep fill-in with weight zero — nothing to load, nothing to add
+                const double2 c0 = w_lev[2 * iz + 1];
+                if ((r2 < c0.x) & (r2 > c0.y)) continue;
+            }
             const float r2f = (float)r2;
             const float rinv = rsqrt_approx(r2f);
             const float rf = r2f * rinv;
