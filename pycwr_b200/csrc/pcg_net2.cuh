@@ -62,6 +62,11 @@ __device__ __forceinline__ void net2_tile_column(const NetArgs& p, int tile, boo
 #endif
 constexpr int kNet2SmemKB = NET2_SMEM_KB;   // shared-memory budget of a block: levels per launch follow from it
 
+// one warp's copy of a radar's per-sweep descriptors: AzDesc, pair table entry, tan(elevation); 16-byte granular
+__host__ __device__ inline size_t net2_desc_bytes(int ne_max) {
+    return ((size_t)ne_max * (sizeof(AzDesc) + sizeof(NetPairQ) + sizeof(double)) + 15) & ~(size_t)15;
+}
+
 // dynamic shared memory of net_tile_kernel
 __host__ __device__ inline size_t net2_smem_bytes(int ne_max, int nz, bool nearest) {
     size_t b = 512;                                                    // bbox partials, hit flags, radar list
@@ -69,7 +74,7 @@ __host__ __device__ inline size_t net2_smem_bytes(int ne_max, int nz, bool neare
     b += (size_t)nz * kNet2Threads * (2 * sizeof(float) + sizeof(unsigned short));
     b = (b + 15) & ~(size_t)15;
     if (nearest) b += (size_t)nz * kNet2Threads * sizeof(double);
-    b += (size_t)(kNet2Threads / 32) * ne_max * (sizeof(AzDesc) + sizeof(double));   // per-warp sweep descriptors
+    b += (size_t)(kNet2Threads / 32) * net2_desc_bytes(ne_max);        // per-warp sweep descriptors
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(kNet2Threads / 32) * nz * 2 * sizeof(double2);       // per-warp level constants + lowest-sweep band
     return (b + 15) & ~(size_t)15;
@@ -130,15 +135,17 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
     // per-warp copies of the current radar's sweep descriptors (what the azimuth brackets and the CR pass read):
     // fetched by one lane per sweep in ONE round trip instead of one dependent L2 access per sweep and loop
     AzDesc* w_ad;
+    float4* w_pq;                   // [ne][2]: the pair table of the radar (polynomial + quality terms)
     double* w_tan;
     double2* w_lev;                 // [nz][2]: {a2g2, twoag}, {t_lo, t_hi} of the "below the lowest sweep" record
     {
         const size_t acc_end = ((512 + (size_t)p.ne_max * T * sizeof(AzEntry) + (size_t)p.nz * T * 10 + 15) & ~(size_t)15) +
                                (METHOD == kNetNearest ? (size_t)p.nz * T * sizeof(double) : 0);
-        const size_t desc = (size_t)p.ne_max * (sizeof(AzDesc) + sizeof(double));
+        const size_t desc = net2_desc_bytes(p.ne_max);
         unsigned char* base = smem_raw + acc_end + (size_t)warp * desc;
         w_ad = reinterpret_cast<AzDesc*>(base);
-        w_tan = reinterpret_cast<double*>(base + (size_t)p.ne_max * sizeof(AzDesc));
+        w_pq = reinterpret_cast<float4*>(base + (size_t)p.ne_max * sizeof(AzDesc));
+        w_tan = reinterpret_cast<double*>(base + (size_t)p.ne_max * (sizeof(AzDesc) + sizeof(NetPairQ)));
         const size_t lev0 = (acc_end + (T >> 5) * desc + 15) & ~(size_t)15;
         w_lev = reinterpret_cast<double2*>(smem_raw + lev0) + (size_t)warp * p.nz * 2;
     }
@@ -248,6 +255,9 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                 a.val_off = (unsigned)d->val_off; a.ng = d->ng;
                 w_ad[sw] = a;
                 w_tan[sw] = d->tan_e;
+                const float4* pq = reinterpret_cast<const float4*>(R.pq + sw);
+                w_pq[2 * sw] = __ldg(pq);
+                w_pq[2 * sw + 1] = __ldg(pq + 1);
             }
             // ... and its level constants with the confirmation band of "below the lowest sweep" (record 0 of a
             // level's row): a column climbing towards the lowest beam is then recognised without a global access
@@ -431,9 +441,8 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                         lk = __ldg(pk + 1);
                         eb = lds_az(az_addr + (unsigned)(lo_s + 1) * az_pitch);
                         qb4 = ldg_vol(val0 + (eb.row + (unsigned)gi));
-                        const float4* pq = reinterpret_cast<const float4*>(pq_t + lo_s);
-                        q14 = __ldg(pq);
-                        q58 = __ldg(pq + 1);
+                        q14 = w_pq[2 * lo_s];
+                        q58 = w_pq[2 * lo_s + 1];
                     }
                 } else {
                     lk = __ldg(pk + 1);
@@ -494,9 +503,8 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                 if (pair) {
                     eb = lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
                     qb4 = ldg_vol(val0 + (eb.row + (unsigned)gi));
-                    const float4* pq = reinterpret_cast<const float4*>(pq_t + lower);
-                    q14 = __ldg(pq);
-                    q58 = __ldg(pq + 1);
+                    q14 = w_pq[2 * lower];
+                    q58 = w_pq[2 * lower + 1];
                 }
             }
             const float ea0 = fmaf(ea.w, qa4.y - qa4.x, qa4.x), ea1 = fmaf(ea.w, qa4.w - qa4.z, qa4.z);
