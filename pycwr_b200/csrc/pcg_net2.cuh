@@ -11,14 +11,25 @@
 // Here a block OWNS a tile of 128 grid columns (4 warps x (4 rows x 8 columns)) for the whole call:
 //   1. it tests every radar's reach disc against the tile's bounding box (what net_cull_kernel did, no lists in HBM),
 //   2. loops over the reaching radars IN RADAR ORDER (the sums accumulate in the reference's order, np.sum over
-//      axis 0, and exactly as in round 1: the results are bit-identical) — per (column, radar): column geometry,
-//      azimuth table in shared memory, every level through the r2-space voxel path of pcg_r3.cuh,
+//      axis 0) — per (column, radar): column geometry, azimuth table in shared memory, every level through the
+//      r2-space voxel path of pcg_r3.cuh,
 //   3. keeps the tile's accumulators (sum w v, sum w as float32, two uint8 counters: 10 bytes per voxel) in shared
 //      memory, each thread touching only its own column's cells (no barriers in the radar loop),
 //   4. writes composite (with the caller's missing-value marker) / valid_count / coverage_count / blind_mask / CR
 //      once.  No memset, no accumulator traffic, no finalize pass, no relabel pass, no host synchronisation.
-// DRAM traffic is then the volumes the tiles of a grid band reach (each streamed about once, tiles run in row-band
-// order), the grids and the outputs.
+// DRAM traffic is then the radar volumes (each streamed about once: tiles run in panels, so the resident blocks share
+// radars), the grids and the outputs: 6.3 GB for 4.7 GB of algorithmic bytes at config C4.
+//
+// What the kernel waits for is not DRAM but dependent round trips to L2: with 4 x 53 KB of an SM's 256 KB configured as
+// shared memory, ~28 KB of L1 are left and every small per-radar table comes from L2 (~300 cycles).  Hence:
+//   * each warp keeps its own copy of the current radar's sweep descriptors, pair table, level constants and the
+//     confirmation band of "below the lowest sweep" in shared memory, fetched by one lane per entry in one round trip;
+//   * the azimuth brackets and the CR sweeps of a (column, radar) are taken three at a time, their table entries /
+//     gate bands / quads requested together; the CR gate bracket is made in r2 space like the level loop's;
+//   * a sample that can reach no requested output is not taken (quality-weighted composite without valid_count:
+//     the one-sweep fill-in below the lowest beam has weight zero), and a column still below the lowest beam is
+//     recognised from the warp's copy without any global access.
+// 11.9 ms (round 1) -> 6.97 ms on one B200 at config C4; measured steps and rejected variants: DESIGN.md section 4.2.
 #pragma once
 #include "pcg_network.cuh"
 #include "pcg_r3.cuh"
