@@ -241,7 +241,7 @@ class _DevArray(object):
 
 
 def _fused_gather(torch, dist, dev, rank, world, lib, launch_args, nlat, r0, steps, flush, reference):
-    """Network composite with the slab gather fused into net_finalize_kernel (pcg_network_compose_gather_dev):
+    """Network composite with the slab gather fused into the tile kernel (pcg_network_compose_gather_dev):
     timed like the NCCL variant (CUDA events around the launch, max over ranks, barrier outside the events) and
     checked bit for bit against the NCCL all_gather of the same slabs."""
     import ctypes
@@ -292,7 +292,12 @@ def _fused_gather(torch, dist, dev, rank, world, lib, launch_args, nlat, r0, ste
     dp = _lib.c_double_p
 
     def launch():
-        if a["n"] == 0 or a["rows"] == 0:
+        if a["rows"] == 0:
+            return
+        if a["n"] == 0:
+            # no radar reaches this slab: its rows are empty in every rank's grid (written through the same mappings)
+            for q in range(world):
+                torch.as_tensor(_DevArray(peers[q], (nz, nlat, nlon)), device=dev)[:, r0:r0 + a["rows"]] = FILL
             return
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(lib.pcg_network_compose_gather_dev(
@@ -328,7 +333,7 @@ def _fused_gather(torch, dist, dev, rank, world, lib, launch_args, nlat, r0, ste
         del mine
         return {"ms_per_step": float(t[0].item()) / steps, "check": "bit-identical to the NCCL all_gather" if int(ok.item())
                 else "MISMATCH against the NCCL all_gather",
-                "how": "net_finalize_kernel stores each slab into every peer's grid (NVLink P2P, CUDA IPC mappings)"}
+                "how": "net_tile_kernel stores each finished tile of the slab into every peer's grid (NVLink P2P, CUDA IPC mappings)"}
     finally:
         torch.cuda.synchronize()
         dist.barrier()
