@@ -643,6 +643,9 @@ def bench_network(args, torch, dist, dev, rank, world):
         "collective": "all_gather of finished composite slabs (NCCL)" if world > 1 else "none",
         "radars_per_rank_mean": float(nrad.item()) / world, "composite_method": "quality_weighted",
         "blind_method": "hybrid", "style": "stress", "gpu_launches": int(launches),
+        "outputs": "composite, coverage_count, blind_mask, CR — the variables of run_radar_network_3d's dataset; "
+                   "valid_count is not requested (the reference workflow discards it, RadarInterp.py:1957), so samples "
+                   "with quality weight zero, which could only show there, are not taken",
         "valid_fraction_rank0": valid_frac, "e2e": e2e,
         "roofline": {"bound": "hbm", "achieved": balg / kern_s / 1e9, "peak": peak * world, "unit": "GB/s",
                      "frac": balg / kern_s / 1e9 / (peak * world), "algorithmic_bytes": int(balg),
