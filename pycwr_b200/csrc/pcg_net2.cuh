@@ -37,6 +37,9 @@
 namespace pcg {
 
 constexpr int kNet2Threads = 128;
+#ifndef NET2_GRP
+#define NET2_GRP 3                 // sweeps per group in the azimuth-bracket and CR loops (their loads go out together)
+#endif
 #ifndef NET2_PANEL
 #define NET2_PANEL 8
 #endif
@@ -295,13 +298,13 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
             const double az = azimuth_from_xy(x, y);
             const double2* __restrict__ azt = R.r2.az_t;
 #pragma unroll 1
-            for (int sw0 = 0; sw0 < ne; sw0 += 3) {
-                AzDesc d[3];
-                int g[3];
-                double2 lo[3];
-                double hi[3];
+            for (int sw0 = 0; sw0 < ne; sw0 += NET2_GRP) {
+                AzDesc d[NET2_GRP];
+                int g[NET2_GRP];
+                double2 lo[NET2_GRP];
+                double hi[NET2_GRP];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < NET2_GRP; ++j) {
                     const int sw = min(sw0 + j, ne - 1);
                     d[j] = w_ad[sw];
                     g[j] = __double2int_rd(mul(sub(az, d[j].az_first), d[j].az_inv_step)) + 1;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < NET2_GRP; ++j) {
                     const int sw = sw0 + j;
                     if (sw >= ne) break;
                     AzEntry e;
@@ -578,16 +581,16 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                 // A guess the band does not confirm takes the reference chain (net2_cr_exact).
                 const double2 ends = __ldg(reinterpret_cast<const double2*>(&fs_t[0].tg_first));   // {tg_first, tg_gt_last}
 #pragma unroll 1
-                for (int ie0 = 0; ie0 < ne; ie0 += 3) {
-                    double r2v[3];
-                    float rfv[3];
-                    int giv[3];
-                    bool okv[3];
-                    double2 tgv[3];
-                    float4 qv[3];
-                    AzEntry ev[3];
+                for (int ie0 = 0; ie0 < ne; ie0 += NET2_GRP) {
+                    double r2v[NET2_GRP];
+                    float rfv[NET2_GRP];
+                    int giv[NET2_GRP];
+                    bool okv[NET2_GRP];
+                    double2 tgv[NET2_GRP];
+                    float4 qv[NET2_GRP];
+                    AzEntry ev[NET2_GRP];
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
+                    for (int j = 0; j < NET2_GRP; ++j) {
                         const int ie = min(ie0 + j, ne - 1);
                         const double denom = sub(cphi, mul(sphi, w_tan[ie]));
                         const double g = div(R.a, denom);
@@ -604,7 +607,7 @@ __global__ void __launch_bounds__(kNet2Threads, NET2_MINB) net_tile_kernel(const
                         qv[j] = ldg_vol(val0 + (ev[j].row + (unsigned)giv[j]));
                     }
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
+                    for (int j = 0; j < NET2_GRP; ++j) {
                         if (!okv[j]) continue;
                         float v;
                         if ((r2v[j] >= tgv[j].x) & (r2v[j] < tgv[j].y)) {
