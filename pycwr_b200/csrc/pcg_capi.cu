@@ -520,28 +520,30 @@ int launch_fast_flags(const R2Args& args, bool uni, bool lazy, dim3 grid, dim3 b
                 : launch_fast_one<NF, EMIT, false, false>(args, grid, block, smem, st);
 }
 
-// kernel v8 (pcg_r3.cuh): eager azimuth tables only (<= 16 sweeps)
-template <int NF, bool EMIT, bool UNI, bool MERGE, bool CT>
+// kernel v8 (pcg_r3.cuh): a [sweep] azimuth table per column up to 16 sweeps, the current pair's brackets in
+// registers beyond (LAZY; threshold rows in global memory)
+template <int NF, bool EMIT, bool UNI, bool MERGE, bool CT, bool LAZY>
 int launch_r3_one(const R3Args& args, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024)
-        CUDA_TRY(cudaFuncSetAttribute(cappi3d_r3_kernel<NF, EMIT, UNI, MERGE, CT>,
+        CUDA_TRY(cudaFuncSetAttribute(cappi3d_r3_kernel<NF, EMIT, UNI, MERGE, CT, LAZY>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cappi3d_r3_kernel<NF, EMIT, UNI, MERGE, CT><<<grid, block, smem, st>>>(args);
+    cappi3d_r3_kernel<NF, EMIT, UNI, MERGE, CT, LAZY><<<grid, block, smem, st>>>(args);
     return PCG_OK;
 }
 
-template <int NF, bool EMIT, bool CT>
+template <int NF, bool EMIT, bool CT, bool LAZY>
 int launch_r3_flags(const R3Args& args, bool uni, bool merge, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
-    if (uni) return merge ? launch_r3_one<NF, EMIT, true, true, CT>(args, grid, block, smem, st)
-                          : launch_r3_one<NF, EMIT, true, false, CT>(args, grid, block, smem, st);
-    return merge ? launch_r3_one<NF, EMIT, false, true, CT>(args, grid, block, smem, st)
-                 : launch_r3_one<NF, EMIT, false, false, CT>(args, grid, block, smem, st);
+    if (uni) return merge ? launch_r3_one<NF, EMIT, true, true, CT, LAZY>(args, grid, block, smem, st)
+                          : launch_r3_one<NF, EMIT, true, false, CT, LAZY>(args, grid, block, smem, st);
+    return merge ? launch_r3_one<NF, EMIT, false, true, CT, LAZY>(args, grid, block, smem, st)
+                 : launch_r3_one<NF, EMIT, false, false, CT, LAZY>(args, grid, block, smem, st);
 }
 
 template <int NF, bool EMIT>
 int launch_r3_ct(const R3Args& args, bool ct, bool uni, bool merge, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
-    return ct ? launch_r3_flags<NF, EMIT, true>(args, uni, merge, grid, block, smem, st)
-              : launch_r3_flags<NF, EMIT, false>(args, uni, merge, grid, block, smem, st);
+    if (args.a.lazy_az) return launch_r3_flags<NF, EMIT, false, true>(args, uni, merge, grid, block, smem, st);
+    return ct ? launch_r3_flags<NF, EMIT, true, false>(args, uni, merge, grid, block, smem, st)
+              : launch_r3_flags<NF, EMIT, false, false>(args, uni, merge, grid, block, smem, st);
 }
 
 template <bool EMIT>
@@ -565,6 +567,15 @@ int launch_r3_nf(const R3Args& args, bool ct, int nf, bool uni, dim3 grid, dim3 
 bool use_r3_kernel() {
     static const int choice = [] {
         const char* e = getenv("PCG_KERNEL");
+        return (e && strcmp(e, "r2") == 0) ? 0 : 1;
+    }();
+    return choice != 0;
+}
+
+// PCG_LAZY_KERNEL=r2 keeps the v7 kernel for volumes with more than 16 sweeps (A/B runs)
+bool use_r3_lazy_kernel() {
+    static const int choice = [] {
+        const char* e = getenv("PCG_LAZY_KERNEL");
         return (e && strcmp(e, "r2") == 0) ? 0 : 1;
     }();
     return choice != 0;
@@ -671,7 +682,7 @@ int enqueue_cappi_fast(const pcg_volume* vol, double h, double Re, const double*
     const size_t fixed = (size_t)vol->ne * (sizeof(SweepDesc) + sizeof(FastSweep)) + (size_t)(vol->ne - 1) * sizeof(PairDesc);
     // azimuth brackets: a [sweep] table per column up to 16 sweeps, on demand (2-entry cache) beyond
     RA.lazy_az = vol->ne > 16 ? 1 : 0;
-    const bool r3 = !RA.lazy_az && use_r3_kernel();
+    const bool r3 = use_r3_kernel() && (!RA.lazy_az || use_r3_lazy_kernel());
     const size_t per_thread = RA.lazy_az ? 2 * (sizeof(AzEntry) + sizeof(int) + (d_idx ? sizeof(int) : 0))
                                          : (size_t)vol->ne * (sizeof(AzEntry) + (d_idx ? sizeof(int) : 0));
     int threads = 256;

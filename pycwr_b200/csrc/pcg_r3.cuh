@@ -57,9 +57,13 @@ struct SlowArgs {
     double a2, twoa, guard, inv_twoa;
     float fill32;
     int blind;                    // bit 0 nearest_gate, 1 lowest_sweep, 2 highest_sweep
+    // LAZY kernels: my_az / my_iaz are the tagged 2-entry caches of pcg_fast.cuh (az_entry<true>)
+    int* my_tag;
+    const double2* azt;
+    double az;
 };
 
-template <int NF, bool EMIT>
+template <int NF, bool EMIT, bool LAZY = false>
 __device__ __noinline__ void r3_slow_voxel(const SlowArgs* a, const LevelConst* lc, double cphi, int* k6, float* res,
                                            VoxelInfo* vi) {
     ColumnCtx c;
@@ -67,11 +71,11 @@ __device__ __noinline__ void r3_slow_voxel(const SlowArgs* a, const LevelConst* 
     c.ne = a->ne; c.rg_t = a->rg_t; c.a2 = a->a2; c.twoa = a->twoa; c.guard = a->guard; c.inv_twoa = a->inv_twoa;
     c.fill32 = a->fill32;
     c.nearest_gate = (a->blind & 1) != 0; c.lowest_sweep = (a->blind & 2) != 0; c.highest_sweep = (a->blind & 4) != 0;
-    c.my_tag = nullptr; c.azt = nullptr; c.az = 0.0;
+    c.my_tag = LAZY ? a->my_tag : nullptr; c.azt = LAZY ? a->azt : nullptr; c.az = LAZY ? a->az : 0.0;
     float tmp[NF];
     int k = *k6;
     VoxelInfo v;
-    fast_voxel<NF, EMIT, false>(c, a->val, *lc, cphi, k, tmp, v);
+    fast_voxel<NF, EMIT, LAZY>(c, a->val, *lc, cphi, k, tmp, v);
     *k6 = k;
     *vi = v;
 #pragma unroll
@@ -163,8 +167,43 @@ __device__ __forceinline__ float lds_f(unsigned addr) {
     return v;
 }
 
-template <int NF, bool EMIT, bool UNI, bool MERGE, bool CT>
-__global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_constant__ R3Args Q) {
+// One column's azimuth bracket of one sweep (RadarGridC.pyx:282-289): interior guesses verified in line against the
+// two entries they bracket (entries g-1 and g must both exist: 1 <= g <= naz-1; jittered tables put the arithmetic
+// guess off by one for a few lanes of almost every warp: one repair step in line), anything else through the
+// general routine.
+__device__ __forceinline__ void r3_az_bracket(const AzDesc& d, const SweepDesc* sw_desc, const double2* __restrict__ azt,
+                                              double az, AzEntry& e, int& rec) {
+    int g = __double2int_rd(mul(sub(az, d.az_first), d.az_inv_step)) + 1;
+    bool done = false;
+    if (g >= 1 && g < d.naz) {
+        const double2* Tt = azt + d.az_off + (unsigned)(g - 1);
+        double2 lo = __ldg(Tt);
+        double hi = __ldg(&Tt[1].x);
+        if (az < lo.x) {
+            if (g >= 2) { --g; hi = lo.x; lo = __ldg(Tt - 1); }
+        } else if (!(az < hi)) {
+            if (g + 1 < d.naz) { ++g; lo = __ldg(Tt + 1); hi = __ldg(&Tt[2].x); }
+        }
+        if (!(az < lo.x) && (az < hi)) {
+            e.row = d.val_off + (unsigned)(g - 1) * (unsigned)d.ng;
+            e.w = (float)sub(az, lo.x) * (float)lo.y;
+            rec = g;
+            done = true;
+        }
+    }
+    if (!done) az_bracket_general(sw_desc, azt, az, &e, &rec);
+}
+
+// LAZY (volumes with more than 16 sweeps, e.g. the 64-sweep phased-array config C5): a [sweep] azimuth table per
+// column would take the block's shared memory (64 x 256 x 8 bytes) and most of it would never be read — a column
+// crosses a fraction of the sweeps, climbing one pair at a time.  The brackets of the CURRENT pair live in registers
+// instead: when the column moves up one pair the upper entry becomes the lower one and one new bracket is computed;
+// the tagged 2-entry shared-memory cache of pcg_fast.cuh only serves the deferred reference chain.
+#ifndef R3_LAZY_MINB
+#define R3_LAZY_MINB 4
+#endif
+template <int NF, bool EMIT, bool UNI, bool MERGE, bool CT, bool LAZY = false>
+__global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3_kernel(const __grid_constant__ R3Args Q) {
     const R2Args& P = Q.a;
     const FastArgs& p = P.base;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -174,8 +213,10 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
     PairDesc* s_pr = reinterpret_cast<PairDesc*>(s_sw + ne);
     FastSweep* s_fs = reinterpret_cast<FastSweep*>(s_pr + (ne - 1));
     AzDesc* s_ad = reinterpret_cast<AzDesc*>(s_fs + ne);
-    AzEntry* s_az = reinterpret_cast<AzEntry*>(s_ad + ne);                 // [sweep][thread]
-    int* s_iaz = reinterpret_cast<int*>(s_az + (size_t)ne * T);            // EMIT only, [sweep][thread]
+    const int nslot = LAZY ? 2 : ne;
+    AzEntry* s_az = reinterpret_cast<AzEntry*>(s_ad + ne);                 // [sweep][thread] (LAZY: [slot][thread])
+    int* s_tag = reinterpret_cast<int*>(s_az + (size_t)nslot * T);         // LAZY only, [slot][thread]
+    int* s_iaz = s_tag + (LAZY ? (size_t)nslot * T : 0);                   // EMIT only, [sweep or slot][thread]
     stage_sweeps(s_sw, p.vol.sweeps, ne);
     stage_pairs(s_pr, p.pairs, ne - 1, p.twoa);
     {
@@ -216,41 +257,26 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
     const double cphi = cos_small(div(s, p.Re));
     AzEntry* my_az = s_az + threadIdx.x;
     int* my_iaz = s_iaz + threadIdx.x;
-    {
-        // the column's azimuth bracket of every sweep (RadarGridC.pyx:282-289): interior guesses verified in
-        // line against the two entries they bracket, anything else through the general routine
-        const double az = azimuth_from_xy(x, y);
-        const double2* __restrict__ azt = P.r2.az_t;
+    int* my_tag = s_tag + threadIdx.x;
+    const double az = azimuth_from_xy(x, y);
+    const double2* __restrict__ azt = P.r2.az_t;
+    if (LAZY) {
+        my_tag[0] = -1; my_tag[T] = -1;
+    } else {
+        // the column's azimuth bracket of every sweep
 #pragma unroll 1
         for (int sw = 0; sw < ne; ++sw) {
-            const AzDesc d = s_ad[sw];
-            int g = __double2int_rd(mul(sub(az, d.az_first), d.az_inv_step)) + 1;
             AzEntry e;
             int rec;
-            bool done = false;
-            // interior brackets in line: entries g-1 and g must both exist (1 <= g <= naz-1).  Jittered tables
-            // put the arithmetic guess off by one for a few lanes of almost every warp: one repair step in line.
-            if (g >= 1 && g < d.naz) {
-                const double2* Tt = azt + d.az_off + (unsigned)(g - 1);
-                double2 lo = __ldg(Tt);
-                double hi = __ldg(&Tt[1].x);
-                if (az < lo.x) {
-                    if (g >= 2) { --g; hi = lo.x; lo = __ldg(Tt - 1); }
-                } else if (!(az < hi)) {
-                    if (g + 1 < d.naz) { ++g; lo = __ldg(Tt + 1); hi = __ldg(&Tt[2].x); }
-                }
-                if (!(az < lo.x) && (az < hi)) {
-                    e.row = d.val_off + (unsigned)(g - 1) * (unsigned)d.ng;
-                    e.w = (float)sub(az, lo.x) * (float)lo.y;
-                    rec = g;
-                    done = true;
-                }
-            }
-            if (!done) az_bracket_general(s_sw + sw, azt, az, &e, &rec);
+            r3_az_bracket(s_ad[sw], s_sw + sw, azt, az, e, rec);
             my_az[(size_t)sw * T] = e;
             if (EMIT) my_iaz[(size_t)sw * T] = rec;
         }
     }
+    // LAZY: the brackets of sweeps az_k and min(az_k + 1, ne - 1), az_k = -2: none yet
+    AzEntry za, zb;
+    int rec_a = -1, rec_b = -1, az_k = -2;
+    za.row = 0u; za.w = 0.f; zb = za;
 
     float fill32 = p.fill32, inv2a = P.r2.inv2a;
     float u_inv_step = P.r2.u_inv_step, u_c0 = P.r2.u_c0, u_step = P.r2.u_step, u_r_first = P.r2.u_r_first;
@@ -296,13 +322,13 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
     // loop then contains no call, so its state stays in registers (kMaxLevelsPerLaunch <= 64)
     unsigned long long slow_mask = 0ull;
 #ifdef R3_SPEC
-    constexpr bool SPEC = UNI;      // uniform-table volumes: every speculative address below is valid
+    constexpr bool SPEC = UNI && !LAZY;   // uniform-table volumes: every speculative address below is valid
 #else
     constexpr bool SPEC = false;    // measured on B200, config C3: 0.386 ms with, 0.344 ms without
 #endif
 
 #ifndef R3_NOUNROLL2
-#pragma unroll 2        // (0.3334 -> 0.3319 ms at config C3)
+#pragma unroll(LAZY ? 1 : 2)        // (0.3334 -> 0.3319 ms at config C3)
 #else
 #pragma unroll 1
 #endif
@@ -374,6 +400,22 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
             for (int f = 0; f < NF; ++f) res[f] = fill32;
         } else {
             float rj, idr;
+            if (LAZY && lower != az_k) {
+                // the column moved to another sweep pair: one step up keeps the upper bracket as the new lower one
+                const int top = min(lower + 1, (int)pair_top);
+                int sw = lower;
+                if (lower == az_k + 1) { za = zb; rec_a = rec_b; sw = top; }
+                az_k = lower;
+#pragma unroll 1
+                for (;;) {
+                    AzEntry e;
+                    int rec;
+                    r3_az_bracket(s_ad[sw], s_sw + sw, azt, az, e, rec);
+                    if (sw == lower) { za = e; rec_a = rec; }
+                    if (sw == top) { zb = e; rec_b = rec; break; }
+                    sw = top;
+                }
+            }
             if (SPEC) {
                 if (!((r2 >= tg.x) & (r2 < tg.y))) { slow_mask |= 1ull << iz; continue; }
                 rj = fmaf((float)(gi - 1), u_step, u_r_first); idr = u_inv_step;
@@ -398,8 +440,8 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
                     // uniform tables: the guessed gate's quads are asked for together with its band, before the band
                     // is checked (the guess is right for all but ~1e-4 of the voxels; every address is valid): one
                     // dependent memory round trip less per level, 0.342 -> 0.333 ms at config C3
-                    ea = lds_az(az_addr + (unsigned)lower * az_pitch);
-                    if (pair) eb = lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
+                    ea = LAZY ? za : lds_az(az_addr + (unsigned)lower * az_pitch);
+                    if (pair) eb = LAZY ? zb : lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
 #pragma unroll
                     for (int fi = 0; fi < NF; ++fi) {
                         const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
@@ -419,8 +461,8 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
                 if (!UNI)
 #endif
                 {
-                    ea = lds_az(az_addr + (unsigned)lower * az_pitch);
-                    if (pair) eb = lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
+                    ea = LAZY ? za : lds_az(az_addr + (unsigned)lower * az_pitch);
+                    if (pair) eb = LAZY ? zb : lds_az(az_addr + (unsigned)(lower + 1) * az_pitch);
 #pragma unroll
                     for (int fi = 0; fi < NF; ++fi) {
                         const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
@@ -466,10 +508,10 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
                 }
             }
             if (EMIT) {
-                const int ra = my_iaz[(size_t)lower * T];
+                const int ra = LAZY ? rec_a : my_iaz[(size_t)lower * T];
                 r_ir0 = gi; r_iaz0 = ra & 0x3fffffff; r_fl0 = (ra >> 30) & 1;
                 if (pair) {
-                    const int rb2 = my_iaz[(size_t)(lower + 1) * T];
+                    const int rb2 = LAZY ? rec_b : my_iaz[(size_t)(lower + 1) * T];
                     r_ir1 = gi; r_iaz1 = rb2 & 0x3fffffff; r_fl1 = (rb2 >> 30) & 1;
                 }
             }
@@ -507,13 +549,14 @@ __global__ void __launch_bounds__(256, R3_MINB) cappi3d_r3_kernel(const __grid_c
         sa.rg_t = reinterpret_cast<const double2*>(p.vol.rng); sa.val = p.vol.val; sa.az_stride = T; sa.ne = ne;
         sa.a2 = p.a2; sa.twoa = p.twoa; sa.guard = p.guard; sa.inv_twoa = p.inv_twoa; sa.fill32 = fill32;
         sa.blind = (p.nearest_gate != 0 ? 1 : 0) | (lowest_sweep ? 2 : 0) | (highest_sweep ? 4 : 0);
+        sa.my_tag = LAZY ? my_tag : nullptr; sa.azt = azt; sa.az = az;
 #pragma unroll 1
         while (slow_mask) {
             const int iz = __ffsll((long long)slow_mask) - 1;
             slow_mask &= slow_mask - 1;
             VoxelInfo vi;
             float tmp[NF];
-            r3_slow_voxel<NF, EMIT>(&sa, &p.levels[iz], cphi, &k6, tmp, &vi);
+            r3_slow_voxel<NF, EMIT, LAZY>(&sa, &p.levels[iz], cphi, &k6, tmp, &vi);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 double* dst = p.out + (size_t)f * (size_t)p.field_stride + (size_t)iz * (size_t)ncol + (size_t)col;

@@ -276,13 +276,9 @@ def test_non_finite_grid_coordinates():
     assert_parity(got, want, what="non-finite grid")
 
 
-@pytest.mark.parametrize("seed", range(24))
-def test_randomised_geometry_parity(seed):
-    """Random radar heights, earth radii, elevation sets (dense and sparse, up to 60 degrees), gate
-    spacings (regular and irregular, per-sweep lengths), level sets and blind modes: interpolation
-    indices and masks must stay bit-exact over the whole parameter space of the r2 thresholds."""
+def _fuzz_geometry(seed, ne_lo, ne_hi, tag):
     rng = np.random.default_rng(1000 + seed)
-    ne = int(rng.integers(2, 14))
+    ne = int(rng.integers(ne_lo, ne_hi))
     top = rng.choice([6.0, 20.0, 60.0])
     fe = np.sort(rng.uniform(rng.choice([-0.5, 0.2, 0.5]), top, ne))
     fe = fe + np.arange(ne) * 1e-3                       # strictly increasing
@@ -312,10 +308,63 @@ def test_randomised_geometry_parity(seed):
     for blind in ("mask", "hybrid", "nearest_valid"):
         got, gi = G.get_CAPPI_3d(az, rg, fe, vv, h, gx, gy, lv, FILL, Re, blind, return_index=True)
         want, wi = O.get_CAPPI_3d(az, rg, fe, vv, h, gx, gy, lv, FILL, Re, blind, return_index=True)
-        assert_parity(got, want, gi, wi, "fuzz %d %s (ne=%d h=%g Re=%g step=%g regular=%s shared=%s)" % (
-            seed, blind, ne, h, Re, step, regular, shared))
+        assert_parity(got, want, gi, wi, "%s %d %s (ne=%d h=%g Re=%g step=%g regular=%s shared=%s)" % (
+            tag, seed, blind, ne, h, Re, step, regular, shared))
+        # the production instantiation (no index records) returns the same values bit for bit
+        plain = G.get_CAPPI_3d(az, rg, fe, vv, h, gx, gy, lv, FILL, Re, blind)
+        assert np.array_equal(plain, got), "%s %d %s: values differ between the kernels with and without index records" % (
+            tag, seed, blind)
     assert_parity(G.get_CR_xy(az, rg, fe, vv, h, gx, gy, FILL, Re), O.get_CR_xy(az, rg, fe, vv, h, gx, gy, FILL, Re),
-                  what="fuzz CR %d" % seed)
+                  what="%s CR %d" % (tag, seed))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_geometry_parity(seed):
+    """Random radar heights, earth radii, elevation sets (dense and sparse, up to 60 degrees), gate
+    spacings (regular and irregular, per-sweep lengths), level sets and blind modes: interpolation
+    indices and masks must stay bit-exact over the whole parameter space of the r2 thresholds."""
+    _fuzz_geometry(seed, 2, 14, "fuzz")
+
+
+@pytest.mark.parametrize("seed", range(100, 110))
+def test_many_sweep_geometry_parity(seed):
+    """The same fuzz over volumes with 17 .. 47 sweeps (phased-array scans, BASELINE config C5): these take the kernel
+    that keeps the azimuth brackets of the column's current sweep pair in registers instead of a [sweep] table per
+    column (pcg_r3.cuh, LAZY) — regular and irregular range tables, shared and per-sweep lengths, every blind mode."""
+    _fuzz_geometry(seed, 17, 48, "many-sweep")
+
+
+def _many_sweep_volume(rng, ne, naz, ng, step):
+    fe = np.linspace(0.9, 0.9 * ne, ne)
+    rg = (np.arange(ng) + 1.0) * step
+    az = [synth.azimuth_table(rng, naz) for _ in range(ne)]
+    return az, [rg] * ne, fe
+
+
+def test_many_sweep_mosaic_and_multifield():
+    """Volumes with more than 16 sweeps through the mosaic merge (fill-aware max over radars, RadarGridC.pyx:568-592)
+    and as a multi-field volume sharing one set of indices: the LAZY instantiations of cappi3d_r3_kernel with MERGE
+    and with NF = 3."""
+    rng = np.random.default_rng(77)
+    vols, vals = [], []
+    for ne in (24, 33):
+        az, rg, fe = _many_sweep_volume(rng, ne, 96, 180, 150.0)
+        vols.append((az, rg, fe))
+        vals.append([synth.stress_moment(rng, 96, 180, -5.0, 70.0) for _ in range(ne)])
+    gx, gy = np.meshgrid(np.linspace(-26e3, 26e3, 41), np.linspace(-26e3, 26e3, 37), indexing="ij")
+    lv = np.arange(1, 25) * 500.0
+    rx, ry, rh = np.array([0.0, 9000.0]), np.array([0.0, -4000.0]), np.array([120.0, 640.0])
+    args = ([v[0] for v in vols], [v[1] for v in vols], [v[2] for v in vols], vals, rx, ry, rh, gx, gy, lv, FILL)
+    assert_parity(G.get_mosaic_CAPPI_3d(*args), O.get_mosaic_CAPPI_3d(*args), what="many-sweep mosaic")
+    az, rg, fe = vols[0]
+    fields = [vals[0], [synth.stress_moment(rng, 96, 180, -2.0, 5.0) for _ in range(fe.size)],
+              [synth.stress_moment(rng, 96, 180, -27.0, 27.0) for _ in range(fe.size)]]
+    dv = DeviceVolume(az, rg, fe, fields, value_dtype=G.VALUE_DTYPE)
+    out = G.get_CAPPI_3d(None, None, None, dv, 120.0, gx, gy, lv, FILL, None, "hybrid")
+    for k, f in enumerate(fields):
+        assert_parity(out[k], O.get_CAPPI_3d(az, rg, fe, f, 120.0, gx, gy, lv, FILL, None, "hybrid"),
+                      what="many-sweep multi-field %d" % k)
+    dv.close()
 
 
 def test_full_size_c3_properties():
