@@ -149,6 +149,21 @@ __device__ __forceinline__ double2 ldg_vol(const double2* p) {
 #endif
 }
 
+// LAZY kernels on uniform-table volumes: the quads the NEXT level will gather (same sweep pair, that level's gate
+// guess) are requested while this level's are in flight.  R3_LAZY_PF: 0 off, 1 into L1, 2 into L2.
+#ifndef R3_LAZY_PF
+#define R3_LAZY_PF 0
+#endif
+__device__ __forceinline__ void r3_prefetch(const void* p) {
+#if R3_LAZY_PF == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif R3_LAZY_PF == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // shared-memory reads of the level loop through 32-bit shared addresses held in registers (the compiler would
 // otherwise rebuild the carve-up offsets from `ne` at every use)
 __device__ __forceinline__ AzEntry lds_az(unsigned addr) {
@@ -386,6 +401,11 @@ __global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3
                 break;
             }
             if (slow) break;
+            // the band test that ended the walk IS the confirmation of pair k ({t_lo[k], t_hi[k+1]}); its
+            // {rho2, rho, b1} is the second half of sweep k's own record.  Rows in global memory only: with the rows
+            // in the constant bank the second look is two broadcasts, and taking it keeps the pair record's loads
+            // inside the pair branch (config C3: 0.332 ms with the second look, 0.339 ms without)
+            if (!SPEC && !CT) { lk = row16(ls_off + (unsigned)(k + 1) * 32u + 16u); break; }
         }
         if (slow) { slow_mask |= 1ull << iz; continue; }
         const bool pair = (unsigned)k < pair_top;
@@ -448,9 +468,33 @@ __global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3
                         qa4[fi] = ldg_vol(v + (ea.row + (unsigned)gi));
                         if (pair) qb4[fi] = ldg_vol(v + (eb.row + (unsigned)gi));
                     }
+                    if (LAZY && R3_LAZY_PF && iz + 1 < p.nz) {
+                        const float r2n = (float)sub(p.levels[iz + 1].a2g2, mul(p.levels[iz + 1].twoag, cphi));
+                        const float rn = r2n * rsqrt_approx(r2n);
+                        const unsigned gn = (unsigned)min(max(__float2int_rd(fmaf(rn, u_inv_step, u_c0)), 1), u_ngm1);
+#pragma unroll
+                        for (int fi = 0; fi < NF; ++fi) {
+                            const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
+                            r3_prefetch(v + (za.row + gn));
+                            r3_prefetch(v + (zb.row + gn));
+                        }
+                    }
                 }
 #endif
-                if (!(usable & (r2 >= tg.x) & (r2 < tg.y))) { slow_mask |= 1ull << iz; continue; }
+                if (!(usable & (r2 >= tg.x) & (r2 < tg.y))) {
+                    // beyond the last gate of the (shared) range table: every sample is missing, and so is the voxel
+                    // (RadarGridC.pyx:275-276,246-251).  Index records of such voxels come from the reference chain.
+                    if (!EMIT && usable && r2 >= s_fs[lower].tg_gt_last) {
+                        if (!MERGE) {
+#pragma unroll
+                            for (int f2 = 0; f2 < NF; ++f2)
+                                reinterpret_cast<double*>(out_b)[(size_t)f2 * (size_t)p.field_stride] = (double)fill32;
+                        }
+                    } else {
+                        slow_mask |= 1ull << iz;
+                    }
+                    continue;
+                }
                 if (UNI) {
                     rj = fmaf((float)(gi - 1), u_step, u_r_first); idr = u_inv_step;
                 } else {
