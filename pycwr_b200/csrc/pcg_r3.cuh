@@ -43,6 +43,14 @@ __device__ __noinline__ void az_bracket_general(const SweepDesc* d, const double
     *rec = rr;
 }
 
+// the same, returned in registers {row, w, rec} (nothing of the caller has its address taken)
+__device__ __noinline__ int4 az_bracket_general_v(const SweepDesc* d, const double2* azt, double az) {
+    AzEntry ee;
+    int rr;
+    az_bracket_one(*d, azt, az, ee, rr);
+    return make_int4((int)ee.row, __float_as_int(ee.w), rr, 0);
+}
+
 // the reference chain for one voxel, everything by value (rare: guard bands, flagged levels, ragged or degenerate
 // tables, range gating / clamping, wrong gate guesses)
 struct SlowArgs {
@@ -149,21 +157,6 @@ __device__ __forceinline__ double2 ldg_vol(const double2* p) {
 #endif
 }
 
-// LAZY kernels on uniform-table volumes: the quads the NEXT level will gather (same sweep pair, that level's gate
-// guess) are requested while this level's are in flight.  R3_LAZY_PF: 0 off, 1 into L1, 2 into L2.
-#ifndef R3_LAZY_PF
-#define R3_LAZY_PF 0
-#endif
-__device__ __forceinline__ void r3_prefetch(const void* p) {
-#if R3_LAZY_PF == 1
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#elif R3_LAZY_PF == 2
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-
 // shared-memory reads of the level loop through 32-bit shared addresses held in registers (the compiler would
 // otherwise rebuild the carve-up offsets from `ne` at every use)
 __device__ __forceinline__ AzEntry lds_az(unsigned addr) {
@@ -206,7 +199,10 @@ __device__ __forceinline__ void r3_az_bracket(const AzDesc& d, const SweepDesc* 
             done = true;
         }
     }
-    if (!done) az_bracket_general(sw_desc, azt, az, &e, &rec);
+    if (!done) {
+        const int4 r = az_bracket_general_v(sw_desc, azt, az);
+        e.row = (unsigned)r.x; e.w = __int_as_float(r.y); rec = r.z;
+    }
 }
 
 // LAZY (volumes with more than 16 sweeps, e.g. the 64-sweep phased-array config C5): a [sweep] azimuth table per
@@ -215,7 +211,7 @@ __device__ __forceinline__ void r3_az_bracket(const AzDesc& d, const SweepDesc* 
 // instead: when the column moves up one pair the upper entry becomes the lower one and one new bracket is computed;
 // the tagged 2-entry shared-memory cache of pcg_fast.cuh only serves the deferred reference chain.
 #ifndef R3_LAZY_MINB
-#define R3_LAZY_MINB 4
+#define R3_LAZY_MINB 5
 #endif
 template <int NF, bool EMIT, bool UNI, bool MERGE, bool CT, bool LAZY = false>
 __global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3_kernel(const __grid_constant__ R3Args Q) {
@@ -308,12 +304,14 @@ __global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3
     unsigned pair_top = (unsigned)(ne - 1);                // k < pair_top (unsigned): between two sweeps
     unsigned az_addr = (unsigned)__cvta_generic_to_shared(my_az), az_pitch = T * (unsigned)sizeof(AzEntry);
     unsigned fs_addr = (unsigned)__cvta_generic_to_shared(&s_fs[0].q1);
+    unsigned ad_addr = (unsigned)__cvta_generic_to_shared(s_ad);
     {
         const int pin_zero = (int)((unsigned long long)clock64() >> 63);     // 0, unknown to the compiler
         (void)pin_zero;
         R3_PIN(fill32); R3_PIN(inv2a); R3_PIN(g_t); R3_PIN(val0);
         R3_PIN(k_first); R3_PIN(k_span); R3_PIN(row_bytes); R3_PIN(ls_off); R3_PIN(pair_top);
         R3_PIN(az_addr); R3_PIN(az_pitch); R3_PIN(fs_addr);
+        if (LAZY) R3_PIN(ad_addr);
         if (UNI) { R3_PIN(u_inv_step); R3_PIN(u_c0); R3_PIN(u_step); R3_PIN(u_r_first); R3_PIN(u_ngm1); R3_PIN(u_rng_off); }
     }
     const char* lrow = reinterpret_cast<const char*>(P.r2.lp);   // this level's row (block-uniform), global copy
@@ -369,43 +367,68 @@ __global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3
         ea.row = 0u; ea.w = 0.f; eb = ea;
 #pragma unroll
         for (int fi = 0; fi < NF; ++fi) { qa4[fi] = make_float4(0.f, 0.f, 0.f, 0.f); qb4[fi] = qa4[fi]; }
-#pragma unroll 1
-        for (;;) {
+        if (!SPEC && !CT) {
+            // rows in global memory: ONE block with a single exit and a warp barrier behind it, so that the lanes that
+            // walked and the lanes whose pair was confirmed at once run the rest of the level together (the nested
+            // loops below left them apart until the end of the level: 1.39 executions of the sampling code per
+            // voxel-warp at config C5).  The band
+            // test that ends the walk IS the confirmation of pair k ({t_lo[k], t_hi[k+1]}); its {rho2, rho, b1} is the
+            // second half of sweep k's own record.
             const unsigned pk = (unsigned)(k + 1) * 32u;
             const double2 cf = as_d2(row16(pk));
-            lk = row16(pk + 16u);                                 // {rho2, rho, b1} of pair k: used if k is confirmed
-            if (SPEC) {
-                const int lo_s = max(k, 0), hi_s = min(lo_s + 1, ne - 1);
-                gi = min(max(__float2int_rd(fmaf(rf, u_inv_step, u_c0)), 1), u_ngm1);
-                tg = ldg_vol(g_t + (u_rng_off + (unsigned)(gi - 1)));
-                ea = lds_az(az_addr + (unsigned)lo_s * az_pitch);
-                eb = lds_az(az_addr + (unsigned)hi_s * az_pitch);
-#pragma unroll
-                for (int fi = 0; fi < NF; ++fi) {
-                    const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
-                    qa4[fi] = ldg_vol(v + (ea.row + (unsigned)gi));
-                    qb4[fi] = ldg_vol(v + (eb.row + (unsigned)gi));
+            lk = row16(pk + 16u);
+            if (!((r2 < cf.x) & (r2 > cf.y))) {
+#pragma unroll 1
+                for (;;) {
+                    const unsigned ro = ls_off + (unsigned)(k + 1) * 32u;
+                    const double2 cur = as_d2(row16(ro));
+                    const double2 nxt = as_d2(row16(ro + 32u));
+                    if ((r2 < cur.x) & (r2 > nxt.y)) { lk = row16(ro + 16u); break; }
+                    if (r2 > cur.y) { --k; continue; }
+                    if (r2 < nxt.x) { ++k; continue; }
+                    slow = true;
+                    break;
                 }
             }
-            if ((r2 < cf.x) & (r2 > cf.y)) break;
-            // the column left its sweep pair: walk the per-sweep bands (pcg_r2.cuh)
+            // (ptxas puts no convergence barrier behind this block on its own; every lane that has not left the
+            // kernel runs every level, so the full mask is exact)
+            __syncwarp();
+        } else {
 #pragma unroll 1
             for (;;) {
-                const unsigned ro = ls_off + (unsigned)(k + 1) * 32u;
-                const double2 cur = as_d2(row16(ro));
-                const double2 nxt = as_d2(row16(ro + 32u));
-                if ((r2 < cur.x) & (r2 > nxt.y)) break;
-                if (r2 > cur.y) { --k; continue; }
-                if (r2 < nxt.x) { ++k; continue; }
-                slow = true;
-                break;
+                const unsigned pk = (unsigned)(k + 1) * 32u;
+                const double2 cf = as_d2(row16(pk));
+                lk = row16(pk + 16u);                                 // {rho2, rho, b1} of pair k: used if k is confirmed
+                if (SPEC) {
+                    const int lo_s = max(k, 0), hi_s = min(lo_s + 1, ne - 1);
+                    gi = min(max(__float2int_rd(fmaf(rf, u_inv_step, u_c0)), 1), u_ngm1);
+                    tg = ldg_vol(g_t + (u_rng_off + (unsigned)(gi - 1)));
+                    ea = lds_az(az_addr + (unsigned)lo_s * az_pitch);
+                    eb = lds_az(az_addr + (unsigned)hi_s * az_pitch);
+#pragma unroll
+                    for (int fi = 0; fi < NF; ++fi) {
+                        const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
+                        qa4[fi] = ldg_vol(v + (ea.row + (unsigned)gi));
+                        qb4[fi] = ldg_vol(v + (eb.row + (unsigned)gi));
+                    }
+                }
+                if ((r2 < cf.x) & (r2 > cf.y)) break;
+                // the column left its sweep pair: walk the per-sweep bands (pcg_r2.cuh)
+#pragma unroll 1
+                for (;;) {
+                    const unsigned ro = ls_off + (unsigned)(k + 1) * 32u;
+                    const double2 cur = as_d2(row16(ro));
+                    const double2 nxt = as_d2(row16(ro + 32u));
+                    if ((r2 < cur.x) & (r2 > nxt.y)) break;
+                    if (r2 > cur.y) { --k; continue; }
+                    if (r2 < nxt.x) { ++k; continue; }
+                    slow = true;
+                    break;
+                }
+                if (slow) break;
+                // (rows in the constant bank: the second look at the pair entry is two broadcasts and keeps the pair
+                // record's loads inside the pair branch — config C3: 0.332 ms with it, 0.339 ms without)
             }
-            if (slow) break;
-            // the band test that ended the walk IS the confirmation of pair k ({t_lo[k], t_hi[k+1]}); its
-            // {rho2, rho, b1} is the second half of sweep k's own record.  Rows in global memory only: with the rows
-            // in the constant bank the second look is two broadcasts, and taking it keeps the pair record's loads
-            // inside the pair branch (config C3: 0.332 ms with the second look, 0.339 ms without)
-            if (!SPEC && !CT) { lk = row16(ls_off + (unsigned)(k + 1) * 32u + 16u); break; }
         }
         if (slow) { slow_mask |= 1ull << iz; continue; }
         const bool pair = (unsigned)k < pair_top;
@@ -430,7 +453,14 @@ __global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3
                 for (;;) {
                     AzEntry e;
                     int rec;
-                    r3_az_bracket(s_ad[sw], s_sw + sw, azt, az, e, rec);
+                    AzDesc d;
+                    {
+                        const unsigned da = ad_addr + (unsigned)sw * (unsigned)sizeof(AzDesc);
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(d.az_first), "=d"(d.az_inv_step) : "r"(da) : "memory");
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(d.az_off), "=r"(d.naz), "=r"(d.val_off), "=r"(d.ng) : "r"(da + 16u) : "memory");
+                    }
+                    r3_az_bracket(d, s_sw + sw, azt, az, e, rec);
                     if (sw == lower) { za = e; rec_a = rec; }
                     if (sw == top) { zb = e; rec_b = rec; break; }
                     sw = top;
@@ -467,17 +497,6 @@ __global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3
                         const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
                         qa4[fi] = ldg_vol(v + (ea.row + (unsigned)gi));
                         if (pair) qb4[fi] = ldg_vol(v + (eb.row + (unsigned)gi));
-                    }
-                    if (LAZY && R3_LAZY_PF && iz + 1 < p.nz) {
-                        const float r2n = (float)sub(p.levels[iz + 1].a2g2, mul(p.levels[iz + 1].twoag, cphi));
-                        const float rn = r2n * rsqrt_approx(r2n);
-                        const unsigned gn = (unsigned)min(max(__float2int_rd(fmaf(rn, u_inv_step, u_c0)), 1), u_ngm1);
-#pragma unroll
-                        for (int fi = 0; fi < NF; ++fi) {
-                            const float4* v = fi == 0 ? val0 : static_cast<const float4*>(p.vol.val[fi]);
-                            r3_prefetch(v + (za.row + gn));
-                            r3_prefetch(v + (zb.row + gn));
-                        }
                     }
                 }
 #endif
