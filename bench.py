@@ -714,7 +714,9 @@ def bench_extra_config(cid, args, torch, dev, steps=10):
     return {"workload": cfg["name"], "fields": fields, "grid": [nz, nx, ny], "ms_per_step": ms,
             "value": voxels / (ms * 1e-3), "unit": UNIT + (" (voxel-fields)" if nfield > 1 else ""),
             "roofline": {"achieved": balg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": balg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": int(balg)}}
+                         "frac": balg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": int(balg),
+                         "traffic": _static_traffic(cfg["name"]),
+                         "traffic_source": "profiles/traffic.json (static ncu capture, when one exists for this workload)"}}
 
 def bench_next_rows(args):
     """SURVEY §8(f) rows built beyond the gridding path, timed through their host-facing calls (host buffers,
