@@ -179,14 +179,12 @@ __device__ __forceinline__ float lds_f(unsigned addr) {
 // two entries they bracket (entries g-1 and g must both exist: 1 <= g <= naz-1; jittered tables put the arithmetic
 // guess off by one for a few lanes of almost every warp: one repair step in line), anything else through the
 // general routine.
-__device__ __forceinline__ void r3_az_bracket(const AzDesc& d, const SweepDesc* sw_desc, const double2* __restrict__ azt,
-                                              double az, AzEntry& e, int& rec) {
-    int g = __double2int_rd(mul(sub(az, d.az_first), d.az_inv_step)) + 1;
+__device__ __forceinline__ void r3_az_bracket_loaded(const AzDesc& d, int g, double2 lo, double hi, const SweepDesc* sw_desc,
+                                                     const double2* __restrict__ azt, double az, AzEntry& e, int& rec) {
+    // (g, lo = T[g-1], hi = T[g].x: requested by the caller when 1 <= g <= naz-1)
     bool done = false;
     if (g >= 1 && g < d.naz) {
         const double2* Tt = azt + d.az_off + (unsigned)(g - 1);
-        double2 lo = __ldg(Tt);
-        double hi = __ldg(&Tt[1].x);
         if (az < lo.x) {
             if (g >= 2) { --g; hi = lo.x; lo = __ldg(Tt - 1); }
         } else if (!(az < hi)) {
@@ -203,6 +201,19 @@ __device__ __forceinline__ void r3_az_bracket(const AzDesc& d, const SweepDesc* 
         const int4 r = az_bracket_general_v(sw_desc, azt, az);
         e.row = (unsigned)r.x; e.w = __int_as_float(r.y); rec = r.z;
     }
+}
+
+__device__ __forceinline__ void r3_az_bracket(const AzDesc& d, const SweepDesc* sw_desc, const double2* __restrict__ azt,
+                                              double az, AzEntry& e, int& rec) {
+    const int g = __double2int_rd(mul(sub(az, d.az_first), d.az_inv_step)) + 1;
+    double2 lo = make_double2(0.0, 0.0);
+    double hi = 0.0;
+    if (g >= 1 && g < d.naz) {
+        const double2* Tt = azt + d.az_off + (unsigned)(g - 1);
+        lo = __ldg(Tt);
+        hi = __ldg(&Tt[1].x);
+    }
+    r3_az_bracket_loaded(d, g, lo, hi, sw_desc, azt, az, e, rec);
 }
 
 // LAZY (volumes with more than 16 sweeps, e.g. the 64-sweep phased-array config C5): a [sweep] azimuth table per
@@ -228,6 +239,23 @@ __global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3
     AzEntry* s_az = reinterpret_cast<AzEntry*>(s_ad + ne);                 // [sweep][thread] (LAZY: [slot][thread])
     int* s_tag = reinterpret_cast<int*>(s_az + (size_t)nslot * T);         // LAZY only, [slot][thread]
     int* s_iaz = s_tag + (LAZY ? (size_t)nslot * T : 0);                   // EMIT only, [sweep or slot][thread]
+    // the column and its coordinates first: the two loads are in flight while the descriptors are staged
+    const long long ncol = p.grid.ncol;
+    long long col;
+    bool in_grid;
+    {
+        const int pyl = p.grid.py_log2;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = T >> 5;
+        const int wy = nwarp >= 4 ? 4 : nwarp;
+        const int ly = lane & ((1 << pyl) - 1), lx = lane >> pyl;
+        const int by = blockIdx.x % p.grid.tiles_y, bx = blockIdx.x / p.grid.tiles_y;
+        const int iy = ((by * wy + (warp % wy)) << pyl) + ly;
+        const int ix = (bx * (nwarp / wy) + (warp / wy)) * (32 >> pyl) + lx;
+        in_grid = ix < p.grid.nx && iy < p.grid.ny;
+        col = in_grid ? (long long)ix * p.grid.ny + iy : 0;
+    }
+    double x = p.grid.gx[col], y = p.grid.gy[col];
+
     stage_sweeps(s_sw, p.vol.sweeps, ne);
     stage_pairs(s_pr, p.pairs, ne - 1, p.twoa);
     {
@@ -244,44 +272,54 @@ __global__ void __launch_bounds__(256, LAZY ? R3_LAZY_MINB : R3_MINB) cappi3d_r3
             s_ad[i] = a;
         }
     }
-    __syncthreads();
-
-    const long long ncol = p.grid.ncol;
-    long long col;
-    {
-        const int pyl = p.grid.py_log2;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = T >> 5;
-        const int wy = nwarp >= 4 ? 4 : nwarp;
-        const int ly = lane & ((1 << pyl) - 1), lx = lane >> pyl;
-        const int by = blockIdx.x % p.grid.tiles_y, bx = blockIdx.x / p.grid.tiles_y;
-        const int iy = ((by * wy + (warp % wy)) << pyl) + ly;
-        const int ix = (bx * (nwarp / wy) + (warp / wy)) * (32 >> pyl) + lx;
-        if (ix >= p.grid.nx || iy >= p.grid.ny) return;
-        col = (long long)ix * p.grid.ny + iy;
-    }
-
-    double x = p.grid.gx[col], y = p.grid.gy[col];
+    // column invariants (RadarGridC.pyx:142-146,158): nothing here reads the staged tables, so it runs ahead of
+    // the barrier
     if (p.grid.shift) { x = sub(x, p.grid.radar_x); y = sub(y, p.grid.radar_y); }
-    // column invariants (RadarGridC.pyx:142-146,158)
     const double s = sqrt_rn(add(mul(x, x), mul(y, y)));
-    if (P.nonfinite && !(s < __longlong_as_double(0x7ff0000000000000LL))) *P.nonfinite = 1;
     const double cphi = cos_small(div(s, p.Re));
+    const double az = azimuth_from_xy(x, y);
+    __syncthreads();
+    if (!in_grid) return;
+    if (P.nonfinite && !(s < __longlong_as_double(0x7ff0000000000000LL))) *P.nonfinite = 1;
+
     AzEntry* my_az = s_az + threadIdx.x;
     int* my_iaz = s_iaz + threadIdx.x;
     int* my_tag = s_tag + threadIdx.x;
-    const double az = azimuth_from_xy(x, y);
     const double2* __restrict__ azt = P.r2.az_t;
     if (LAZY) {
         my_tag[0] = -1; my_tag[T] = -1;
     } else {
-        // the column's azimuth bracket of every sweep
+        // the column's azimuth bracket of every sweep, three sweeps at a time: the guesses of a group and the table
+        // entries they point at are requested together (one L2 round trip per group instead of one per sweep)
 #pragma unroll 1
-        for (int sw = 0; sw < ne; ++sw) {
-            AzEntry e;
-            int rec;
-            r3_az_bracket(s_ad[sw], s_sw + sw, azt, az, e, rec);
-            my_az[(size_t)sw * T] = e;
-            if (EMIT) my_iaz[(size_t)sw * T] = rec;
+        for (int s0 = 0; s0 < ne; s0 += 3) {
+            AzDesc d[3];
+            int g[3];
+            double2 lo[3];
+            double hi[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                d[j] = s_ad[min(s0 + j, ne - 1)];
+                g[j] = __double2int_rd(mul(sub(az, d[j].az_first), d[j].az_inv_step)) + 1;
+                lo[j] = make_double2(0.0, 0.0);
+                hi[j] = 0.0;
+                if (g[j] >= 1 && g[j] < d[j].naz) {
+                    const double2* Tt = azt + d[j].az_off + (unsigned)(g[j] - 1);
+                    lo[j] = __ldg(Tt);
+                    hi[j] = __ldg(&Tt[1].x);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int sw = s0 + j;
+                if (sw < ne) {
+                    AzEntry e;
+                    int rec;
+                    r3_az_bracket_loaded(d[j], g[j], lo[j], hi[j], s_sw + sw, azt, az, e, rec);
+                    my_az[(size_t)sw * T] = e;
+                    if (EMIT) my_iaz[(size_t)sw * T] = rec;
+                }
+            }
         }
     }
     // LAZY: the brackets of sweeps az_k and min(az_k + 1, ne - 1), az_k = -2: none yet
