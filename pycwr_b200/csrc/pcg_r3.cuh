@@ -18,9 +18,17 @@
 //   * azimuth table [sweep][thread] (conflict-free), interior azimuth brackets verified in line with one repair
 //     step, quads resolved against missing data in RANGE as well at pack time (pack_quads_kernel): a quad is either
 //     all-fill or fill-free, so only the elevation lerp tests for fill.
+//   * per-column prologue (22 % of the samples of the first v8 captures): the grid coordinates are requested before
+//     the descriptors are staged, sqrt / cos / atan2 run ahead of the block barrier, and the azimuth brackets are
+//     resolved three sweeps at a time (the guesses of a group and the table entries they point at are requested
+//     together: three L2 round trips per column instead of nine).
+//   * volumes with more than 16 sweeps (LAZY): the azimuth brackets of the column's CURRENT sweep pair live in
+//     registers and are computed when the column moves; confirm / walk form one block with a warp barrier behind
+//     it; voxels beyond the last gate are filled in line.  Config C5: 1.08 ms (pcg_r2.cuh) -> 0.60 ms.
 // Measured and rejected on B200: carrying the gate band and the azimuth-lerped samples from level
 // to level (63 % of the voxels keep both) — fewer L1 wavefronts, but nearly every warp has a lane that left its
-// band, so the warp walks both paths and ends up slower.
+// band, so the warp walks both paths and ends up slower; prefetching the next level's quads (LAZY, C5: 0.747 ms
+// against 0.715 ms); five or nine azimuth brackets per group instead of three (C3: 0.3295 / 0.3646 ms against 0.3277).
 #pragma once
 #include "pcg_r2.cuh"
 
