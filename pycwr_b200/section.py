@@ -274,7 +274,7 @@ def extract_section_lonlat(prd, start_lonlat, end_lonlat, field_name="dBZ", inte
     return ds
 
 
-def extract_rhi(prd, azimuth, field_name="dBZ", range_mode=None):
+def extract_rhi(prd, azimuth=None, field_name="dBZ", range_mode=None):
     """The ppi branch of ``PRD.extract_rhi``: an RHI-style cut along one azimuth."""
     if azimuth is None:
         raise ValueError("azimuth is required when extracting an RHI from a ppi volume.")
