@@ -117,3 +117,22 @@ def test_product_path_has_no_oracle_or_cpu_fallback():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"import\s+oracle|from\s+oracle|oracle/|oracle\.|libgrid_oracle|_ref/|build_ref", text), f
                 assert "/root/reference" not in text, f
+
+
+def test_committed_traffic_captures_name_real_workloads():
+    """`roofline.traffic` of the bench line is read from profiles/traffic.json by workload name: every key must be a
+    workload `synth` can build (or a kernel name kept from round 1), and the headline workloads must have a capture
+    whose DRAM bytes are read + write."""
+    import json
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    table = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+    src = open(os.path.join(root, "pycwr_b200", "synth.py")).read()
+    names = set(re.findall(r'"name": "(C[0-9][A-Za-z0-9_]+)"', src)) | {"C4_network_32r_3000x3000x30"}
+    for key, rec in table.items():
+        assert key in names or key.startswith("cappi3d_"), key
+        assert rec["bytes"] == rec["read"] + rec["write"]
+        assert os.path.basename(rec["report"]) == rec["report"] and rec["report"].endswith(".ncu-rep")
+    for must in ("C3_3D_lonlat_1201x1201x40", "C4_network_32r_3000x3000x30", "C5_PA_1001x1001x60"):
+        assert must in table, must
