@@ -156,3 +156,24 @@ def test_oracle_equals_compiled_reference_random(ref_module):
                               O.get_CR_xy(va, vr, fe, vv, h, gx, gy, FILL))
         assert np.array_equal(R.ppi_to_grid(va[1], vr[1], fe[1], vv[1], h, gx, gy, FILL, None, "nearest_gate"),
                               O.ppi_to_grid(va[1], vr[1], fe[1], vv[1], h, gx, gy, FILL, None, "nearest_gate"))
+
+
+def test_oracle_equals_compiled_reference_many_sweeps(ref_module):
+    """The many-sweep regime (phased-array scans, BASELINE config C5: sweeps 0.9 degrees apart up to 57.6 degrees,
+    30 m gates, levels every 250 m, targets beyond the last gate): the oracle is the checker of the GPU kernels that
+    serve volumes with more than 16 sweeps, so it is pinned to the compiled reference there as well."""
+    if ref_module is None:
+        pytest.skip("compiled reference (oracle/_ref) not present on this machine")
+    R = ref_module
+    for seed, ne in ((7, 24), (8, 64)):
+        vol = synth.make_volume(300 + seed, elevations=np.linspace(0.9, 0.9 * ne, ne), naz=90 + seed, ngate=400,
+                                gate_m=30.0)
+        va, vr, fe, vv, h = synth.vol_tuple(vol)
+        rng = np.random.default_rng(seed)
+        gx, gy = rng.uniform(-13e3, 13e3, (31, 29)), rng.uniform(-13e3, 13e3, (31, 29))   # some beyond 12 km
+        lv = np.arange(1, 41) * 250.0
+        for b in BLINDS:
+            assert np.array_equal(R.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, b),
+                                  O.get_CAPPI_3d(va, vr, fe, vv, h, gx, gy, lv, FILL, None, b)), (ne, b)
+        assert np.array_equal(R.get_CR_xy(va, vr, fe, vv, h, gx, gy, FILL),
+                              O.get_CR_xy(va, vr, fe, vv, h, gx, gy, FILL)), ne
